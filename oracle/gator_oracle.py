@@ -1,0 +1,442 @@
+"""TEST INFRASTRUCTURE ONLY - CPU restatement of the reference's pose->mesh forward.
+
+A plain functional restatement (torch CPU ops, fp32 or fp64) of the reference algorithm, written
+from the reference sources so the checker can travel to the GPU box, where /root/reference does
+not exist.  It is pinned against the real reference by ``tests/golden/*.npz`` (produced by
+``tests/golden/make_golden.py`` from the unmodified reference modules) - see
+``tests/test_oracle_golden.py``.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import this module; the product (``gator_b200/``)
+never does.
+
+Every function cites the reference file:line it follows (paths relative to the reference root).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Sequence
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+NO_VIA = 510
+
+
+# ----------------------------------------------------------------------------------------------
+# init-time constants (reference constructors)
+# ----------------------------------------------------------------------------------------------
+def build_adj(joint_num: int, skeleton, flip_pairs) -> np.ndarray:
+    """lib/graph_utils.py:60-69  skeleton U flip_pairs U I."""
+    a = np.zeros((joint_num, joint_num))
+    for (i, j) in skeleton:
+        a[i, j] = 1
+        a[j, i] = 1
+    for (i, j) in flip_pairs:
+        a[i, j] = 1
+        a[j, i] = 1
+    return a + np.eye(joint_num)
+
+
+def gat_graph_adj(joint_num: int, skeleton, flip_pairs) -> torch.Tensor:
+    """lib/models/GAT.py:57-65: dense adjacency with the hard-coded H36M flip edges removed
+    (applied to both joint sets)."""
+    g = torch.from_numpy(build_adj(joint_num, skeleton, flip_pairs).astype(np.float32)).clone()
+    for (i, j) in ((1, 4), (2, 5), (3, 6), (11, 14), (12, 15), (13, 16)):
+        g[i, j] = 0
+        g[j, i] = 0
+    return g
+
+
+def _all_edges(path, i, j):
+    """lib/models/backbones/modules.py:6-11."""
+    k = int(path[i][j])
+    if k == NO_VIA:
+        return []
+    return _all_edges(path, i, k) + [k] + _all_edges(path, k, j)
+
+
+def gen_edg_input(max_dist: int, path: np.ndarray, edge_feat: torch.Tensor) -> torch.Tensor:
+    """lib/models/backbones/modules.py:13-29."""
+    n = path.shape[0]
+    out = torch.zeros(n, n, max_dist)
+    for i in range(n):
+        for j in range(n):
+            if i == j or path[i][j] == NO_VIA:
+                continue
+            p = [i] + _all_edges(path, i, j) + [j]
+            for k in range(len(p) - 1):
+                out[i, j, k] = edge_feat[p[k], p[k + 1]]
+    return out
+
+
+def gat_constants(joint_num: int, graph_adj: torch.Tensor, J_regressor: torch.Tensor,
+                  mean_vertices: np.ndarray, shortest: np.ndarray, path: np.ndarray) -> Dict:
+    """lib/models/GAT.py:74-112 (template joints, pelvis/neck for J=19, edge lengths, path tensor)."""
+    init_vertices = torch.from_numpy(mean_vertices).unsqueeze(0)
+    tj = torch.matmul(J_regressor[None, :, :], init_vertices).squeeze(0)
+    if joint_num == 19:
+        pelvis = ((tj[11, :] + tj[12, :]) * 0.5).reshape(1, -1)
+        neck = ((tj[5, :] + tj[6, :]) * 0.5).reshape(1, -1)
+        tj = torch.cat((tj, pelvis, neck), dim=0)
+    edg_d = torch.zeros(joint_num, joint_num)
+    for i in range(joint_num):
+        for j in range(i + 1, joint_num):
+            if graph_adj[i][j] == 1:
+                edg_d[i][j] = math.sqrt(((tj[i] - tj[j]) ** 2).sum(0))
+    max_dist = int(np.amax(shortest))
+    edge_input = gen_edg_input(max_dist, path, edg_d)
+    return {'J': joint_num, 'graph_adj': graph_adj, 'init_vertices': init_vertices,
+            'edge_input': edge_input, 'spatial_pos': torch.from_numpy(shortest).long()}
+
+
+def verts_joints_relation(joints: np.ndarray, vertices: np.ndarray) -> np.ndarray:
+    """lib/graph_utils.py:71-89: index of the nearest joint per vertex (argmin: first minimum)."""
+    out = np.zeros(vertices.shape[0], np.int64)
+    for idx, v in enumerate(vertices):
+        d = ((v - joints) ** 2).sum(1)
+        out[idx] = int(np.argmin(d))
+    return out
+
+
+def mdr_constants(mean_vertices: np.ndarray, regressor_h36m: np.ndarray, D) -> Dict:
+    """lib/models/MDR.py:77-90.  D = [D0 (1723x6890), D1 (431x1723)] scipy sparse."""
+    v0 = torch.from_numpy(mean_vertices)
+    v1 = mesh_spmm(D[0], v0)
+    v2 = mesh_spmm(D[1], v1)
+    jt = torch.matmul(torch.from_numpy(regressor_h36m.astype(np.float32)), v0)
+    vj = verts_joints_relation(jt.numpy(), v2.numpy())
+    return {'init_vertices': v2, 'init_vertices_6890': v0, 'vj_relation': vj}
+
+
+# ----------------------------------------------------------------------------------------------
+# Mesh re-sampling
+# ----------------------------------------------------------------------------------------------
+def mesh_spmm(M, x: torch.Tensor) -> torch.Tensor:
+    """lib/models/backbones/graph_layers.py:105-124 / mesh.py:9-26: torch sparse COO (float32) @ dense."""
+    import scipy.sparse
+    m = scipy.sparse.coo_matrix(M)
+    idx = torch.from_numpy(np.array([m.row, m.col])).long()
+    val = torch.from_numpy(m.data.astype(np.float32)).to(x.dtype)
+    sp = torch.sparse_coo_tensor(idx, val, m.shape)
+    return torch.matmul(sp, x)
+
+
+def mesh_downsample(D, x: torch.Tensor, n1=0, n2=1) -> torch.Tensor:
+    """lib/models/backbones/mesh.py:93-108."""
+    if x.ndimension() < 3:
+        for i in range(n1, n2):
+            x = mesh_spmm(D[i], x)
+        return x
+    out = []
+    for b in range(x.shape[0]):
+        y = x[b]
+        for i in range(n1, n2):
+            y = mesh_spmm(D[i], y)
+        out.append(y)
+    return torch.stack(out, 0)
+
+
+def mesh_upsample(U, x: torch.Tensor, n1=1, n2=0) -> torch.Tensor:
+    """lib/models/backbones/mesh.py:110-123."""
+    if x.ndimension() < 3:
+        for i in reversed(range(n2, n1)):
+            x = mesh_spmm(U[i], x)
+        return x
+    out = []
+    for b in range(x.shape[0]):
+        y = x[b]
+        for i in reversed(range(n2, n1)):
+            y = mesh_spmm(U[i], y)
+        out.append(y)
+    return torch.stack(out, 0)
+
+
+# ----------------------------------------------------------------------------------------------
+# GAT
+# ----------------------------------------------------------------------------------------------
+def hop_path_encoding(sd, p, c, num_heads=8):
+    """lib/models/backbones/modules.py:77-107."""
+    J = c['J']
+    dt = sd[p + 'W'].dtype
+    spatial_pos = c['spatial_pos']
+    ones = torch.ones_like(spatial_pos)
+    spatial = spatial_pos - ones
+    spatial = torch.where(spatial > 0, spatial, ones)
+    spatial = 1.0 / spatial.expand(num_heads, -1, -1)
+    spb = F.embedding(spatial_pos, sd[p + 'spatial_pos_encoder.weight']).permute(2, 0, 1)
+    e = c['edge_input'].to(dt).permute(2, 0, 1)
+    e = F.linear(e.reshape(-1, J * J), sd[p + 'edge_encoder.weight'], sd[p + 'edge_encoder.bias'])
+    e = e.reshape(-1, num_heads, J, J).permute(1, 2, 3, 0)
+    eb = torch.mul(sd[p + 'W'], e).sum(-1)
+    eb = torch.mul(eb, spatial.to(dt))
+    return spb + eb
+
+
+def gat_block(sd, p, c, x, bias, num_heads=8):
+    """lib/models/GAT.py:33-43 with Attention (modules.py:121-138), MGCN (:243-255),
+    X_Feat (:158-177) and MLP (:188-196)."""
+    B, N, C = x.shape
+    res = x
+    n = F.layer_norm(x, (C,), sd[p + 'norm1.weight'], sd[p + 'norm1.bias'], 1e-5)
+    # Attention
+    qkv = F.linear(n, sd[p + 'attn.qkv.weight'], sd[p + 'attn.qkv.bias'])
+    qkv = qkv.reshape(B, N, 3, num_heads, C // num_heads).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv[0], qkv[1], qkv[2]
+    attn = (q @ k.transpose(-2, -1)) * ((C // num_heads) ** -0.5)
+    attn = (attn + bias.expand(B, -1, -1, -1)).softmax(dim=-1)
+    a = (attn @ v).transpose(1, 2).reshape(B, N, C)
+    a = F.linear(a, sd[p + 'attn.proj.weight'], sd[p + 'attn.proj.bias'])
+    # MGCN
+    W, M = sd[p + 'gcn.W'], sd[p + 'gcn.M']
+    h0 = torch.matmul(n, W[0])
+    h1 = torch.matmul(n, W[1])
+    adj = c['graph_adj'].to(x.dtype) + sd[p + 'gcn.adj2']
+    adj = (adj.T + adj) / 2
+    E = torch.eye(adj.size(0), dtype=x.dtype)
+    g = torch.matmul(adj * E, M * h0) + torch.matmul(adj * (1 - E), M * h1) + sd[p + 'gcn.bias'].view(1, 1, -1)
+    s = a + g
+    # X_Feat
+    sp = c['spatial_pos']
+    feats = []
+    for k_, lin in ((1, 'x_feat.linears.0'), (2, 'x_feat.linears.1')):
+        nc = F.linear(s, sd[p + lin + '.weight'], sd[p + lin + '.bias'])
+        mask = (sp <= k_) if k_ == 1 else (sp == k_)
+        mask = mask.to(nc.dtype).expand(B, -1, -1)
+        feats.append(torch.bmm(mask, nc))
+    f = F.linear(torch.cat(feats, -1), sd[p + 'x_feat.linearback.weight'], sd[p + 'x_feat.linearback.bias'])
+    x = res + f
+    # MLP
+    n2 = F.layer_norm(x, (C,), sd[p + 'norm2.weight'], sd[p + 'norm2.bias'], 1e-5)
+    h = F.gelu(F.linear(n2, sd[p + 'mlp.fc1.weight'], sd[p + 'mlp.fc1.bias']))
+    return x + F.linear(h, sd[p + 'mlp.fc2.weight'], sd[p + 'mlp.fc2.bias'])
+
+
+def gat_forward(sd, c, pose2d, prefix='pose_lifter.', depth=6, trace=None):
+    """lib/models/GAT.py:133-152.  pose2d (B, 2J) or (B, J, 2) -> (x_out (B,3J), x (B,J,128))."""
+    J = c['J']
+    B = pose2d.shape[0]
+    p = prefix
+    x = pose2d.reshape(-1, J, 2).permute(0, 2, 1)
+    # GraphLinear (modules.py:49-50) -> GroupNorm(4,64) -> GELU -> GraphLinear (GAT.py:69-72)
+    x = torch.matmul(sd[p + 'GLinear.0.W'][None, :], x) + sd[p + 'GLinear.0.b'][None, :, None]
+    x = F.group_norm(x, 4, sd[p + 'GLinear.1.weight'], sd[p + 'GLinear.1.bias'], 1e-5)
+    x = F.gelu(x)
+    x = torch.matmul(sd[p + 'GLinear.3.W'][None, :], x) + sd[p + 'GLinear.3.b'][None, :, None]
+    x = x.permute(0, 2, 1)
+    x = x + F.embedding(torch.arange(1, J + 1), sd[p + 'pos_id_embed.weight'])
+    pos_num = sd[p + 'graph_adj'].long().sum(dim=1).view(-1)
+    x = x + F.embedding(pos_num, sd[p + 'pos_num_embed.weight'])
+    if trace is not None:
+        trace['gat_embed'] = x
+    bias = hop_path_encoding(sd, p + 'get_hop_path_encoding.', c)
+    if trace is not None:
+        trace['hop_path_bias'] = bias
+    for i in range(depth):
+        x = gat_block(sd, f'{p}blocks.{i}.', c, x, bias)
+        if trace is not None:
+            trace[f'gat_block{i}'] = x
+    C = x.shape[-1]
+    x = F.gelu(F.layer_norm(x, (C,), sd[p + 'norm.weight'], sd[p + 'norm.bias'], 1e-5))
+    x_out = F.linear(x.reshape(B, -1), sd[p + 'lifter.weight'], sd[p + 'lifter.bias'])
+    return x_out, x
+
+
+# ----------------------------------------------------------------------------------------------
+# MDR
+# ----------------------------------------------------------------------------------------------
+def _cross_block(sd, p, x, J, heads=2):
+    """lib/models/MDR.py:64-69 (CrossAttentionBlock) + :34-46 (CrossAttention) + timm Mlp."""
+    B, N, C = x.shape
+    V = N - J
+    y = F.layer_norm(x, (C,), sd[p + 'norm1.weight'], sd[p + 'norm1.bias'], 1e-5)
+    q = F.linear(y[:, :V], sd[p + 'attn.wq.weight']).reshape(B, V, heads, C // heads).permute(0, 2, 1, 3)
+    k = F.linear(y[:, -J:], sd[p + 'attn.wk.weight']).reshape(B, J, heads, C // heads).permute(0, 2, 1, 3)
+    v = F.linear(y[:, -J:], sd[p + 'attn.wv.weight']).reshape(B, J, heads, C // heads).permute(0, 2, 1, 3)
+    attn = ((q @ k.transpose(-2, -1)) * ((C // heads) ** -0.5)).softmax(dim=-1)
+    o = (attn @ v).transpose(1, 2).reshape(B, V, C)
+    o = F.linear(o, sd[p + 'attn.proj.weight'], sd[p + 'attn.proj.bias'])
+    x = x[:, :V] + o
+    n2 = F.layer_norm(x, (C,), sd[p + 'norm2.weight'], sd[p + 'norm2.bias'], 1e-5)
+    h = F.gelu(F.linear(n2, sd[p + 'mlp.fc1.weight'], sd[p + 'mlp.fc1.bias']))
+    return x + F.linear(h, sd[p + 'mlp.fc2.weight'], sd[p + 'mlp.fc2.bias'])
+
+
+def _custom_ln(sd, p, x, eps=1e-6):
+    """lib/models/vanilla_transformer_encoder.py:24-34: a_2 (x-mean)/(std_unbiased + eps) + b_2."""
+    mean = x.mean(-1, keepdim=True)
+    std = x.std(-1, keepdim=True)
+    return sd[p + 'a_2'] * (x - mean) / (std + eps) + sd[p + 'b_2']
+
+
+def _self_attn(sd, p, x, h=2):
+    """lib/models/vanilla_transformer_encoder.py:82-94 + :36-46."""
+    B, N, C = x.shape
+    dk = C // h
+    q, k, v = [F.linear(x, sd[f'{p}linears.{i}.weight'], sd[f'{p}linears.{i}.bias']).view(B, -1, h, dk).transpose(1, 2)
+               for i in range(3)]
+    scores = torch.matmul(q, k.transpose(-2, -1)) / math.sqrt(dk)
+    o = torch.matmul(F.softmax(scores, dim=-1), v)
+    o = o.transpose(1, 2).contiguous().view(B, -1, h * dk)
+    return F.linear(o, sd[p + 'linears.3.weight'], sd[p + 'linears.3.bias'])
+
+
+def mdr_forward(sd, c, x, alpha: bool, prefix='pose2mesh.', trace=None):
+    """lib/models/MDR.py:124-170.  x = pose_combine (B, J, 2+3+128) -> (B, 6890, 3) metres."""
+    p = prefix
+    B, J = x.shape[0], x.shape[1]
+    iv = sd[p + 'init_vertices']
+    V = iv.shape[0]
+    vj = torch.from_numpy(np.asarray(c['vj_relation'])).long()
+    verts = torch.cat([iv.unsqueeze(0).expand(B, -1, -1), x[:, vj, 2:5]], dim=2)
+    joint = F.linear(x, sd[p + 'get_joint_feature.weight'], sd[p + 'get_joint_feature.bias'])
+    verts = F.linear(verts, sd[p + 'get_verts_feature.weight'], sd[p + 'get_verts_feature.bias'])
+    joint = joint + F.embedding(torch.arange(1, J + 1), sd[p + 'pos_j_id_embed.weight'])
+    verts = verts + F.embedding(torch.arange(1, V + 1), sd[p + 'pos_v_id_embed.weight'])
+    if trace is not None:
+        trace['mdr_verts_embed'] = verts
+        trace['mdr_joint_embed'] = joint
+    for li, sfx in enumerate(('', '_1', '_2')):
+        fusion = torch.cat([verts, joint], dim=1)
+        verts = _cross_block(sd, f'{p}encoder{sfx}.', fusion, J)
+        if trace is not None:
+            trace[f'mdr_cross{li}'] = verts
+        verts = _custom_ln(sd, f'{p}norm{sfx}.', verts)
+        verts = verts + _self_attn(sd, f'{p}selfatt{sfx}.', verts)
+        if trace is not None:
+            trace[f'mdr_layer{li}'] = verts
+    ac = F.linear(verts, sd[p + 'motion_linear.weight'], sd[p + 'motion_linear.bias'])
+    mat_A, mat_C = ac[:, :, :20], ac[:, :, -3:]
+    mat_B = F.linear(verts, sd[p + 'bias_linear.weight'], sd[p + 'bias_linear.bias'])
+    if alpha:
+        mat_B = F.layer_norm(mat_B, (3,), sd[p + 'bias_norm.weight'], sd[p + 'bias_norm.bias'], 1e-5)
+    else:
+        mat_B = F.batch_norm(mat_B, sd[p + 'bias_norm.running_mean'], sd[p + 'bias_norm.running_var'],
+                             sd[p + 'bias_norm.weight'], sd[p + 'bias_norm.bias'], False, 0.1, 1e-5)
+    mat_B = F.gelu(mat_B)
+    mat_B = F.conv1d(mat_B, sd[p + 'bias_conv1d.weight'], sd[p + 'bias_conv1d.bias'], padding=1)
+    if alpha:
+        a = 1.1 ** F.linear(verts, sd[p + 'scale_linear.weight'], sd[p + 'scale_linear.bias'])
+    else:
+        a = 1
+    coarse = a * mat_A.softmax(dim=-1).bmm(mat_B) + mat_C
+    if trace is not None:
+        trace['mdr_coarse'] = coarse
+    out = F.conv1d(coarse, sd[p + 'upsample_conv.weight'], sd[p + 'upsample_conv.bias'], padding=1)
+    return out + sd[p + 'init_vertices_6890']
+
+
+def gator_forward(sd, gat_c, mdr_c, pose2d, alpha: bool, trace=None):
+    """lib/models/GATOR.py:16-22.  pose2d (B,J,2) -> (cam_mesh (B,6890,3) m, pose3d (B,J,3) mm)."""
+    J = gat_c['J']
+    pose3d, feat = gat_forward(sd, gat_c, pose2d.reshape(len(pose2d), -1), trace=trace)
+    pose3d = pose3d.reshape(-1, J, 3)
+    combine = torch.cat((pose2d, pose3d / 1000, feat), dim=2)
+    mesh = mdr_forward(sd, mdr_c, combine, alpha, trace=trace)
+    return mesh, pose3d
+
+
+def joint_regress(J_regressor: torch.Tensor, mesh: torch.Tensor) -> torch.Tensor:
+    """lib/core/base.py:221, demo/run.py:142: J_regressor[None] @ pred_mesh."""
+    return torch.matmul(J_regressor[None, :, :], mesh)
+
+
+# ----------------------------------------------------------------------------------------------
+# SMPL linear blend skinning
+# ----------------------------------------------------------------------------------------------
+def batch_rodrigues(aa: torch.Tensor) -> torch.Tensor:
+    """smplpytorch/pytorch/rodrigues_layer.py:41-52 + quat2mat :13-38 -> (N, 9)."""
+    angle = torch.norm(aa + 1e-8, p=2, dim=1).unsqueeze(-1)
+    axis = aa / angle
+    angle = angle * 0.5
+    quat = torch.cat([torch.cos(angle), torch.sin(angle) * axis], dim=1)
+    quat = quat / quat.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = quat[:, 0], quat[:, 1], quat[:, 2], quat[:, 3]
+    w2, x2, y2, z2 = w.pow(2), x.pow(2), y.pow(2), z.pow(2)
+    wx, wy, wz, xy, xz, yz = w * x, w * y, w * z, x * y, x * z, y * z
+    return torch.stack([w2 + x2 - y2 - z2, 2 * xy - 2 * wz, 2 * wy + 2 * xz,
+                        2 * wz + 2 * xy, w2 - x2 + y2 - z2, 2 * yz - 2 * wx,
+                        2 * xz - 2 * wy, 2 * wx + 2 * yz, w2 - x2 - y2 + z2], dim=1)
+
+
+def smpl_forward(buf: Dict[str, torch.Tensor], parents: Sequence[int], pose, betas=None, trans=None,
+                 center_idx=None):
+    """smplpytorch/pytorch/smpl_layer.py:65-158 (+ tensutils.py:6-48).  Returns (verts, jtr, aux)."""
+    B = pose.shape[0]
+    dt = pose.dtype
+    rot = torch.cat([batch_rodrigues(pose[:, 3 * j:3 * j + 3]) for j in range(24)], 1)   # tensutils.py:6-19
+    root_rot = rot[:, :9].view(B, 3, 3)
+    rot = rot[:, 9:]
+    pose_map = rot - torch.eye(3, dtype=dt).view(1, 9).repeat(B, 23)                    # tensutils.py:41-48
+    S, P = buf['th_shapedirs'].to(dt), buf['th_posedirs'].to(dt)
+    T, Jr, W = buf['th_v_template'].to(dt), buf['th_J_regressor'].to(dt), buf['th_weights'].to(dt)
+    if betas is None or bool(torch.norm(betas) == 0):
+        v_shaped = T + torch.matmul(S, buf['th_betas'].to(dt).transpose(1, 0)).permute(2, 0, 1)
+        th_j = torch.matmul(Jr, v_shaped).repeat(B, 1, 1)
+    else:
+        v_shaped = T + torch.matmul(S, betas.transpose(1, 0)).permute(2, 0, 1)
+        th_j = torch.matmul(Jr, v_shaped)
+    v_posed = v_shaped + torch.matmul(P, pose_map.transpose(0, 1)).permute(2, 0, 1)
+
+    def with_zeros(t):                                                                  # tensutils.py:22-29
+        pad = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=dt).view(1, 1, 4).repeat(B, 1, 1)
+        return torch.cat([t, pad], 1)
+    results = [with_zeros(torch.cat([root_rot, th_j[:, 0, :].view(B, 3, 1)], 2))]
+    for i in range(1, 24):
+        jr = rot[:, (i - 1) * 9:i * 9].contiguous().view(B, 3, 3)
+        rel = with_zeros(torch.cat([jr, (th_j[:, i, :] - th_j[:, parents[i], :]).view(B, 3, 1)], 2))
+        results.append(torch.matmul(results[parents[i]], rel))
+    res2 = torch.zeros((B, 4, 4, 24), dtype=dt)
+    for i in range(24):
+        jj = torch.cat([th_j[:, i], torch.zeros(B, 1, dtype=dt)], 1)
+        tmp = torch.bmm(results[i], jj.unsqueeze(2))
+        res2[:, :, :, i] = results[i] - torch.cat([torch.zeros(B, 4, 3, dtype=dt), tmp], 2)  # th_pack
+    th_T = torch.matmul(res2, W.transpose(0, 1))
+    rest_h = torch.cat([v_posed.transpose(2, 1), torch.ones((B, 1, v_posed.shape[1]), dtype=dt)], 1)
+    verts = (th_T * rest_h.unsqueeze(1)).sum(2).transpose(2, 1)[:, :, :3]
+    jtr = torch.stack(results, dim=1)[:, :, :3, 3]
+    if trans is None or bool(torch.norm(trans) == 0):
+        if center_idx is not None:
+            cj = jtr[:, center_idx].unsqueeze(1)
+            jtr = jtr - cj
+            verts = verts - cj
+    else:
+        jtr = jtr + trans.unsqueeze(1)
+        verts = verts + trans.unsqueeze(1)
+    return verts, jtr, {'v_posed': v_posed, 'th_j': th_j, 'rotmats': torch.cat([root_rot.reshape(B, 9), rot], 1)}
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation helpers restated for the drift metric (not on the hot path)
+# ----------------------------------------------------------------------------------------------
+H36M_EVAL_JOINTS = (1, 2, 3, 4, 5, 6, 8, 10, 11, 12, 13, 14, 15, 16)
+
+
+def rigid_align(A: np.ndarray, B: np.ndarray) -> np.ndarray:
+    """lib/coord_utils.py:127-149: similarity Procrustes of A onto B."""
+    mu_a, mu_b = A.mean(0), B.mean(0)
+    a0, b0 = A - mu_a, B - mu_b
+    H = a0.T @ b0
+    U, s, Vt = np.linalg.svd(H)
+    R = Vt.T @ U.T
+    if np.linalg.det(R) < 0:
+        s[-1] = -s[-1]
+        Vt[2] = -Vt[2]
+        R = Vt.T @ U.T
+    var_a = (a0 ** 2).sum() / len(A)
+    c = s.sum() / len(A) / var_a
+    t = mu_b - c * R @ mu_a
+    return (c * (R @ A.T)).T + t
+
+
+def mpjpe_pa(pred_mesh_m: np.ndarray, gt_mesh_m: np.ndarray, regressor_h36m: np.ndarray):
+    """MPJPE / PA-MPJPE in mm on the 14 H36M eval joints, root-aligned
+    (lib/core/base.py:219-221, data/Human36M/dataset.py:466-478)."""
+    mp, pa = [], []
+    for p, g in zip(pred_mesh_m, gt_mesh_m):
+        jp = regressor_h36m @ (p * 1000.0)
+        jg = regressor_h36m @ (g * 1000.0)
+        jp, jg = jp - jp[:1], jg - jg[:1]
+        jp, jg = jp[list(H36M_EVAL_JOINTS)], jg[list(H36M_EVAL_JOINTS)]
+        mp.append(np.sqrt(((jp - jg) ** 2).sum(1)).mean())
+        pa.append(np.sqrt(((rigid_align(jp, jg) - jg) ** 2).sum(1)).mean())
+    return float(np.mean(mp)), float(np.mean(pa))

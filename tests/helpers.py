@@ -1,0 +1,70 @@
+"""Shared test plumbing: golden fixtures, synthetic checkpoints, oracle constants (CPU only)."""
+from __future__ import annotations
+
+import functools
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), '..'))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from gator_b200 import synthetic          # noqa: E402
+from oracle import gator_oracle as orc    # noqa: E402
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+@functools.lru_cache(None)
+def golden(name: str):
+    return dict(np.load(os.path.join(GOLDEN, name + '.npz'), allow_pickle=False))
+
+
+@functools.lru_cache(None)
+def regressor(name: str) -> np.ndarray:
+    """The reference's shipped 17x6890 J-regressors (stored sparsely in fixtures.npz), as float32."""
+    fx = golden('fixtures')
+    a = np.zeros((17, synthetic.V_FULL), np.float64)
+    a[fx[f'J_regressor_{name}/row'], fx[f'J_regressor_{name}/col']] = fx[f'J_regressor_{name}/val']
+    return a.astype(np.float32)
+
+
+CONFIGS = {
+    # tag: (joint category, alpha, regressor name)
+    'h36m': ('human36', False, 'h36m'),
+    'coco': ('coco', True, 'coco'),
+}
+
+
+def key_spec(tag: str):
+    spec = []
+    for s in golden('gator')[f'{tag}/keys']:
+        k, shape, dt = str(s).split('|')
+        spec.append((k, tuple(int(x) for x in shape.split(',')) if shape else (), dt))
+    return spec
+
+
+@functools.lru_cache(None)
+def oracle_setup(tag: str):
+    """(state_dict of torch fp32 tensors, gat constants, mdr constants, alpha) for the oracle."""
+    category, alpha, regname = CONFIGS[tag]
+    J, skel, flip, _ = synthetic.joint_set(category)
+    mv = synthetic.mean_vertices()
+    shortest, path = synthetic.floyd_warshall(J, skel)
+    A, D, U = synthetic.mesh_sampling_matrices()
+    gadj = orc.gat_graph_adj(J, skel, flip)
+    gat_c = orc.gat_constants(J, gadj, torch.from_numpy(regressor(regname)), mv, shortest, path)
+    mdr_c = orc.mdr_constants(mv, regressor('h36m'), D)
+    sd = {k: torch.from_numpy(v) for k, v in synthetic.synth_state_dict(key_spec(tag)).items()}
+    sd['pose_lifter.graph_adj'] = gadj
+    sd['pose_lifter.init_vertices'] = gat_c['init_vertices']
+    sd['pose2mesh.init_vertices'] = mdr_c['init_vertices']
+    sd['pose2mesh.init_vertices_6890'] = mdr_c['init_vertices_6890']
+    return sd, gat_c, mdr_c, alpha
+
+
+def to_dtype(sd, dt):
+    return {k: (v.to(dt) if v.is_floating_point() else v) for k, v in sd.items()}
