@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""Headline benchmark: meshes/sec of the GATOR pose->mesh forward (BASELINE.json configs[3]: full
+GAT+MDR+upsample forward, synthetic COCO poses, J=19, alpha=True, batch 4096 per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--precision fp32|bf16]
+
+One JSON line on stdout (rank 0).  `value` = whole-job meshes/s with inputs resident in HBM;
+`e2e` = the same through the nn.Module API with pinned-host inputs and the mesh copied back to the host
+inside the timed region; `roofline` = the dominant kernel (MDR 431x431 self-attention) timed on its own
+with CUDA events; `cpu_baseline` = the CPU oracle (port of the reference forward, same torch ops) timed
+on the box's host cores on a bounded sample.  --impl reference times that CPU path as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, 'tests')):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = 'meshes_per_sec'
+UNIT = 'meshes/s'
+TAG = 'coco'                      # J=19, alpha=True (3dpw configuration of demo/run.py)
+FLOP_PER_MESH = 418.1e6           # GATOR.forward J=19, dense, 2*MAC
+SA_FLOP_PER_SAMPLE = 2 * 2 * 2 * 431 * 431 * 32   # self-attention core: 2 heads x (QK^T + PV) x 2*MAC
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+            p = json.load(f)
+        return {'hbm_gbs': float(p['hbm_gbs']), 'bf16_tflops': float(p['bf16_tflops']),
+                'bf16_tflops_sustained': float(p.get('bf16_tflops_sustained', p['bf16_tflops'])), 'src': 'measured'}
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'src': 'fallback'}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax = float(r[2])
+                for name, col in (('hw_slowdown', 5), ('hw_thermal_slowdown', 6), ('sw_thermal_slowdown', 7), ('sw_power_cap', 8)):
+                    if r[col].lower().startswith('active'):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def make_inputs(batch, seed=2):
+    import numpy as np
+    from helpers import golden, synthetic
+    base = golden('fixtures')['demo_pose19']
+    return synthetic.coco_poses2d(base, batch, seed=seed)
+
+
+def cpu_forward_rate(sample_batch, min_seconds, threads):
+    """Reference arm / cpu_baseline: the CPU oracle (oracle/gator_oracle.py, same ATen ops as the reference's
+    forward) on `threads` host threads, batches of `sample_batch` until `min_seconds` elapsed."""
+    import torch
+    from helpers import oracle_setup, orc
+    torch.set_num_threads(threads)
+    sd, gc, mc, alpha = oracle_setup(TAG)
+    x = torch.from_numpy(make_inputs(sample_batch))
+    with torch.no_grad():
+        orc.gator_forward(sd, gc, mc, x, alpha)            # warm-up
+        t0, n = time.perf_counter(), 0
+        times = []
+        while time.perf_counter() - t0 < min_seconds or n < 2:
+            t1 = time.perf_counter()
+            orc.gator_forward(sd, gc, mc, x, alpha)
+            times.append(time.perf_counter() - t1)
+            n += 1
+    times.sort()
+    med = times[len(times) // 2]
+    return sample_batch / med, med, n
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    sample = 64
+    # one "step" = one forward over a 64-sample slice of the 4096-sample workload (bounded sample)
+    from helpers import oracle_setup, orc
+    torch.set_num_threads(threads)
+    sd, gc, mc, alpha = oracle_setup(TAG)
+    x = torch.from_numpy(make_inputs(sample))
+    with torch.no_grad():
+        for _ in range(max(args.warmup, 1)):
+            orc.gator_forward(sd, gc, mc, x, alpha)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            orc.gator_forward(sd, gc, mc, x, alpha)
+        dt = (time.perf_counter() - t0) / args.steps
+    v = sample / dt
+    line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
+            'config': {'workload': f'GATOR.forward J=19 alpha=True, batch {args.batch}/GPU (BASELINE configs[3])',
+                       'note': 'CPU reference forward (oracle port, same ATen ops); each step = a 64-sample slice'},
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                             'sample': f'{args.steps} forwards of batch {sample}'},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    from gator_b200 import _lib
+    from gator_b200.dist import shard_range
+    from helpers import build_b200_gator
+    L = _lib.lib()
+    model = build_b200_gator(TAG, dev).set_precision(args.precision)
+    J = model.num_joint
+    B = args.batch                                         # per GPU (weak scaling)
+    lo, hi = shard_range(B * world, world, rank)
+    x_host = torch.from_numpy(make_inputs(B * world)[lo:hi]).pin_memory()
+    x = x_host.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ----
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            model(x)
+        barrier()
+        L.gator_launch_count(1)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        evs = []
+        t_wall = time.perf_counter()
+        for _ in range(args.steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            mesh, p3 = model(x)
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        t_wall = time.perf_counter() - t_wall
+        launches = L.gator_launch_count(1)
+        clocks = sampler.stop() if rank == 0 else None
+    step_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    t = torch.tensor([step_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    step_ms = t.item()
+    value = B * world / (step_ms * 1e-3)
+
+    # ---- end to end: pinned host input -> H2D -> forward -> mesh + pose3d D2H ----
+    mesh_host = torch.empty((B, 6890, 3), dtype=torch.float32).pin_memory()
+    p3_host = torch.empty((B, J, 3), dtype=torch.float32).pin_memory()
+    with torch.no_grad():
+        def e2e_step():
+            xd = x_host.to(dev, non_blocking=True)
+            m, p = model(xd)
+            mesh_host.copy_(m, non_blocking=True)
+            p3_host.copy_(p, non_blocking=True)
+        e2e_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        barrier()
+    e2e_ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([e2e_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item()
+
+    line = None
+    if rank == 0:
+        peaks = measured_peaks()
+        # ---- dominant kernel alone: MDR self-attention core ----
+        nb = 148
+        qkv = torch.randn(nb * 431, 192, device=dev)
+        out = torch.empty(nb * 431, 64, device=dev)
+        s = _lib.stream_ptr()
+        for _ in range(3):
+            L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, 0, s)
+        torch.cuda.synchronize()
+        reps = 20
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, 0, s)
+        e1.record()
+        torch.cuda.synchronize()
+        k_ms = e0.elapsed_time(e1) / reps
+        achieved = SA_FLOP_PER_SAMPLE * nb / (k_ms * 1e-3) / 1e12
+        roofline = {'kernel': 'mdr_self_attn_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'],
+                    'unit': 'TFLOP/s', 'frac': achieved / peaks['bf16_tflops'], 'traffic': None,
+                    'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)', 'launch_ms': k_ms,
+                    'note': 'fp32 FFMA kernel (parity path); flops = 2 heads x (QK^T + PV) x 148 samples per launch'}
+        threads = os.cpu_count() or 1
+        cpu_v, cpu_med, cpu_n = cpu_forward_rate(64, 12.0, threads)
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': args.precision, 'data': 'synthetic',
+                'config': {'workload': f'GATOR.forward J=19 alpha=True, batch {B}/GPU (BASELINE configs[3]); '
+                                       'random-init weights, synthetic SMPL-shaped template/bases',
+                           'global_batch': B * world, 'l2': 'flushed (256 MiB memset) before every timed step',
+                           'parallelism': f'batch-sharded x{world}, no collective on the data path'},
+                'clocks': clocks,
+                'e2e': {'value': B * world / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
+                        'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': int((mesh_host.numel() + p3_host.numel()) * 4)},
+                'gpu_launches': int(launches),
+                'tflops_effective': FLOP_PER_MESH * value / 1e12,
+                'wall_s_timed_region': t_wall,
+                'roofline': roofline,
+                'cpu_baseline': {'value': cpu_v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                                 'sample': f'{cpu_n} forwards of batch 64 (median {cpu_med * 1e3:.0f} ms), oracle port of the reference forward'}}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch', type=int, default=4096, help='samples per GPU')
+    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

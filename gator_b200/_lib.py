@@ -1,0 +1,142 @@
+"""ctypes binding of libgator_b200.so (the C ABI declared in include/gator_b200.h).
+
+No fallback: if the shared library is missing or a call fails, a RuntimeError is raised - the product
+never routes through a CPU or PyTorch-eager implementation.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, '_C', 'libgator_b200.so')
+
+PREC_FP32, PREC_BF16 = 0, 1
+
+c_float_p = C.POINTER(C.c_float)
+c_int_p = C.POINTER(C.c_int32)
+
+
+class GatArgs(C.Structure):
+    _fields_ = [('num_joint', C.c_int32), ('depth', C.c_int32), ('batch', C.c_int32), ('chunk', C.c_int32),
+                ('precision', C.c_int32), ('reserved', C.c_int32),
+                ('weights', C.POINTER(C.c_void_p)), ('pose2d', C.c_void_p), ('pose3d', C.c_void_p),
+                ('feat', C.c_void_p), ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
+
+
+class MdrArgs(C.Structure):
+    _fields_ = [('num_joint', C.c_int32), ('batch', C.c_int32), ('chunk', C.c_int32), ('alpha', C.c_int32),
+                ('precision', C.c_int32), ('reserved', C.c_int32),
+                ('weights', C.POINTER(C.c_void_p)), ('pose2d', C.c_void_p), ('pose3d', C.c_void_p),
+                ('feat', C.c_void_p), ('mesh', C.c_void_p), ('coarse', C.c_void_p),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
+
+
+class SmplArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('center_idx', C.c_int32), ('has_betas', C.c_int32), ('has_trans', C.c_int32),
+                ('check_zero_norm', C.c_int32), ('weights_per_vertex', C.c_int32), ('precision', C.c_int32),
+                ('reserved', C.c_int32),
+                ('parents', C.c_void_p), ('j_template', C.c_void_p), ('j_shapedirs', C.c_void_p),
+                ('default_betas', C.c_void_p), ('blend_w', C.c_void_p), ('v_template', C.c_void_p),
+                ('skin_idx', C.c_void_p), ('skin_w', C.c_void_p), ('pose', C.c_void_p), ('betas', C.c_void_p),
+                ('trans', C.c_void_p), ('verts', C.c_void_p), ('jtr', C.c_void_p),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
+
+
+class CsrArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('rows', C.c_int32), ('cols', C.c_int32), ('feat', C.c_int32),
+                ('scale', C.c_float), ('reserved', C.c_int32),
+                ('rowptr', C.c_void_p), ('colidx', C.c_void_p), ('values', C.c_void_p),
+                ('x', C.c_void_p), ('y', C.c_void_p)]
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32),
+                ('lda', C.c_int32), ('ldw', C.c_int32), ('ldc', C.c_int32), ('ldr', C.c_int32),
+                ('act', C.c_int32), ('bias_period', C.c_int32), ('precision', C.c_int32),
+                ('A', C.c_void_p), ('W', C.c_void_p), ('bias', C.c_void_p), ('bias_rows', C.c_void_p),
+                ('R', C.c_void_p), ('C', C.c_void_p)]
+
+
+_STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs]
+EXPORTS = ['gator_abi_version', 'gator_last_error', 'gator_abi_sizeof', 'gator_launch_count',
+           'gator_mdr_self_attention',
+           'gator_gat_slot_name', 'gator_gat_workspace_bytes', 'gator_gat_forward',
+           'gator_mdr_slot_name', 'gator_mdr_workspace_bytes', 'gator_mdr_forward',
+           'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_gemm']
+
+_lock = threading.Lock()
+_lib = None
+
+
+def lib():
+    """The loaded library; raises RuntimeError (never falls back) when it is absent or inconsistent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'gator_b200: CUDA library {LIB_PATH} is missing - run `python -m gator_b200.build` '
+                '(or __graft_entry__.build()); there is no CPU fallback.')
+        L = C.CDLL(LIB_PATH)
+        L.gator_abi_version.restype = C.c_int
+        L.gator_last_error.restype = C.c_char_p
+        L.gator_abi_sizeof.restype = C.c_size_t
+        L.gator_abi_sizeof.argtypes = [C.c_int]
+        for name in ('gator_gat_slot_name', 'gator_mdr_slot_name'):
+            getattr(L, name).restype = C.c_char_p
+            getattr(L, name).argtypes = [C.c_int]
+        for name in ('gator_gat_workspace_bytes', 'gator_mdr_workspace_bytes'):
+            getattr(L, name).restype = C.c_size_t
+            getattr(L, name).argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.gator_smpl_workspace_bytes.restype = C.c_size_t
+        L.gator_smpl_workspace_bytes.argtypes = [C.c_int32]
+        for name, st in (('gator_gat_forward', GatArgs), ('gator_mdr_forward', MdrArgs),
+                         ('gator_smpl_forward', SmplArgs), ('gator_csr_spmm', CsrArgs), ('gator_gemm', GemmArgs)):
+            getattr(L, name).restype = C.c_int
+            getattr(L, name).argtypes = [C.POINTER(st), C.c_void_p]
+        L.gator_launch_count.restype = C.c_longlong
+        L.gator_launch_count.argtypes = [C.c_int]
+        L.gator_mdr_self_attention.restype = C.c_int
+        L.gator_mdr_self_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        if L.gator_abi_version() != 1:
+            raise RuntimeError('gator_b200: ABI version mismatch between _lib.py and libgator_b200.so')
+        for i, st in enumerate(_STRUCTS):
+            if L.gator_abi_sizeof(i) != C.sizeof(st):
+                raise RuntimeError(f'gator_b200: struct {st.__name__} is {C.sizeof(st)} B in Python, '
+                                   f'{L.gator_abi_sizeof(i)} B in the library')
+        _lib = L
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        raise RuntimeError(f'{what} failed ({status}): {lib().gator_last_error().decode()}')
+
+
+def slot_names(kind: str):
+    """(global slot names, per-block/layer slot names) as exported by the library."""
+    fn = lib().gator_gat_slot_name if kind == 'gat' else lib().gator_mdr_slot_name
+    names, i = [], 0
+    while True:
+        s = fn(i)
+        if s is None:
+            break
+        names.append(s.decode())
+        i += 1
+    # the per-block names follow the global ones; the first block name is LN1_W / N1_W
+    split = names.index('LN1_W' if kind == 'gat' else 'N1_W')
+    return names[:split], names[split:]
+
+
+def ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def stream_ptr():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)

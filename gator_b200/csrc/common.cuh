@@ -1,0 +1,70 @@
+// Shared device/host helpers for the gator_b200 kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+
+#include "../../include/gator_b200.h"
+
+namespace gator {
+
+// thread-local error text behind gator_last_error()
+void set_error(const char* fmt, ...);
+int check_launch(const char* what);   // cudaGetLastError -> status
+
+#define GATOR_REQUIRE(cond, ...)                       \
+  do {                                                 \
+    if (!(cond)) {                                     \
+      ::gator::set_error(__VA_ARGS__);                 \
+      return GATOR_ERR_BAD_ARG;                        \
+    }                                                  \
+  } while (0)
+
+#define GATOR_TRY(expr)                                \
+  do {                                                 \
+    int _st = (expr);                                  \
+    if (_st != GATOR_OK) return _st;                   \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- epilogue descriptor shared by the GEMM launchers --------------------------------------
+struct Epilogue {
+  const float* bias = nullptr;        // (N)
+  const float* bias_rows = nullptr;   // (period, N) indexed by m % period
+  int bias_period = 0;
+  int act = 0;                        // 1 = GELU(erf)
+  const float* R = nullptr;           // residual (M, ldr); may alias C
+  int ldr = 0;
+  // conv3 scatter (upsample_conv): row m = (b, t), col n = o -> C[(b*N + o)*3 + t] + bias_rows[o*3+t]
+  int conv3 = 0;
+};
+
+// C = epi(A (M,K;lda) * W (N,K;ldw)^T).  fp32 FFMA.
+int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+             const Epilogue& epi, cudaStream_t stream);
+
+// LayerNorm over the last dim (C = 64 or 128).  mode 0: nn.LayerNorm (eps 1e-5, biased var);
+// mode 1: a*(x-mean)/(std_unbiased+1e-6)+b (vanilla_transformer_encoder.py:31-34).  gelu: apply after.
+int layernorm_rows(const float* x, float* y, const float* w, const float* b, int rows, int C, int mode,
+                   int gelu, cudaStream_t stream);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+#endif
+
+}  // namespace gator

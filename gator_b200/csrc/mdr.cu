@@ -1,0 +1,485 @@
+// MDR decoder forward (lib/models/MDR.py:124-170): vertex/joint embedding, 3 x (cross-attention block +
+// unbiased-std LayerNorm + 431x431 self-attention), MDR head, dense upsample conv + template.
+// fp32 parity path: dense products through gemm_f32; attention, head and embedding hand-fused here.
+#include "common.cuh"
+
+namespace gator {
+namespace {
+
+constexpr int E = 64;                 // MDR embed dim (MDR.py:74)
+constexpr int V = GATOR_V_COARSE;     // 431
+constexpr int VF = GATOR_V_FULL;      // 6890
+constexpr int DK = 32;                // head dim (2 heads)
+constexpr int MAXJ = 32;
+constexpr int HEADN = 28;
+constexpr int UPK = GATOR_UP_K;       // 1296
+
+// ---------------------------------------------------------------------------------------------
+// Embedding (MDR.py:127-137 with the concat of GATOR.py:19 folded in).  One CTA per sample.
+//   jf[b,j,:]  = W_j[:, :5] . [pose2d, pose3d/1000]      (the feat part is added by the GEMM that follows)
+//   x[b,v,:]   = VF_CONST[v,:] + W_v[:,3:6] . pose3d[b, vj[v]]/1000
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mdr_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ pose3d, const float* __restrict__ wpose,
+                 const float* __restrict__ vconst, const float* __restrict__ w3, const int* __restrict__ vj,
+                 float* __restrict__ jf, float* __restrict__ x, int J) {
+  __shared__ float p5[MAXJ][5];
+  __shared__ float sw3[E * 3];
+  __shared__ float swp[E * 5];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < J) {
+    p5[tid][0] = pose2d[((size_t)b * J + tid) * 2 + 0];
+    p5[tid][1] = pose2d[((size_t)b * J + tid) * 2 + 1];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) p5[tid][2 + t] = pose3d[((size_t)b * J + tid) * 3 + t] / 1000.0f;
+  }
+  for (int i = tid; i < E * 3; i += 256) sw3[i] = w3[i];
+  for (int i = tid; i < E * 5; i += 256) swp[i] = wpose[i];
+  __syncthreads();
+  for (int i = tid; i < J * E; i += 256) {
+    const int j = i / E, n = i - j * E;
+    float a = 0.f;
+#pragma unroll
+    for (int q = 0; q < 5; ++q) a = fmaf(swp[n * 5 + q], p5[j][q], a);
+    jf[((size_t)b * J + j) * E + n] = a;
+  }
+  float* xb = x + (size_t)b * V * E;
+  for (int i = tid; i < V * (E / 4); i += 256) {
+    const int v = i / (E / 4), n = (i - v * (E / 4)) * 4;
+    const int j = __ldg(vj + v);
+    const float px = p5[j][2], py = p5[j][3], pz = p5[j][4];
+    float4 c = __ldg(reinterpret_cast<const float4*>(vconst + (size_t)v * E + n));
+    float r[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float* w = sw3 + (n + u) * 3;
+      r[u] += fmaf(w[0], px, fmaf(w[1], py, w[2] * pz));
+    }
+    *reinterpret_cast<float4*>(xb + (size_t)v * E + n) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cross attention core (MDR.py:34-46): 431 vertex queries x J joint keys, 2 heads of 32.
+// One CTA per sample; K/V of the sample in shared memory; one thread per (head, vertex).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mdr_cross_attn_kernel(const float* __restrict__ q, const float* __restrict__ kv, float* __restrict__ out, int J) {
+  __shared__ __align__(16) float sk[MAXJ][E];
+  __shared__ __align__(16) float sv[MAXJ][E];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < J * 2 * E; i += 256) {
+    const int j = i / (2 * E), c = i - j * 2 * E;
+    const float val = kv[((size_t)b * J + j) * 2 * E + c];
+    if (c < E) sk[j][c] = val; else sv[j][c - E] = val;
+  }
+  __syncthreads();
+  const float scale = 0.17677669529663687f;   // 32 ** -0.5
+  for (int w = tid; w < 2 * V; w += 256) {
+    const int h = w / V, v = w - h * V;
+    const float* qr = q + ((size_t)b * V + v) * E + h * DK;
+    float qq[DK];
+#pragma unroll
+    for (int d = 0; d < DK; d += 4) {
+      float4 t = *reinterpret_cast<const float4*>(qr + d);
+      qq[d] = t.x; qq[d + 1] = t.y; qq[d + 2] = t.z; qq[d + 3] = t.w;
+    }
+    float s[MAXJ];
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      if (j < J) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < DK; ++d) a = fmaf(qq[d], sk[j][h * DK + d], a);
+        s[j] = a * scale;
+        m = fmaxf(m, s[j]);
+      }
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j)
+      if (j < J) { s[j] = expf(s[j] - m); l += s[j]; }
+    const float inv = 1.0f / l;
+    float o[DK];
+#pragma unroll
+    for (int d = 0; d < DK; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      if (j < J) {
+        const float p = s[j] * inv;
+#pragma unroll
+        for (int d = 0; d < DK; ++d) o[d] = fmaf(p, sv[j][h * DK + d], o[d]);
+      }
+    }
+    float* orow = out + ((size_t)b * V + v) * E + h * DK;
+#pragma unroll
+    for (int d = 0; d < DK; d += 4) *reinterpret_cast<float4*>(orow + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Self attention core (vanilla_transformer_encoder.py:36-46): softmax(q k^T / sqrt(32)) v over the 431
+// coarse vertices, 2 heads.  fp32 flash-style: one CTA per (sample, head) keeps that head's K and V
+// (2 x 432 x 32 fp32 = 108 KB) in shared memory; each thread owns QPT query rows and streams the keys in
+// chunks of 8 with an online softmax (exp2 domain), so the 431x431 score matrix never exists.
+// ---------------------------------------------------------------------------------------------
+constexpr int SA_THREADS = 224;
+constexpr int SA_QPT = 2;
+constexpr int SA_KC = 8;
+constexpr int SA_VPAD = 432;
+
+__global__ void __launch_bounds__(SA_THREADS)
+mdr_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
+  extern __shared__ __align__(16) float smem[];
+  float* sk = smem;                    // [432][32]
+  float* sv = smem + SA_VPAD * DK;     // [432][32]
+  const int b = blockIdx.x >> 1, h = blockIdx.x & 1, tid = threadIdx.x;
+  const float* base = qkv + (size_t)b * V * 3 * E;
+  for (int i = tid; i < SA_VPAD * (DK / 4); i += SA_THREADS) {
+    const int r = i / (DK / 4), c = (i - r * (DK / 4)) * 4;
+    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+    if (r < V) {
+      kk = *reinterpret_cast<const float4*>(base + (size_t)r * 3 * E + E + h * DK + c);
+      vv = *reinterpret_cast<const float4*>(base + (size_t)r * 3 * E + 2 * E + h * DK + c);
+    }
+    *reinterpret_cast<float4*>(sk + r * DK + c) = kk;
+    *reinterpret_cast<float4*>(sv + r * DK + c) = vv;
+  }
+  __syncthreads();
+  // 1/sqrt(32) * log2(e): scores live in the exp2 domain
+  const float qscale = 0.17677669529663687f * 1.4426950408889634f;
+  float qq[SA_QPT][DK], o[SA_QPT][DK], m[SA_QPT], l[SA_QPT];
+  int row[SA_QPT];
+#pragma unroll
+  for (int r = 0; r < SA_QPT; ++r) {
+    row[r] = tid + r * SA_THREADS;
+    const int rr = row[r] < V ? row[r] : V - 1;     // clamp: duplicate work, store is masked
+    const float* qr = base + (size_t)rr * 3 * E + h * DK;
+#pragma unroll
+    for (int d = 0; d < DK; d += 4) {
+      float4 t = *reinterpret_cast<const float4*>(qr + d);
+      qq[r][d] = t.x * qscale; qq[r][d + 1] = t.y * qscale; qq[r][d + 2] = t.z * qscale; qq[r][d + 3] = t.w * qscale;
+    }
+#pragma unroll
+    for (int d = 0; d < DK; ++d) o[r][d] = 0.f;
+    m[r] = -INFINITY;
+    l[r] = 0.f;
+  }
+  for (int k0 = 0; k0 < SA_VPAD; k0 += SA_KC) {
+    float s[SA_QPT][SA_KC];
+#pragma unroll
+    for (int kk = 0; kk < SA_KC; ++kk) {
+      const float4* kr = reinterpret_cast<const float4*>(sk + (k0 + kk) * DK);
+      float a[SA_QPT];
+#pragma unroll
+      for (int r = 0; r < SA_QPT; ++r) a[r] = 0.f;
+#pragma unroll
+      for (int d4 = 0; d4 < DK / 4; ++d4) {
+        const float4 kv4 = kr[d4];
+#pragma unroll
+        for (int r = 0; r < SA_QPT; ++r) {
+          a[r] = fmaf(qq[r][d4 * 4 + 0], kv4.x, a[r]);
+          a[r] = fmaf(qq[r][d4 * 4 + 1], kv4.y, a[r]);
+          a[r] = fmaf(qq[r][d4 * 4 + 2], kv4.z, a[r]);
+          a[r] = fmaf(qq[r][d4 * 4 + 3], kv4.w, a[r]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < SA_QPT; ++r) s[r][kk] = (k0 + kk < V) ? a[r] : -INFINITY;
+    }
+#pragma unroll
+    for (int r = 0; r < SA_QPT; ++r) {
+      float cm = s[r][0];
+#pragma unroll
+      for (int kk = 1; kk < SA_KC; ++kk) cm = fmaxf(cm, s[r][kk]);
+      const float mn = fmaxf(m[r], cm);
+      const float corr = exp2f(m[r] - mn);     // m = -inf on the first chunk -> 0
+      m[r] = mn;
+      float ps = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < SA_KC; ++kk) { s[r][kk] = exp2f(s[r][kk] - mn); ps += s[r][kk]; }
+      l[r] = fmaf(l[r], corr, ps);
+#pragma unroll
+      for (int d = 0; d < DK; ++d) o[r][d] *= corr;
+    }
+#pragma unroll
+    for (int kk = 0; kk < SA_KC; ++kk) {
+      const float4* vr = reinterpret_cast<const float4*>(sv + (k0 + kk) * DK);
+#pragma unroll
+      for (int d4 = 0; d4 < DK / 4; ++d4) {
+        const float4 vv = vr[d4];
+#pragma unroll
+        for (int r = 0; r < SA_QPT; ++r) {
+          const float p = s[r][kk];
+          o[r][d4 * 4 + 0] = fmaf(p, vv.x, o[r][d4 * 4 + 0]);
+          o[r][d4 * 4 + 1] = fmaf(p, vv.y, o[r][d4 * 4 + 1]);
+          o[r][d4 * 4 + 2] = fmaf(p, vv.z, o[r][d4 * 4 + 2]);
+          o[r][d4 * 4 + 3] = fmaf(p, vv.w, o[r][d4 * 4 + 3]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < SA_QPT; ++r) {
+    if (row[r] >= V) continue;
+    const float inv = 1.0f / l[r];
+    float* orow = out + ((size_t)b * V + row[r]) * E + h * DK;
+#pragma unroll
+    for (int d = 0; d < DK; d += 4)
+      *reinterpret_cast<float4*>(orow + d) = make_float4(o[r][d] * inv, o[r][d + 1] * inv, o[r][d + 2] * inv, o[r][d + 3] * inv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// MDR head (MDR.py:156-166) given hd = [motion_linear(23) | bias_linear(3) | scale_linear(1) | 0](x):
+// bias branch norm + GELU + Conv1d(431->20,k3,p1), softmax(A) @ B, alpha scaling, + C; then the im2col
+// rows of upsample_conv's input (MDR.py:167).  One CTA per sample.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mdr_head_kernel(const float* __restrict__ hd, const float* __restrict__ nscale, const float* __restrict__ nshift,
+                const float* __restrict__ cw, const float* __restrict__ cb, int alpha, float* __restrict__ coarse_out,
+                float* __restrict__ a3) {
+  __shared__ float gB[V + 2][3];
+  __shared__ float matB[20][3];
+  __shared__ float sc[V][3];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* hb = hd + (size_t)b * V * HEADN;
+  for (int v = tid; v < V; v += 256) {
+    float y[3];
+    const float x0 = hb[v * HEADN + 23], x1 = hb[v * HEADN + 24], x2 = hb[v * HEADN + 25];
+    if (alpha) {   // nn.LayerNorm(3)
+      const float mean = (x0 + x1 + x2) / 3.0f;
+      const float d0 = x0 - mean, d1 = x1 - mean, d2 = x2 - mean;
+      const float rstd = rsqrtf((d0 * d0 + d1 * d1 + d2 * d2) / 3.0f + 1e-5f);
+      y[0] = d0 * rstd * nscale[0] + nshift[0];
+      y[1] = d1 * rstd * nscale[1] + nshift[1];
+      y[2] = d2 * rstd * nscale[2] + nshift[2];
+    } else {       // eval BatchNorm1d(431): channel = vertex
+      const float s = nscale[v], t = nshift[v];
+      y[0] = fmaf(x0, s, t); y[1] = fmaf(x1, s, t); y[2] = fmaf(x2, s, t);
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) gB[v][t] = gelu_erf(y[t]);
+  }
+  __syncthreads();
+  for (int o = warp; o < 20; o += 8) {
+    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+    const float* w = cw + (size_t)o * V * 3;
+    for (int c = lane; c < V; c += 32) {
+      const float w0 = __ldg(w + c * 3), w1 = __ldg(w + c * 3 + 1), w2 = __ldg(w + c * 3 + 2);
+      const float g0 = gB[c][0], g1 = gB[c][1], g2 = gB[c][2];
+      p0 = fmaf(w1, g0, fmaf(w2, g1, p0));
+      p1 = fmaf(w0, g0, fmaf(w1, g1, fmaf(w2, g2, p1)));
+      p2 = fmaf(w0, g1, fmaf(w1, g2, p2));
+    }
+    p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
+    if (lane == 0) {
+      const float bb = cb[o];
+      matB[o][0] = p0 + bb; matB[o][1] = p1 + bb; matB[o][2] = p2 + bb;
+    }
+  }
+  __syncthreads();
+  for (int v = tid; v < V; v += 256) {
+    const float* r = hb + v * HEADN;
+    float a[20];
+    float m = -INFINITY;
+#pragma unroll
+    for (int o = 0; o < 20; ++o) { a[o] = r[o]; m = fmaxf(m, a[o]); }
+    float l = 0.f;
+#pragma unroll
+    for (int o = 0; o < 20; ++o) { a[o] = expf(a[o] - m); l += a[o]; }
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+#pragma unroll
+    for (int o = 0; o < 20; ++o) {
+      const float p = a[o] / l;
+      c0 = fmaf(p, matB[o][0], c0); c1 = fmaf(p, matB[o][1], c1); c2 = fmaf(p, matB[o][2], c2);
+    }
+    const float al = alpha ? powf(1.1f, r[26]) : 1.0f;
+    sc[v][0] = al * c0 + r[20]; sc[v][1] = al * c1 + r[21]; sc[v][2] = al * c2 + r[22];
+  }
+  __syncthreads();
+  if (coarse_out) {
+    float* co = coarse_out + (size_t)b * V * 3;
+    for (int i = tid; i < V * 3; i += 256) co[i] = (&sc[0][0])[i];
+  }
+  float* ab = a3 + (size_t)b * 3 * UPK;
+  for (int i = tid; i < 3 * UPK; i += 256) {
+    const int t = i / UPK, r = i - t * UPK;
+    float val = 0.f;
+    if (r < V * 3) {
+      const int c = r / 3, k = r - c * 3, tt = t + k - 1;
+      if (tt >= 0 && tt < 3) val = sc[c][tt];
+    }
+    ab[i] = val;
+  }
+}
+
+const char* kGlobalNames[MDR_NUM_GLOBAL] = {
+    "JF_WFEAT", "JF_WPOSE", "JF_BIASROWS", "VF_CONST", "VF_W3", "VJ", "HEAD_W", "HEAD_B",
+    "BNORM_SCALE", "BNORM_SHIFT", "BCONV_W", "BCONV_B", "UP_W", "UP_BIAST"};
+const char* kLayerNames[MDRL_NUM] = {
+    "N1_W", "N1_B", "WQ", "WKV", "PROJ_W", "PROJ_B", "N2_W", "N2_B", "FC1_W", "FC1_B", "FC2_W", "FC2_B",
+    "CLN_A", "CLN_B", "SQKV_W", "SQKV_B", "SO_W", "SO_B"};
+
+constexpr int kDefaultChunk = 148;   // 296 (sample, head) self-attention CTAs = one wave at 2 CTAs / SM
+
+int resolve_chunk(int batch, int chunk) {
+  if (chunk <= 0) chunk = kDefaultChunk;
+  return chunk < batch ? chunk : batch;
+}
+
+struct Ws {
+  float *x, *y, *q, *hid, *jf, *yj, *kv, *hd, *coarse, *a3;
+  size_t bytes;
+};
+
+Ws carve(float* base, int nb, int J) {
+  Ws w;
+  const size_t mv = (size_t)nb * V, mj = (size_t)nb * J;
+  size_t off = 0;
+  auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return p; };
+  w.x = take(mv * E);
+  w.y = take(mv * E);
+  w.q = take(mv * E);
+  w.hid = take(mv * 256);
+  w.jf = take(mj * E);
+  w.yj = take(mj * E);
+  w.kv = take(mj * 2 * E);
+  w.hd = take(mv * HEADN);
+  w.coarse = take((size_t)nb * V * 3);
+  w.a3 = take((size_t)nb * 3 * UPK);
+  w.bytes = off * sizeof(float);
+  return w;
+}
+
+}  // namespace
+}  // namespace gator
+
+extern "C" const char* gator_mdr_slot_name(int slot) {
+  using namespace gator;
+  if (slot < 0) return nullptr;
+  if (slot < MDR_NUM_GLOBAL) return kGlobalNames[slot];
+  if (slot < MDR_NUM_GLOBAL + MDRL_NUM) return kLayerNames[slot - MDR_NUM_GLOBAL];
+  return nullptr;
+}
+
+extern "C" size_t gator_mdr_workspace_bytes(int32_t batch, int32_t num_joint, int32_t chunk) {
+  using namespace gator;
+  if (batch <= 0 || num_joint <= 0) return 0;
+  return align_up(carve(nullptr, resolve_chunk(batch, chunk), num_joint).bytes, 256);
+}
+
+namespace gator {
+namespace {
+int launch_self_attn(const float* qkv, float* out, int nb, cudaStream_t stream) {
+  constexpr int sa_smem = 2 * SA_VPAD * DK * (int)sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(mdr_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sa_smem);
+    attr_done = true;
+  }
+  mdr_self_attn_kernel<<<nb * 2, SA_THREADS, sa_smem, stream>>>(qkv, out);
+  return check_launch("mdr_self_attn");
+}
+}  // namespace
+}  // namespace gator
+
+extern "C" int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_t precision, void* stream) {
+  using namespace gator;
+  GATOR_REQUIRE(qkv && out && batch >= 0, "gator_mdr_self_attention: bad argument");
+  GATOR_REQUIRE(precision == GATOR_PREC_FP32, "gator_mdr_self_attention: precision %d has no kernel yet", precision);
+  if (batch == 0) return GATOR_OK;
+  return launch_self_attn(qkv, out, batch, (cudaStream_t)stream);
+}
+
+extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
+  using namespace gator;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GATOR_REQUIRE(a, "gator_mdr_forward: null args");
+  const int J = a->num_joint, B = a->batch;
+  GATOR_REQUIRE(J >= 2 && J <= MAXJ, "gator_mdr_forward: num_joint=%d out of range [2,%d]", J, MAXJ);
+  GATOR_REQUIRE(a->precision == GATOR_PREC_FP32 || a->precision == GATOR_PREC_BF16, "gator_mdr_forward: bad precision");
+  if (B == 0) return GATOR_OK;
+  GATOR_REQUIRE(B > 0 && a->weights && a->pose2d && a->pose3d && a->feat && a->mesh, "gator_mdr_forward: null buffer");
+  const int nslots = MDR_NUM_GLOBAL + GATOR_MDR_LAYERS * MDRL_NUM;
+  for (int i = 0; i < nslots; ++i) {
+    if (i == MDR_HEAD_W || a->weights[i]) continue;
+    GATOR_REQUIRE(false, "gator_mdr_forward: weight slot %d is null", i);
+  }
+  GATOR_REQUIRE(a->weights[MDR_HEAD_W], "gator_mdr_forward: HEAD_W is null");
+  const size_t need = gator_mdr_workspace_bytes(B, J, a->chunk);
+  if (!a->workspace || a->workspace_bytes < need) {
+    set_error("gator_mdr_forward: workspace %zu < %zu bytes", a->workspace_bytes, need);
+    return GATOR_ERR_WORKSPACE;
+  }
+  auto G = [&](int s) { return static_cast<const float*>(a->weights[s]); };
+  const int cb = resolve_chunk(B, a->chunk);
+  Ws w = carve(static_cast<float*>(a->workspace), cb, J);
+
+  for (int b0 = 0; b0 < B; b0 += cb) {
+    const int nb = (B - b0 < cb) ? B - b0 : cb;
+    const int Mv = nb * V, Mj = nb * J;
+    mdr_embed_kernel<<<nb, 256, 0, stream>>>(a->pose2d + (size_t)b0 * J * 2, a->pose3d + (size_t)b0 * J * 3,
+                                             G(MDR_JF_WPOSE), G(MDR_VF_CONST), G(MDR_VF_W3),
+                                             static_cast<const int*>(a->weights[MDR_VJ]), w.jf, w.x, J);
+    GATOR_TRY(check_launch("mdr_embed"));
+    Epilogue e;
+    e.bias_rows = G(MDR_JF_BIASROWS);
+    e.bias_period = J;
+    e.R = w.jf;
+    e.ldr = E;
+    GATOR_TRY(gemm_f32(a->feat + (size_t)b0 * J * 128, 128, G(MDR_JF_WFEAT), 128, w.jf, E, Mj, E, 128, e, stream));
+
+    for (int l = 0; l < GATOR_MDR_LAYERS; ++l) {
+      const int base = MDR_NUM_GLOBAL + l * MDRL_NUM;
+      auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
+      // CrossAttentionBlock
+      GATOR_TRY(layernorm_rows(w.x, w.y, W(MDRL_N1_W), W(MDRL_N1_B), Mv, E, 0, 0, stream));
+      GATOR_TRY(layernorm_rows(w.jf, w.yj, W(MDRL_N1_W), W(MDRL_N1_B), Mj, E, 0, 0, stream));
+      GATOR_TRY(gemm_f32(w.y, E, W(MDRL_WQ), E, w.q, E, Mv, E, E, Epilogue(), stream));
+      GATOR_TRY(gemm_f32(w.yj, E, W(MDRL_WKV), E, w.kv, 2 * E, Mj, 2 * E, E, Epilogue(), stream));
+      mdr_cross_attn_kernel<<<nb, 256, 0, stream>>>(w.q, w.kv, w.y, J);
+      GATOR_TRY(check_launch("mdr_cross_attn"));
+      e = Epilogue();
+      e.bias = W(MDRL_PROJ_B);
+      e.R = w.x;
+      e.ldr = E;
+      GATOR_TRY(gemm_f32(w.y, E, W(MDRL_PROJ_W), E, w.x, E, Mv, E, E, e, stream));
+      GATOR_TRY(layernorm_rows(w.x, w.y, W(MDRL_N2_W), W(MDRL_N2_B), Mv, E, 0, 0, stream));
+      e = Epilogue();
+      e.bias = W(MDRL_FC1_B);
+      e.act = 1;
+      GATOR_TRY(gemm_f32(w.y, E, W(MDRL_FC1_W), E, w.hid, 256, Mv, 256, E, e, stream));
+      e = Epilogue();
+      e.bias = W(MDRL_FC2_B);
+      e.R = w.x;
+      e.ldr = E;
+      GATOR_TRY(gemm_f32(w.hid, 256, W(MDRL_FC2_W), 256, w.x, E, Mv, E, 256, e, stream));
+      // unbiased-std LayerNorm, then x = x3 + selfatt(x3)
+      GATOR_TRY(layernorm_rows(w.x, w.q, W(MDRL_CLN_A), W(MDRL_CLN_B), Mv, E, 1, 0, stream));
+      e = Epilogue();
+      e.bias = W(MDRL_SQKV_B);
+      GATOR_TRY(gemm_f32(w.q, E, W(MDRL_SQKV_W), E, w.hid, 3 * E, Mv, 3 * E, E, e, stream));
+      GATOR_TRY(launch_self_attn(w.hid, w.y, nb, stream));
+      e = Epilogue();
+      e.bias = W(MDRL_SO_B);
+      e.R = w.q;
+      e.ldr = E;
+      GATOR_TRY(gemm_f32(w.y, E, W(MDRL_SO_W), E, w.x, E, Mv, E, E, e, stream));
+    }
+    // head
+    e = Epilogue();
+    e.bias = G(MDR_HEAD_B);
+    GATOR_TRY(gemm_f32(w.x, E, G(MDR_HEAD_W), E, w.hd, HEADN, Mv, HEADN, E, e, stream));
+    mdr_head_kernel<<<nb, 256, 0, stream>>>(w.hd, G(MDR_BNORM_SCALE), G(MDR_BNORM_SHIFT), G(MDR_BCONV_W),
+                                            G(MDR_BCONV_B), a->alpha, a->coarse ? a->coarse + (size_t)b0 * V * 3 : nullptr, w.a3);
+    GATOR_TRY(check_launch("mdr_head"));
+    // upsample_conv + template: (3 nb) x 1296 @ 1296 x 6890, scattered to (b, vertex, xyz)
+    e = Epilogue();
+    e.conv3 = 1;
+    e.bias_rows = G(MDR_UP_BIAST);
+    GATOR_TRY(gemm_f32(w.a3, UPK, G(MDR_UP_W), UPK, a->mesh + (size_t)b0 * VF * 3, 0, nb * 3, VF, UPK, e, stream));
+  }
+  return GATOR_OK;
+}

@@ -1,0 +1,323 @@
+// SMPL linear blend skinning forward (smplpytorch/smplpytorch/pytorch/smpl_layer.py:65-158).
+//   K4 smpl_pose_kernel : Rodrigues (rodrigues_layer.py:13-52) + 24-joint kinematic chain (:103-132),
+//                         one warp per sample, lane = joint, tree walked level by level with shuffles.
+//   K3b blend shapes    : v_posed = T + [S|P] . [beta | R-I]   (:87-99) - dense GEMM, K = 217 (+3 pad).
+//   K5 smpl_skin_kernel : per-vertex blend of the joint transforms + apply (:134-145), ELL weights,
+//                         output staged through shared memory and written as aligned float4.
+#include "common.cuh"
+
+namespace gator {
+namespace {
+
+constexpr int NJ = GATOR_SMPL_JOINTS;   // 24
+constexpr int KB = GATOR_SMPL_K;        // 220
+constexpr int NV = GATOR_V_FULL;        // 6890
+constexpr int NV3 = NV * 3;             // 20670
+
+__global__ void smpl_flags_kernel(const float* __restrict__ betas, int nb, const float* __restrict__ trans, int nt,
+                                  int* __restrict__ flags) {
+  // flags[0] = any(betas != 0), flags[1] = any(trans != 0)   (norm(x) == 0  <=>  all zero)
+  __shared__ int f[2];
+  if (threadIdx.x < 2) f[threadIdx.x] = 0;
+  __syncthreads();
+  int a = 0, b = 0;
+  for (int i = threadIdx.x; i < nb; i += blockDim.x) a |= (betas[i] != 0.f);
+  for (int i = threadIdx.x; i < nt; i += blockDim.x) b |= (trans[i] != 0.f);
+  if (a) atomicOr(&f[0], 1);
+  if (b) atomicOr(&f[1], 1);
+  __syncthreads();
+  if (threadIdx.x < 2) flags[threadIdx.x] = f[threadIdx.x];
+}
+
+struct PoseParams {
+  const float* pose;        // (B,72)
+  const float* betas;       // (B,10) or null
+  const float* trans;       // (B,3) or null
+  const float* def_betas;   // (10)
+  const float* jt;          // (24,3)
+  const float* js;          // (24,3,10)
+  const int* parents;       // (24)
+  const int* flags;         // null or [any_betas, any_trans]
+  float* aop;               // (B,220)  [beta | R-I | 0]
+  float* amat;              // (B,24,12) skinning transforms (top 3 rows of G')
+  float* offset;            // (B,3) added to verts
+  float* jtr;               // (B,24,3)
+  int batch;
+  int center_idx;
+};
+
+__global__ void __launch_bounds__(128)
+smpl_pose_kernel(PoseParams p) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= p.batch) return;
+  const bool use_betas = p.betas && (!p.flags || p.flags[0]);
+  const bool use_trans = p.trans && (!p.flags || p.flags[1]);
+  const float* beta = use_betas ? p.betas + (size_t)b * 10 : p.def_betas;
+  const int i = lane < NJ ? lane : NJ - 1;
+
+  // --- Rodrigues: axis-angle -> unit quaternion -> rotation matrix ---
+  const float ax = p.pose[(size_t)b * 72 + i * 3 + 0];
+  const float ay = p.pose[(size_t)b * 72 + i * 3 + 1];
+  const float az = p.pose[(size_t)b * 72 + i * 3 + 2];
+  const float ex = ax + 1e-8f, ey = ay + 1e-8f, ez = az + 1e-8f;
+  const float angle = sqrtf(ex * ex + ey * ey + ez * ez);
+  const float nx = ax / angle, ny = ay / angle, nz = az / angle;
+  const float half = angle * 0.5f;
+  const float cs = cosf(half), sn = sinf(half);
+  float qw = cs, qx = sn * nx, qy = sn * ny, qz = sn * nz;
+  const float qn = sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
+  qw /= qn; qx /= qn; qy /= qn; qz /= qn;
+  const float w2 = qw * qw, x2 = qx * qx, y2 = qy * qy, z2 = qz * qz;
+  const float wx = qw * qx, wy = qw * qy, wz = qw * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz;
+  float R[9];
+  R[0] = w2 + x2 - y2 - z2; R[1] = 2 * xy - 2 * wz;     R[2] = 2 * wy + 2 * xz;
+  R[3] = 2 * wz + 2 * xy;     R[4] = w2 - x2 + y2 - z2; R[5] = 2 * yz - 2 * wx;
+  R[6] = 2 * xz - 2 * wy;     R[7] = 2 * wx + 2 * yz;     R[8] = w2 - x2 - y2 + z2;
+
+  // --- blend-shape operand row: [beta(10) | R_1..R_23 - I (207) | 0 0 0] ---
+  float* arow = p.aop + (size_t)b * KB;
+  if (lane < 10) arow[lane] = beta[lane];
+  if (lane >= 1 && lane < NJ) {
+#pragma unroll
+    for (int e = 0; e < 9; ++e) arow[10 + (lane - 1) * 9 + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
+  }
+  if (lane >= NJ && lane < NJ + 3) arow[217 + lane - NJ] = 0.f;
+
+  // --- rest joints: J_regressor @ (T + S beta) with the regressor pre-applied to T and S ---
+  float j[3];
+#pragma unroll
+  for (int t = 0; t < 3; ++t) {
+    float a = 0.f;
+#pragma unroll
+    for (int s = 0; s < 10; ++s) a = fmaf(__ldg(p.js + (i * 3 + t) * 10 + s), beta[s], a);
+    j[t] = __ldg(p.jt + i * 3 + t) + a;
+  }
+  int parent = (i == 0) ? 0 : p.parents[i];
+  parent = parent < 0 ? 0 : (parent >= NJ ? 0 : parent);
+  int depth = 0;
+  for (int q = i; q != 0 && depth < NJ; q = p.parents[q]) ++depth;
+
+  // local transform: [R | j_i - j_parent] (root: [R | j_0])
+  const float pjx = __shfl_sync(0xffffffffu, j[0], parent);
+  const float pjy = __shfl_sync(0xffffffffu, j[1], parent);
+  const float pjz = __shfl_sync(0xffffffffu, j[2], parent);
+  float t[3] = {j[0] - (i ? pjx : 0.f), j[1] - (i ? pjy : 0.f), j[2] - (i ? pjz : 0.f)};
+  // G = G_parent @ local, level by level
+  float G[12];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) { G[r * 4 + 0] = R[r * 3]; G[r * 4 + 1] = R[r * 3 + 1]; G[r * 4 + 2] = R[r * 3 + 2]; G[r * 4 + 3] = t[r]; }
+  for (int level = 1; level < NJ; ++level) {
+    const bool mine = (depth == level) && lane < NJ;
+    if (!__any_sync(0xffffffffu, mine)) break;
+    float P[12];
+#pragma unroll
+    for (int e = 0; e < 12; ++e) P[e] = __shfl_sync(0xffffffffu, G[e], parent);
+    if (mine) {
+      float N[12];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          N[r * 4 + c] = P[r * 4 + 0] * R[c] + P[r * 4 + 1] * R[3 + c] + P[r * 4 + 2] * R[6 + c];
+        N[r * 4 + 3] = P[r * 4 + 0] * t[0] + P[r * 4 + 1] * t[1] + P[r * 4 + 2] * t[2] + P[r * 4 + 3];
+      }
+#pragma unroll
+      for (int e = 0; e < 12; ++e) G[e] = N[e];
+    }
+  }
+  // translation of verts/joints (smpl_layer.py:148-155)
+  float off[3] = {0.f, 0.f, 0.f};
+  if (use_trans) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) off[c] = p.trans[(size_t)b * 3 + c];
+  } else if (p.center_idx >= 0) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) off[c] = -__shfl_sync(0xffffffffu, G[c * 4 + 3], p.center_idx);
+  }
+  if (lane < NJ) {
+    float* jo = p.jtr + ((size_t)b * NJ + lane) * 3;
+    jo[0] = G[3] + off[0]; jo[1] = G[7] + off[1]; jo[2] = G[11] + off[2];
+    // G' = G - pack(G @ [j; 0]): last column becomes t - R j
+    float* ao = p.amat + ((size_t)b * NJ + lane) * 12;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      ao[r * 4 + 0] = G[r * 4 + 0]; ao[r * 4 + 1] = G[r * 4 + 1]; ao[r * 4 + 2] = G[r * 4 + 2];
+      ao[r * 4 + 3] = G[r * 4 + 3] - (G[r * 4 + 0] * j[0] + G[r * 4 + 1] * j[1] + G[r * 4 + 2] * j[2]);
+    }
+  }
+  if (lane < 3) p.offset[(size_t)b * 3 + lane] = off[lane];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Skinning.  CTA = 256 consecutive vertices x SG consecutive samples.  Per sample: the 24 transforms go
+// to shared memory, each thread blends its vertex's KW transforms, applies them to v_posed and parks
+// the 3 outputs in shared memory; the 768-float segment is then written with aligned float4 stores
+// (a sample row is 82 680 B = 8 mod 16, so odd samples start mid-float4: 2-float head/tail).
+// ---------------------------------------------------------------------------------------------
+constexpr int SK_VT = 256;
+constexpr int SK_SG = 8;
+
+__global__ void __launch_bounds__(SK_VT)
+smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ amat, const float* __restrict__ offset,
+                 const int* __restrict__ sidx, const float* __restrict__ sw, int KW, float* __restrict__ verts, int batch) {
+  __shared__ __align__(16) float sA[NJ * 12];
+  __shared__ __align__(16) float sin_[SK_VT * 3 + 4];
+  __shared__ __align__(16) float sout[SK_VT * 3 + 4];
+  __shared__ float soff[3];
+  const int tid = threadIdx.x;
+  const int v0 = blockIdx.x * SK_VT;
+  const int nv = min(SK_VT, NV - v0);
+  const int v = v0 + tid;
+  const bool active = tid < nv;
+  int jid[4];
+  float jw[4];
+  if (KW <= 4) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      jid[k] = (active && k < KW) ? __ldg(sidx + (size_t)v * KW + k) : 0;
+      jw[k] = (active && k < KW) ? __ldg(sw + (size_t)v * KW + k) : 0.f;
+    }
+  }
+  const int s_begin = blockIdx.y * SK_SG;
+  const int s_end = min(batch, s_begin + SK_SG);
+  const int seg = nv * 3;
+  for (int s = s_begin; s < s_end; ++s) {
+    __syncthreads();   // previous sample's sout/sA fully consumed
+    for (int i = tid; i < NJ * 12; i += SK_VT) sA[i] = amat[(size_t)s * NJ * 12 + i];
+    if (tid < 3) soff[tid] = offset[(size_t)s * 3 + tid];
+    {
+      // v_posed segment: 8-byte aligned always -> float2 loads
+      const float2* src = reinterpret_cast<const float2*>(vposed + (size_t)s * NV3 + (size_t)v0 * 3);
+      for (int i = tid; i < seg / 2; i += SK_VT) *reinterpret_cast<float2*>(&sin_[i * 2]) = src[i];
+      if ((seg & 1) && tid == 0) sin_[seg - 1] = vposed[(size_t)s * NV3 + (size_t)v0 * 3 + seg - 1];
+    }
+    __syncthreads();
+    if (active) {
+      float T[12];
+#pragma unroll
+      for (int e = 0; e < 12; ++e) T[e] = 0.f;
+      if (KW <= 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4* a4 = reinterpret_cast<const float4*>(sA + jid[k] * 12);
+          const float4 r0 = a4[0], r1 = a4[1], r2 = a4[2];
+          T[0] = fmaf(jw[k], r0.x, T[0]); T[1] = fmaf(jw[k], r0.y, T[1]); T[2] = fmaf(jw[k], r0.z, T[2]); T[3] = fmaf(jw[k], r0.w, T[3]);
+          T[4] = fmaf(jw[k], r1.x, T[4]); T[5] = fmaf(jw[k], r1.y, T[5]); T[6] = fmaf(jw[k], r1.z, T[6]); T[7] = fmaf(jw[k], r1.w, T[7]);
+          T[8] = fmaf(jw[k], r2.x, T[8]); T[9] = fmaf(jw[k], r2.y, T[9]); T[10] = fmaf(jw[k], r2.z, T[10]); T[11] = fmaf(jw[k], r2.w, T[11]);
+        }
+      } else {
+        for (int k = 0; k < KW; ++k) {
+          const int jj = __ldg(sidx + (size_t)v * KW + k);
+          const float ww = __ldg(sw + (size_t)v * KW + k);
+#pragma unroll
+          for (int e = 0; e < 12; ++e) T[e] = fmaf(ww, sA[jj * 12 + e], T[e]);
+        }
+      }
+      const float px = sin_[tid * 3], py = sin_[tid * 3 + 1], pz = sin_[tid * 3 + 2];
+      sout[tid * 3 + 0] = T[0] * px + T[1] * py + T[2] * pz + T[3] + soff[0];
+      sout[tid * 3 + 1] = T[4] * px + T[5] * py + T[6] * pz + T[7] + soff[1];
+      sout[tid * 3 + 2] = T[8] * px + T[9] * py + T[10] * pz + T[11] + soff[2];
+    }
+    __syncthreads();
+    // aligned float4 body with scalar head / tail
+    float* dst = verts + (size_t)s * NV3 + (size_t)v0 * 3;
+    const int head = (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) >> 2;   // floats until 16B boundary
+    const int h = min(head, seg);
+    if (tid < h) dst[tid] = sout[tid];
+    const int body = (seg - h) >> 2;
+    for (int i = tid; i < body; i += SK_VT) {
+      const float* sp = sout + h + i * 4;
+      *reinterpret_cast<float4*>(dst + h + i * 4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+    }
+    const int tail0 = h + body * 4;
+    if (tid < seg - tail0) dst[tail0 + tid] = sout[tail0 + tid];
+  }
+}
+
+constexpr int kChunk = 512;
+
+struct Ws {
+  float *aop, *amat, *offset, *vposed;
+  int* flags;
+  size_t bytes;
+};
+
+Ws carve(char* base, int nb) {
+  Ws w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
+  w.flags = reinterpret_cast<int*>(take(16));
+  w.aop = reinterpret_cast<float*>(take((size_t)nb * KB * 4));
+  w.amat = reinterpret_cast<float*>(take((size_t)nb * NJ * 12 * 4));
+  w.offset = reinterpret_cast<float*>(take((size_t)nb * 3 * 4));
+  w.vposed = reinterpret_cast<float*>(take((size_t)nb * NV3 * 4));
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace
+}  // namespace gator
+
+extern "C" size_t gator_smpl_workspace_bytes(int32_t batch) {
+  using namespace gator;
+  if (batch <= 0) return 0;
+  return carve(nullptr, batch < kChunk ? batch : kChunk).bytes;
+}
+
+extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
+  using namespace gator;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GATOR_REQUIRE(a, "gator_smpl_forward: null args");
+  const int B = a->batch;
+  if (B == 0) return GATOR_OK;
+  GATOR_REQUIRE(B > 0 && a->pose && a->verts && a->jtr, "gator_smpl_forward: null buffer");
+  GATOR_REQUIRE(a->parents && a->j_template && a->j_shapedirs && a->default_betas && a->blend_w && a->v_template &&
+                    a->skin_idx && a->skin_w, "gator_smpl_forward: null model buffer");
+  GATOR_REQUIRE(a->weights_per_vertex >= 1 && a->weights_per_vertex <= NJ, "gator_smpl_forward: bad weights_per_vertex");
+  GATOR_REQUIRE(a->center_idx >= -1 && a->center_idx < NJ, "gator_smpl_forward: bad center_idx");
+  GATOR_REQUIRE(!a->has_betas || a->betas, "gator_smpl_forward: has_betas without betas");
+  GATOR_REQUIRE(!a->has_trans || a->trans, "gator_smpl_forward: has_trans without trans");
+  GATOR_REQUIRE(a->precision == GATOR_PREC_FP32 || a->precision == GATOR_PREC_BF16, "gator_smpl_forward: bad precision");
+  const size_t need = gator_smpl_workspace_bytes(B);
+  if (!a->workspace || a->workspace_bytes < need) {
+    set_error("gator_smpl_forward: workspace %zu < %zu bytes", a->workspace_bytes, need);
+    return GATOR_ERR_WORKSPACE;
+  }
+  const int cb = B < kChunk ? B : kChunk;
+  Ws w = carve(static_cast<char*>(a->workspace), cb);
+  const bool flags = a->check_zero_norm && (a->has_betas || a->has_trans);
+  if (flags) {
+    smpl_flags_kernel<<<1, 256, 0, stream>>>(a->has_betas ? a->betas : nullptr, a->has_betas ? B * 10 : 0,
+                                             a->has_trans ? a->trans : nullptr, a->has_trans ? B * 3 : 0, w.flags);
+    GATOR_TRY(check_launch("smpl_flags"));
+  }
+  for (int b0 = 0; b0 < B; b0 += cb) {
+    const int nb = (B - b0 < cb) ? B - b0 : cb;
+    PoseParams p;
+    p.pose = a->pose + (size_t)b0 * 72;
+    p.betas = a->has_betas ? a->betas + (size_t)b0 * 10 : nullptr;
+    p.trans = a->has_trans ? a->trans + (size_t)b0 * 3 : nullptr;
+    p.def_betas = a->default_betas;
+    p.jt = a->j_template;
+    p.js = a->j_shapedirs;
+    p.parents = a->parents;
+    p.flags = flags ? w.flags : nullptr;
+    p.aop = w.aop;
+    p.amat = w.amat;
+    p.offset = w.offset;
+    p.jtr = a->jtr + (size_t)b0 * NJ * 3;
+    p.batch = nb;
+    p.center_idx = a->center_idx;
+    smpl_pose_kernel<<<ceil_div(nb, 4), 128, 0, stream>>>(p);
+    GATOR_TRY(check_launch("smpl_pose"));
+    Epilogue e;
+    e.bias = a->v_template;
+    GATOR_TRY(gemm_f32(w.aop, KB, a->blend_w, KB, w.vposed, NV3, nb, NV3, KB, e, stream));
+    dim3 grid(ceil_div(NV, SK_VT), ceil_div(nb, SK_SG));
+    smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w,
+                                                 a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb);
+    GATOR_TRY(check_launch("smpl_skin"));
+  }
+  return GATOR_OK;
+}

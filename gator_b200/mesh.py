@@ -1,0 +1,121 @@
+"""Drop-in for ``models.backbones.mesh.Mesh`` (lib/models/backbones/mesh.py:60-123).
+
+Same constructor signature and methods; ``downsample`` / ``upsample`` run the batched CSR SpMM CUDA
+kernel (csrc/sparse.cu) over the whole batch in one launch instead of a Python loop of torch.sparse
+products per sample (mesh.py:93-123, graph_layers.py:105-124).  CUDA only - no CPU fallback.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import _lib, graph
+
+
+def _load_npz(filename):
+    """mesh.py:50-58: pickled object arrays A, U, D of scipy sparse matrices (GraphCMR format)."""
+    data = np.load(filename, encoding='latin1', allow_pickle=True)
+    return list(data['A']), list(data['U']), list(data['D'])
+
+
+class _Csr:
+    """One sparse operator resident on the device as CSR (int32 / fp32)."""
+
+    def __init__(self, m, device):
+        rp, ci, va, shape = graph.to_csr(m)
+        self.shape = shape
+        self.rowptr = torch.from_numpy(rp).to(device)
+        self.colidx = torch.from_numpy(ci).to(device)
+        self.values = torch.from_numpy(va).to(device)
+        self.device = torch.device(device)
+
+    def apply(self, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+        """y[..., r, :] = scale * sum_k val_k x[..., col_k, :] for x of shape (N,F) or (B,N,F)."""
+        if not x.is_cuda:
+            raise RuntimeError('gator_b200.Mesh: CUDA tensors only (no CPU fallback)')
+        if x.dtype != torch.float32:
+            raise TypeError('gator_b200.Mesh: float32 only')
+        squeeze = x.dim() == 2
+        xb = x.unsqueeze(0) if squeeze else x
+        if xb.dim() != 3 or xb.shape[1] != self.shape[1]:
+            raise ValueError(f'expected (*, {self.shape[1]}, F), got {tuple(x.shape)}')
+        xb = xb.contiguous()
+        B, _, F = xb.shape
+        y = torch.empty((B, self.shape[0], F), dtype=torch.float32, device=x.device)
+        a = _lib.CsrArgs(batch=B, rows=self.shape[0], cols=self.shape[1], feat=F, scale=scale, reserved=0,
+                         rowptr=_lib.ptr(self.rowptr), colidx=_lib.ptr(self.colidx), values=_lib.ptr(self.values),
+                         x=_lib.ptr(xb), y=_lib.ptr(y))
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().gator_csr_spmm(a, _lib.stream_ptr()), 'gator_csr_spmm')
+        return y[0] if squeeze else y
+
+
+def adjmat_sparse(adjmat, nsize=1):
+    """mesh.py:29-48: row-normalised adjacency (with self loops) as a torch sparse COO tensor."""
+    import scipy.sparse
+    adjmat = scipy.sparse.csr_matrix(adjmat)
+    if nsize > 1:
+        orig = adjmat.copy()
+        for _ in range(1, nsize):
+            adjmat = adjmat * orig
+    adjmat.data = np.ones_like(adjmat.data)
+    adjmat = scipy.sparse.lil_matrix(adjmat)
+    adjmat.setdiag(1)
+    adjmat = scipy.sparse.csr_matrix(adjmat)
+    num_neighbors = np.array(1 / adjmat.sum(axis=-1))
+    adjmat = scipy.sparse.coo_matrix(adjmat.multiply(num_neighbors))
+    i = torch.from_numpy(np.array([adjmat.row, adjmat.col])).long()
+    v = torch.from_numpy(adjmat.data).float()
+    return torch.sparse_coo_tensor(i, v, adjmat.shape)
+
+
+class Mesh(object):
+    """Mesh object that is used for handling certain graph operations (same API as the reference)."""
+
+    def __init__(self, filename='data/base_data/mesh_downsampling.npz', num_downsampling=1, nsize=1,
+                 device=torch.device('cuda')):
+        A, U, D = _load_npz(filename)
+        self._A = [adjmat_sparse(a, nsize=nsize) for a in A]
+        self.device = torch.device(device)
+        self._U_host, self._D_host = U, D          # scipy, for init-time host products
+        self._U = [_Csr(u, self.device) for u in U] if self.device.type == 'cuda' else None
+        self._D = [_Csr(d, self.device) for d in D] if self.device.type == 'cuda' else None
+        self.num_downsampling = num_downsampling
+
+    @property
+    def adjmat(self):
+        """Return the graph adjacency matrix at the specified subsampling level."""
+        return self._A[self.num_downsampling].float()
+
+    def _ops(self, which):
+        ops = self._U if which == 'U' else self._D
+        if ops is None:
+            raise RuntimeError('gator_b200.Mesh was built with a CPU device: re-sampling kernels are CUDA only')
+        return ops
+
+    def downsample(self, x, n1=0, n2=None):
+        """Downsample mesh: x (N,3) or (B,N,3) through D[n1..n2-1]."""
+        if n2 is None:
+            n2 = self.num_downsampling
+        for i in range(n1, n2):
+            x = self._ops('D')[i].apply(x)
+        return x
+
+    def upsample(self, x, n1=1, n2=0):
+        """Upsample mesh: x (N,3) or (B,N,3) through U[n1-1..n2] (coarse to fine)."""
+        for i in reversed(range(n2, n1)):
+            x = self._ops('U')[i].apply(x)
+        return x
+
+    # init-time helper used by MDR.__init__ (MDR.py:79-81): same product as the reference's
+    # torch.sparse COO @ dense, evaluated once on the host in float32.
+    def downsample_host(self, x: torch.Tensor, n1=0, n2=None) -> torch.Tensor:
+        import scipy.sparse
+        if n2 is None:
+            n2 = self.num_downsampling
+        for i in range(n1, n2):
+            d = scipy.sparse.coo_matrix(self._D_host[i])
+            sp = torch.sparse_coo_tensor(torch.from_numpy(np.array([d.row, d.col])).long(),
+                                         torch.from_numpy(d.data.astype(np.float32)), d.shape)
+            x = torch.matmul(sp, x)
+        return x

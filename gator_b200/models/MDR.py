@@ -1,0 +1,236 @@
+"""Drop-in for ``models.MDR`` (lib/models/MDR.py): same constructor signature and ``state_dict`` keys;
+forward executed by the sm_100a kernels behind ``gator_mdr_forward`` (csrc/mdr.cu).
+
+Sub-modules only hold parameters under the reference's names.  :meth:`MDR.pack` folds the
+input-independent terms: the template part of ``get_verts_feature`` plus
+``pos_v_id_embed``, ``pos_j_id_embed`` into the joint bias, eval-mode BatchNorm into scale/shift,
+``upsample_conv.bias`` + ``init_vertices_6890`` into one (6890,3) table.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _lib, config, graph
+from ..mesh import Mesh
+
+V_COARSE, V_FULL, UP_K = 431, 6890, 1296
+
+
+def _invalidate_hook(module, incompatible_keys):
+    module.invalidate()
+
+
+class CrossAttention(nn.Module):
+    """Parameter holder for MDR.py:18-46 (wq/wk/wv without bias, proj with bias)."""
+
+    def __init__(self, dim, joint_num, num_heads):
+        super().__init__()
+        self.num_heads, self.joint_num = num_heads, joint_num
+        self.wq = nn.Linear(dim, dim, bias=False)
+        self.wk = nn.Linear(dim, dim, bias=False)
+        self.wv = nn.Linear(dim, dim, bias=False)
+        self.proj = nn.Linear(dim, dim)
+
+
+class Mlp(nn.Module):
+    """timm.models.vision_transformer.Mlp parameter names (fc1, fc2)."""
+
+    def __init__(self, in_features, hidden_features):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features)
+        self.fc2 = nn.Linear(hidden_features, in_features)
+
+
+class CrossAttentionBlock(nn.Module):
+    """Parameter holder for MDR.py:48-69."""
+
+    def __init__(self, dim, joint_num, num_heads, mlp_ratio=4.):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = CrossAttention(dim, joint_num, num_heads)
+        self.norm2 = nn.LayerNorm(dim)
+        self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+
+class MultiHeadedAttention(nn.Module):
+    """Parameter holder for vanilla_transformer_encoder.py:72-94 (four Linear(64,64))."""
+
+    def __init__(self, h, d_model):
+        super().__init__()
+        self.h, self.d_k = h, d_model // h
+        self.linears = nn.ModuleList([nn.Linear(d_model, d_model) for _ in range(4)])
+
+
+class LayerNorm(nn.Module):
+    """Parameter holder for vanilla_transformer_encoder.py:24-34 (keys a_2, b_2)."""
+
+    def __init__(self, features, eps=1e-6):
+        super().__init__()
+        self.a_2 = nn.Parameter(torch.ones(features))
+        self.b_2 = nn.Parameter(torch.zeros(features))
+        self.eps = eps
+
+
+class MDR(nn.Module):
+    def __init__(self, num_joint, embed_dim, SMPL_MEAN_vertices=None):
+        super().__init__()
+        if embed_dim != 128:
+            raise NotImplementedError('gator_b200.MDR expects the 128-d GAT feature (2+3+128 inputs, MDR.py:111)')
+        if not 2 <= num_joint <= 32:
+            raise NotImplementedError('num_joint must be in [2, 32]')
+        cfg = config.get_cfg()
+        self.embed_dim = 64
+        self.num_joint = num_joint
+        self.alpha = bool(cfg.MODEL.alpha)                      # snapshot of cfg.MODEL.alpha (MDR.py:115,162)
+        if SMPL_MEAN_vertices is None:
+            SMPL_MEAN_vertices = config.base_data_path('smpl_mean_vertices.npy')
+        self.mesh = Mesh(config.base_data_path('mesh_downsampling.npz'),
+                         device=torch.device('cuda' if torch.cuda.is_available() else 'cpu'))
+        init_vertices = torch.from_numpy(np.load(SMPL_MEAN_vertices))
+        v1723 = self.mesh.downsample_host(init_vertices, 0, 1)                   # MDR.py:80
+        v431 = self.mesh.downsample_host(v1723, 1, 2)                            # MDR.py:81
+        self.register_buffer('init_vertices', v431)
+        self.register_buffer('init_vertices_6890', init_vertices)
+        J_regressor = torch.from_numpy(np.load(config.base_data_path('J_regressor_h36m.npy')).astype(np.float32))
+        self.joints_template = torch.matmul(J_regressor, init_vertices)          # MDR.py:85-86
+        self.vj_relation = graph.nearest_joint(self.joints_template.numpy(), v431.numpy())
+        self.num_verts = v431.shape[0]
+        if self.num_verts != V_COARSE or init_vertices.shape[0] != V_FULL:
+            raise NotImplementedError('kernels are built for the 6890 -> 431 SMPL hierarchy')
+
+        E = self.embed_dim
+        self.pos_j_id_embed = nn.Embedding(num_joint + 1, E, padding_idx=0)
+        self.pos_v_id_embed = nn.Embedding(self.num_verts + 1, E, padding_idx=0)
+        self.encoder = CrossAttentionBlock(E, num_joint, 2)
+        self.selfatt = MultiHeadedAttention(2, E)
+        self.norm = LayerNorm(E)
+        self.encoder_1 = CrossAttentionBlock(E, num_joint, 2)
+        self.selfatt_1 = MultiHeadedAttention(2, E)
+        self.norm_1 = LayerNorm(E)
+        self.encoder_2 = CrossAttentionBlock(E, num_joint, 2)
+        self.selfatt_2 = MultiHeadedAttention(2, E)
+        self.norm_2 = LayerNorm(E)
+        self.get_joint_feature = nn.Linear(2 + 3 + embed_dim, E)
+        self.get_verts_feature = nn.Linear(3 + 3, E)
+        self.motion_linear = nn.Linear(E, 23)
+        self.bias_linear = nn.Linear(E, 3)
+        if self.alpha:
+            self.bias_norm = nn.LayerNorm(3)
+            self.scale_linear = nn.Linear(E, 1)
+        else:
+            self.bias_norm = nn.BatchNorm1d(self.num_verts)
+        self.bias_conv1d = nn.Conv1d(self.num_verts, 20, kernel_size=3, padding=1)
+        self.upsample_conv = nn.Conv1d(self.num_verts, 6890, kernel_size=3, padding=1)
+        self._packed = None
+        self._ws = None
+        self.precision = _lib.PREC_FP32
+        self.chunk = 0
+        self.register_load_state_dict_post_hook(_invalidate_hook)
+
+    def invalidate(self):
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        out = super()._apply(fn, *a, **k)
+        self._packed = None
+        return out
+
+    @torch.no_grad()
+    def pack(self):
+        dev = self.upsample_conv.weight.device
+        if dev.type != 'cuda':
+            raise RuntimeError('gator_b200.MDR: parameters must be on a CUDA device (no CPU fallback)')
+        J, E = self.num_joint, self.embed_dim
+        f = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+        wj, wv = self.get_joint_feature.weight, self.get_verts_feature.weight
+        vconst = (self.init_vertices @ wv[:, :3].t() + self.get_verts_feature.bias
+                  + self.pos_v_id_embed.weight[1:self.num_verts + 1])
+        head_w = torch.zeros(28, E, device=dev)
+        head_b = torch.zeros(28, device=dev)
+        head_w[:23], head_b[:23] = self.motion_linear.weight, self.motion_linear.bias
+        head_w[23:26], head_b[23:26] = self.bias_linear.weight, self.bias_linear.bias
+        if self.alpha:
+            head_w[26], head_b[26] = self.scale_linear.weight[0], self.scale_linear.bias[0]
+            nscale, nshift = self.bias_norm.weight, self.bias_norm.bias
+        else:
+            bn = self.bias_norm
+            nscale = bn.weight / torch.sqrt(bn.running_var + bn.eps)
+            nshift = bn.bias - bn.running_mean * nscale
+        up_w = torch.zeros(V_FULL, UP_K, device=dev)
+        up_w[:, :self.num_verts * 3] = self.upsample_conv.weight.reshape(V_FULL, -1)
+        t = {
+            'JF_WFEAT': f(wj[:, 5:]), 'JF_WPOSE': f(wj[:, :5]),
+            'JF_BIASROWS': f(self.get_joint_feature.bias[None, :] + self.pos_j_id_embed.weight[1:J + 1]),
+            'VF_CONST': f(vconst), 'VF_W3': f(wv[:, 3:6]),
+            'VJ': torch.from_numpy(np.asarray(self.vj_relation)).to(device=dev, dtype=torch.int32).contiguous(),
+            'HEAD_W': f(head_w), 'HEAD_B': f(head_b),
+            'BNORM_SCALE': f(nscale), 'BNORM_SHIFT': f(nshift),
+            'BCONV_W': f(self.bias_conv1d.weight), 'BCONV_B': f(self.bias_conv1d.bias),
+            'UP_W': f(up_w),
+            'UP_BIAST': f(self.upsample_conv.bias[:, None] + self.init_vertices_6890),
+        }
+        gnames, lnames = _lib.slot_names('mdr')
+        tensors = [t[n] for n in gnames]
+        for sfx in ('', '_1', '_2'):
+            enc, sa, cln = getattr(self, 'encoder' + sfx), getattr(self, 'selfatt' + sfx), getattr(self, 'norm' + sfx)
+            l = {
+                'N1_W': f(enc.norm1.weight), 'N1_B': f(enc.norm1.bias),
+                'WQ': f(enc.attn.wq.weight), 'WKV': f(torch.cat([enc.attn.wk.weight, enc.attn.wv.weight], 0)),
+                'PROJ_W': f(enc.attn.proj.weight), 'PROJ_B': f(enc.attn.proj.bias),
+                'N2_W': f(enc.norm2.weight), 'N2_B': f(enc.norm2.bias),
+                'FC1_W': f(enc.mlp.fc1.weight), 'FC1_B': f(enc.mlp.fc1.bias),
+                'FC2_W': f(enc.mlp.fc2.weight), 'FC2_B': f(enc.mlp.fc2.bias),
+                'CLN_A': f(cln.a_2), 'CLN_B': f(cln.b_2),
+                'SQKV_W': f(torch.cat([sa.linears[i].weight for i in range(3)], 0)),
+                'SQKV_B': f(torch.cat([sa.linears[i].bias for i in range(3)], 0)),
+                'SO_W': f(sa.linears[3].weight), 'SO_B': f(sa.linears[3].bias),
+            }
+            tensors += [l[n] for n in lnames]
+        table = (ctypes.c_void_p * len(tensors))(*[t_.data_ptr() for t_ in tensors])
+        self._packed = (tensors, table, dev)
+        return self
+
+    def _workspace(self, batch, dev):
+        need = _lib.lib().gator_mdr_workspace_bytes(batch, self.num_joint, self.chunk)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
+            self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return self._ws
+
+    def forward_parts(self, pose2d, pose3d_mm, feat, want_coarse=False):
+        """The fused entry: what GATOR.forward feeds MDR, without materialising the (B,J,133) concat
+        (GATOR.py:19).  pose2d (B,J,2), pose3d_mm (B,J,3) millimetres, feat (B,J,128) -> (B,6890,3) m."""
+        if self.training:
+            raise NotImplementedError('gator_b200.MDR implements the eval() forward only')
+        if self._packed is None:
+            self.pack()
+        tensors, table, dev = self._packed
+        for t_ in (pose2d, pose3d_mm, feat):
+            if not t_.is_cuda:
+                raise RuntimeError('gator_b200.MDR: inputs must be CUDA tensors (no CPU fallback)')
+        B, J = pose2d.shape[0], self.num_joint
+        p2 = pose2d.detach().reshape(B, J, 2).float().contiguous()
+        p3 = pose3d_mm.detach().reshape(B, J, 3).float().contiguous()
+        ft = feat.detach().reshape(B, J, 128).float().contiguous()
+        mesh = torch.empty((B, V_FULL, 3), dtype=torch.float32, device=dev)
+        coarse = torch.empty((B, V_COARSE, 3), dtype=torch.float32, device=dev) if want_coarse else None
+        if B > 0:
+            ws = self._workspace(B, dev)
+            a = _lib.MdrArgs(num_joint=J, batch=B, chunk=self.chunk, alpha=int(self.alpha), precision=self.precision,
+                             reserved=0, weights=table, pose2d=_lib.ptr(p2), pose3d=_lib.ptr(p3), feat=_lib.ptr(ft),
+                             mesh=_lib.ptr(mesh), coarse=_lib.ptr(coarse), workspace=_lib.ptr(ws),
+                             workspace_bytes=ws.numel())
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().gator_mdr_forward(a, _lib.stream_ptr()), 'gator_mdr_forward')
+        return (mesh, coarse) if want_coarse else mesh
+
+    def forward(self, x):
+        """x = pose_combine (B, J, 2+3+128), columns [pose2d | pose3d in metres | feat] (MDR.py:124-170)."""
+        return self.forward_parts(x[:, :, 0:2], x[:, :, 2:5] * 1000.0, x[:, :, 5:])
+
+
+def get_model(num_joint, embed_dim):
+    return MDR(num_joint, embed_dim)

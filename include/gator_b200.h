@@ -1,0 +1,267 @@
+/*
+ * gator_b200 - C ABI of the B200-native (sm_100a) GATOR pose->mesh forward path.
+ *
+ * The reference (kasvii/GATOR) is pure Python/PyTorch and has no FFI of its own; every entry point
+ * below replaces the ATen dispatch sequence of one reference `forward` (file:line relative to the
+ * reference root).  The host side (gator_b200/*.py) mirrors the reference's nn.Module interface and
+ * binds these symbols with ctypes.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name ends in _host;
+ *   - every buffer (inputs, packed weights, workspace, outputs) is allocated and owned by the caller
+ *     (PyTorch); the library never allocates or frees device memory and keeps no pointer after return;
+ *   - `stream` is a cudaStream_t passed as void*; no call synchronises the host, so every forward is
+ *     CUDA-graph capturable;
+ *   - return value: 0 on success, a negative gator_status otherwise; gator_last_error() gives a
+ *     thread-local message.  The library never throws and never exits.
+ *   - weights are passed as a table of pointers indexed by the slot enums below; the slot NAMES are
+ *     exported (gator_*_slot_name) so the Python packer binds by name, not by number.
+ */
+#ifndef GATOR_B200_H_
+#define GATOR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GATOR_ABI_VERSION 1
+
+typedef enum {
+  GATOR_OK = 0,
+  GATOR_ERR_BAD_ARG = -1,      /* null pointer, bad shape, misaligned buffer */
+  GATOR_ERR_WORKSPACE = -2,    /* workspace too small */
+  GATOR_ERR_LAUNCH = -3,       /* cudaGetLastError() after a launch */
+  GATOR_ERR_ARCH = -4,         /* device is not sm_100 */
+  GATOR_ERR_UNSUPPORTED = -5
+} gator_status;
+
+/* precision of the matrix products (accumulation is always fp32) */
+typedef enum {
+  GATOR_PREC_FP32 = 0,         /* FFMA everywhere: the <=1e-4 m parity path */
+  GATOR_PREC_BF16 = 1          /* tcgen05 bf16 operands where a tensor-core kernel exists */
+} gator_precision;
+
+int gator_abi_version(void);
+const char* gator_last_error(void);
+/* sizeof() of the ABI structs as compiled, so the ctypes mirror can be verified at load time:
+ * which = 0 gat, 1 mdr, 2 smpl, 3 csr, 4 gemm */
+size_t gator_abi_sizeof(int which);
+/* number of kernels this library has launched (process-wide); reset != 0 zeroes it after reading.
+ * bench.py reports it as `gpu_launches`. */
+long long gator_launch_count(int reset);
+
+/* ------------------------------------------------------------------------------------------------
+ * GAT lifter - replaces GAT.forward (lib/models/GAT.py:133-152) incl. GATBlock.forward (:33-43),
+ * Attention/MGCN/X_Feat/MLP (lib/models/backbones/modules.py:121-138,243-255,158-177,188-196),
+ * GraphLinear+GroupNorm embedding (GAT.py:69-72,135-144).  embed_dim=128, heads=8 (all call sites).
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum {
+  /* global */
+  GAT_EMB_W1 = 0,     /* (64,2)    GLinear.0.W                                   */
+  GAT_EMB_B1,         /* (64)      GLinear.0.b                                   */
+  GAT_GN_W,           /* (64)      GLinear.1.weight  (GroupNorm(4,64))            */
+  GAT_GN_B,           /* (64)      GLinear.1.bias                                */
+  GAT_EMB_W2T,        /* (64,128)  GLinear.3.W transposed                        */
+  GAT_EMB_B2,         /* (128)     GLinear.3.b                                   */
+  GAT_POS_CONST,      /* (J,128)   pos_id_embed(1..J) + pos_num_embed(row degree) */
+  GAT_ATTN_BIAS,      /* (8,J,J)   HopPathEncoding.forward() (modules.py:98-107)  */
+  GAT_HOP_MASK1,      /* (J,J)     1[hop<=1]  (modules.py:165-166)                */
+  GAT_HOP_MASK2,      /* (J,J)     1[hop==2]  (modules.py:167-168)                */
+  GAT_NORM_W,         /* (128)     norm.weight                                   */
+  GAT_NORM_B,         /* (128)                                                    */
+  GAT_LIFT_W,         /* (3J,128J) lifter.weight                                 */
+  GAT_LIFT_B,         /* (3J)                                                     */
+  GAT_NUM_GLOBAL
+} gator_gat_global_slot;
+
+typedef enum {
+  GATB_LN1_W = 0, GATB_LN1_B,       /* (128)                                          */
+  GATB_QKV_W, GATB_QKV_B,           /* (384,128),(384)                                */
+  GATB_PROJ_W, GATB_PROJ_B,         /* (128,128),(128)                                */
+  GATB_GCN_W01,                     /* (256,128) rows 0..127 = gcn.W[0]^T, 128..255 = gcn.W[1]^T */
+  GATB_GCN_M,                       /* (J,128)                                        */
+  GATB_GCN_ADIAG,                   /* (J)   diag of ((adj+adj2)+(adj+adj2)^T)/2       */
+  GATB_GCN_AOFF,                    /* (J,J) same matrix with the diagonal zeroed     */
+  GATB_GCN_BIAS,                    /* (128)                                          */
+  GATB_XF_W01, GATB_XF_B01,         /* (144,128),(144): x_feat.linears.0 ; linears.1   */
+  GATB_XF_WB, GATB_XF_BB,           /* (128,144),(128): x_feat.linearback             */
+  GATB_LN2_W, GATB_LN2_B,           /* (128)                                          */
+  GATB_FC1_W, GATB_FC1_B,           /* (512,128),(512)                                */
+  GATB_FC2_W, GATB_FC2_B,           /* (128,512),(128)                                */
+  GATB_NUM
+} gator_gat_block_slot;
+
+typedef struct {
+  int32_t num_joint;           /* J: 17 or 19 (any 2..32)                              */
+  int32_t depth;               /* number of GATBlocks (6 at every call site)           */
+  int32_t batch;               /* B                                                    */
+  int32_t chunk;               /* samples per pass through the workspace (0 = default) */
+  int32_t precision;           /* gator_precision                                      */
+  int32_t reserved;
+  const void* const* weights;  /* HOST array of GAT_NUM_GLOBAL + depth*GATB_NUM device pointers */
+  const float* pose2d;         /* (B,J,2)                                              */
+  float* pose3d;               /* (B,3J)   x_out, millimetres                          */
+  float* feat;                 /* (B,J,128) GELU(LN(x)) - second return of GAT.forward */
+  void* workspace;
+  size_t workspace_bytes;
+} gator_gat_args;
+
+const char* gator_gat_slot_name(int slot);        /* slot < GAT_NUM_GLOBAL: global; else block slot */
+size_t gator_gat_workspace_bytes(int32_t batch, int32_t num_joint, int32_t chunk);
+int gator_gat_forward(const gator_gat_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * MDR decoder - replaces MDR.forward (lib/models/MDR.py:124-170) incl. CrossAttentionBlock (:64-69),
+ * CrossAttention (:34-46), LayerNorm / MultiHeadedAttention
+ * (lib/models/vanilla_transformer_encoder.py:24-46,82-94), the MDR head (:156-166) and
+ * upsample_conv + template (:167-168).  The concat of GATOR.forward (GATOR.py:19) is folded in:
+ * the kernel reads pose2d, pose3d (mm) and feat separately.
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum {
+  MDR_JF_WFEAT = 0,   /* (64,128)   get_joint_feature.weight[:, 5:]                          */
+  MDR_JF_WPOSE,       /* (64,5)     get_joint_feature.weight[:, :5]                          */
+  MDR_JF_BIASROWS,    /* (J,64)     get_joint_feature.bias + pos_j_id_embed(1..J)            */
+  MDR_VF_CONST,       /* (431,64)   W_v[:, :3] @ init_vertices^T + b_v + pos_v_id_embed(1..431) */
+  MDR_VF_W3,          /* (64,3)     get_verts_feature.weight[:, 3:6]                         */
+  MDR_VJ,             /* (431) int32 nearest-joint table (graph_utils.py:71-89)              */
+  MDR_HEAD_W,         /* (28,64)    rows 0..22 motion_linear, 23..25 bias_linear, 26 scale_linear, 27 zero */
+  MDR_HEAD_B,         /* (28)                                                                 */
+  MDR_BNORM_SCALE,    /* alpha=0: (431) w/sqrt(rv+eps); alpha=1: (3) LayerNorm(3).weight      */
+  MDR_BNORM_SHIFT,    /* alpha=0: (431) b - rm*scale;   alpha=1: (3) LayerNorm(3).bias        */
+  MDR_BCONV_W,        /* (20,431,3) bias_conv1d.weight                                       */
+  MDR_BCONV_B,        /* (20)                                                                 */
+  MDR_UP_W,           /* (6890,1296) upsample_conv.weight flattened (431*3=1293), K zero-padded */
+  MDR_UP_BIAST,       /* (6890,3)   upsample_conv.bias[:,None] + init_vertices_6890            */
+  MDR_NUM_GLOBAL
+} gator_mdr_global_slot;
+
+typedef enum {
+  MDRL_N1_W = 0, MDRL_N1_B,         /* (64) encoder.norm1                                 */
+  MDRL_WQ,                          /* (64,64)  encoder.attn.wq.weight                    */
+  MDRL_WKV,                         /* (128,64) wk ; wv                                   */
+  MDRL_PROJ_W, MDRL_PROJ_B,         /* (64,64),(64)                                       */
+  MDRL_N2_W, MDRL_N2_B,             /* (64) encoder.norm2                                 */
+  MDRL_FC1_W, MDRL_FC1_B,           /* (256,64),(256)                                     */
+  MDRL_FC2_W, MDRL_FC2_B,           /* (64,256),(64)                                      */
+  MDRL_CLN_A, MDRL_CLN_B,           /* (64) norm.a_2, norm.b_2 (unbiased-std LayerNorm)   */
+  MDRL_SQKV_W, MDRL_SQKV_B,         /* (192,64),(192) selfatt.linears.0 ; 1 ; 2           */
+  MDRL_SO_W, MDRL_SO_B,             /* (64,64),(64)   selfatt.linears.3                   */
+  MDRL_NUM
+} gator_mdr_layer_slot;
+
+#define GATOR_MDR_LAYERS 3
+#define GATOR_V_FULL 6890
+#define GATOR_V_COARSE 431
+#define GATOR_UP_K 1296
+
+typedef struct {
+  int32_t num_joint;           /* J                                                     */
+  int32_t batch;               /* B                                                     */
+  int32_t chunk;               /* samples per pass (0 = default)                        */
+  int32_t alpha;               /* cfg.MODEL.alpha (MDR.py:115,162)                      */
+  int32_t precision;           /* gator_precision                                       */
+  int32_t reserved;
+  const void* const* weights;  /* HOST array of MDR_NUM_GLOBAL + 3*MDRL_NUM device pointers */
+  const float* pose2d;         /* (B,J,2)                                               */
+  const float* pose3d;         /* (B,J,3) millimetres (divided by 1000 inside)          */
+  const float* feat;           /* (B,J,128)                                             */
+  float* mesh;                 /* (B,6890,3) metres                                     */
+  float* coarse;               /* optional (B,431,3) coarse vertices, may be NULL        */
+  void* workspace;
+  size_t workspace_bytes;
+} gator_mdr_args;
+
+const char* gator_mdr_slot_name(int slot);
+size_t gator_mdr_workspace_bytes(int32_t batch, int32_t num_joint, int32_t chunk);
+int gator_mdr_forward(const gator_mdr_args* a, void* stream);
+/* The dominant kernel on its own, for roofline measurement: 2-head 431x431 self-attention core
+ * (vanilla_transformer_encoder.py:36-46) over qkv (B*431, 192) -> out (B*431, 64). */
+int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_t precision, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * SMPL linear blend skinning - replaces SMPL_Layer.forward
+ * (smplpytorch/smplpytorch/pytorch/smpl_layer.py:65-158), batch_rodrigues/quat2mat
+ * (rodrigues_layer.py:13-52) and the tensutils helpers (tensutils.py:6-48).
+ * ---------------------------------------------------------------------------------------------- */
+#define GATOR_SMPL_JOINTS 24
+#define GATOR_SMPL_K 220        /* 10 betas + 207 pose-map terms, zero-padded to a multiple of 4 */
+
+typedef struct {
+  int32_t batch;
+  int32_t center_idx;          /* -1 = None                                              */
+  int32_t has_betas;           /* 0: use th_betas buffer (smpl_layer.py:87-91)           */
+  int32_t has_trans;           /* 0: no translation given                                */
+  int32_t check_zero_norm;     /* 1: reproduce the reference's `norm(x)==0` switches on device */
+  int32_t weights_per_vertex;  /* ELL width of the skinning weights                      */
+  int32_t precision;
+  int32_t reserved;
+  const int32_t* parents;      /* (24) DEVICE int32 kintree parents, parents[0] ignored   */
+  const float* j_template;     /* (24,3)    J_regressor @ v_template                      */
+  const float* j_shapedirs;    /* (24,3,10) J_regressor @ shapedirs                       */
+  const float* default_betas;  /* (10)      th_betas buffer                               */
+  const float* blend_w;        /* (20670,220) [shapedirs | posedirs | 0] rows = (vertex,xyz) */
+  const float* v_template;     /* (20670)                                                 */
+  const int32_t* skin_idx;     /* (6890, weights_per_vertex) joint ids                    */
+  const float* skin_w;         /* (6890, weights_per_vertex)                              */
+  const float* pose;           /* (B,72) axis-angle                                       */
+  const float* betas;          /* (B,10) or NULL                                          */
+  const float* trans;          /* (B,3) or NULL                                           */
+  float* verts;                /* (B,6890,3)                                              */
+  float* jtr;                  /* (B,24,3)                                                */
+  void* workspace;
+  size_t workspace_bytes;
+} gator_smpl_args;
+
+size_t gator_smpl_workspace_bytes(int32_t batch);
+int gator_smpl_forward(const gator_smpl_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sparse resampling / regression - replaces spmm (lib/models/backbones/graph_layers.py:105-124) as
+ * used by Mesh.downsample/upsample (lib/models/backbones/mesh.py:93-123) and the J-regression
+ * post-step of every caller (lib/core/base.py:221, demo/run.py:142).
+ *   y[b, r, :] = scale * sum_k val[k] * x[b, col[k], :],  k in [rowptr[r], rowptr[r+1])
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch;               /* B (1 for a 2-D input)                                   */
+  int32_t rows;                /* output vertices per sample                              */
+  int32_t cols;                /* input vertices per sample                               */
+  int32_t feat;                /* trailing dimension (3 for xyz)                          */
+  float scale;                 /* 1.0f, or 1000.0f for the metres->millimetres of base.py:219 */
+  int32_t reserved;
+  const int32_t* rowptr;       /* (rows+1)                                                */
+  const int32_t* colidx;       /* (nnz)                                                   */
+  const float* values;         /* (nnz)                                                   */
+  const float* x;              /* (B, cols, feat)                                         */
+  float* y;                    /* (B, rows, feat)                                         */
+} gator_csr_args;
+
+int gator_csr_spmm(const gator_csr_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Building block exported for tests and micro-benchmarks:
+ *   C[m,n] = act( sum_k A[m,k] * W[n,k] + bias[n] + bias_rows[m % bias_period, n] ) + R[m,n]
+ * A (M,K) row-major lda, W (N,K) row-major ldw (torch Linear layout); K, lda, ldw multiples of 4.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t M, N, K;
+  int32_t lda, ldw, ldc, ldr;
+  int32_t act;                 /* 0 none, 1 exact-erf GELU                               */
+  int32_t bias_period;         /* rows of bias_rows (0 = unused)                         */
+  int32_t precision;
+  const float* A;
+  const float* W;
+  const float* bias;           /* (N) or NULL                                            */
+  const float* bias_rows;      /* (bias_period, N) or NULL                               */
+  const float* R;              /* (M, ldr) residual or NULL (may alias C)                */
+  float* C;
+} gator_gemm_args;
+
+int gator_gemm(const gator_gemm_args* a, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* GATOR_B200_H_ */

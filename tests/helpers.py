@@ -68,3 +68,44 @@ def oracle_setup(tag: str):
 
 def to_dtype(sd, dt):
     return {k: (v.to(dt) if v.is_floating_point() else v) for k, v in sd.items()}
+
+
+# ---------------------------------------------------------------------------------------------
+# product-side builders (gator_b200 modules); the CUDA library is only touched at forward time
+# ---------------------------------------------------------------------------------------------
+_BASE_ROOT = None
+
+
+def base_data_root() -> str:
+    """Synthetic data/base_data tree (written once per process) + gator_b200.config pointed at it."""
+    global _BASE_ROOT
+    import tempfile
+    from gator_b200 import config
+    if _BASE_ROOT is None:
+        _BASE_ROOT = tempfile.mkdtemp(prefix='gator_base_')
+        synthetic.write_base_data(_BASE_ROOT, regressor('h36m'))
+    config.configure(root=_BASE_ROOT)
+    return _BASE_ROOT
+
+
+def build_b200_gator(tag: str, device=None):
+    import scipy.sparse
+    from gator_b200 import config, graph
+    from gator_b200.models import GATOR
+    base_data_root()
+    category, alpha, regname = CONFIGS[tag]
+    config.configure(alpha=alpha)
+    J, skel, flip, _ = synthetic.joint_set(category)
+    adj = [scipy.sparse.csr_matrix(graph.build_adj(J, skel, flip))]
+    model = GATOR.get_model(J, 128, 6, adj, 1, torch.from_numpy(regressor(regname)))
+    synthetic.load_synth_weights(model)
+    model.eval()
+    if device is not None:
+        model = model.to(device)
+    return model
+
+
+def build_b200_smpl(center_idx=None, device=None):
+    from gator_b200.smpl_layer import SMPL_Layer
+    layer = SMPL_Layer.from_buffers(synthetic.smpl_buffers(), synthetic.SMPL_PARENTS, center_idx=center_idx).eval()
+    return layer.to(device) if device is not None else layer

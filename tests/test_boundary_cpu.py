@@ -1,0 +1,107 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header
+declares, the ctypes mirrors match the compiled structs, the replacement modules keep the reference's
+state_dict contract, and nothing silently falls back to the CPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, CONFIGS, build_b200_gator, build_b200_smpl, golden, key_spec, synthetic
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from gator_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, 'include', 'gator_b200.h')).read()
+    declared = set(re.findall(r'\b(gator_[a-z0-9_]+)\s*\(', hdr))
+    assert len(declared) >= 15
+    for name in declared:
+        assert hasattr(lib, name), name
+    from gator_b200 import _lib
+    assert declared == set(_lib.EXPORTS)
+
+
+def test_struct_mirrors_and_slot_names(lib):
+    from gator_b200 import _lib
+    g, b = _lib.slot_names('gat')
+    assert g[0] == 'EMB_W1' and g[-1] == 'LIFT_B' and len(g) == 14 and len(b) == 21
+    g, l = _lib.slot_names('mdr')
+    assert g[-1] == 'UP_BIAST' and len(g) == 14 and len(l) == 18
+    assert lib.gator_gat_workspace_bytes(64, 17, 0) > 0
+    assert lib.gator_mdr_workspace_bytes(64, 17, 0) > 0
+    assert lib.gator_smpl_workspace_bytes(64) > 0
+
+
+def test_error_reporting_without_gpu(lib):
+    from gator_b200 import _lib
+    a = _lib.GemmArgs(M=4, N=4, K=3, lda=3, ldw=3, ldc=4)       # K not a multiple of 4, null pointers
+    assert lib.gator_gemm(a, None) == -1
+    assert b'null' in lib.gator_last_error() or b'multiple' in lib.gator_last_error()
+    assert lib.gator_gat_forward(None, None) == -1
+
+
+@pytest.mark.parametrize('tag', ['h36m', 'coco'])
+def test_state_dict_contract(tag):
+    """Same keys, order, shapes and dtypes as the reference model (golden key list) -> strict load works."""
+    m = build_b200_gator(tag)
+    keys = [(k, tuple(v.shape), str(v.dtype).replace('torch.', '')) for k, v in m.state_dict().items()]
+    assert keys == key_spec(tag)
+    g = golden('gator')
+    assert (m.pose2mesh.vj_relation == g[f'{tag}/vj_relation']).all()
+    assert (m.pose_lifter.graph_adj.numpy() == g[f'{tag}/graph_adj']).all()
+    assert (m.pose_lifter.get_hop_path_encoding.edg_adj.numpy() == g[f'{tag}/edge_input']).all()
+    assert (m.pose2mesh.init_vertices.numpy() == g[f'{tag}/init_vertices_431']).all()
+    # a checkpoint round trip through torch.save, as funcs_utils.save/load_checkpoint do
+    import io
+    buf = io.BytesIO()
+    torch.save({'model_state_dict': m.state_dict()}, buf)
+    buf.seek(0)
+    m.load_state_dict(torch.load(buf)['model_state_dict'], strict=True)
+    assert m.pose_lifter._packed is None and m.pose2mesh._packed is None
+
+
+def test_no_cpu_fallback():
+    m = build_b200_gator('h36m')
+    x = torch.from_numpy(synthetic.poses2d(2, 17))
+    with pytest.raises(RuntimeError):
+        m(x)
+    with pytest.raises(NotImplementedError):
+        m.train()(x)
+    s = build_b200_smpl()
+    with pytest.raises(RuntimeError):
+        s(torch.zeros(1, 72))
+
+
+def test_unsupported_configurations_fail_loudly():
+    from gator_b200.models import GAT
+    with pytest.raises(NotImplementedError):
+        GAT.GAT(num_joint=17, embed_dim=256, depth=4, graph_adj=[np.eye(17)], J_regressor=torch.zeros(17, 6890))
+
+
+@pytest.mark.needs_reference
+def test_install_rebinds_reference_modules():
+    import tempfile
+    from oracle import refshim
+    import gator_b200
+    refshim.install_shims()
+    root = tempfile.mkdtemp()
+    synthetic.write_base_data(root)
+    with refshim.chdir(root):
+        import models.GATOR as ref_GATOR          # the reference module
+        orig = ref_GATOR.GATOR
+        try:
+            done = gator_b200.install()
+            from gator_b200.models import GATOR as b
+            assert ref_GATOR.GATOR is b.GATOR and 'models.GATOR.get_model' in done
+        finally:
+            ref_GATOR.GATOR = orig
+            import importlib
+            for name in ('models.GATOR', 'models.GAT', 'models.MDR', 'models.backbones.mesh'):
+                importlib.reload(importlib.import_module(name))

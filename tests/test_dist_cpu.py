@@ -1,0 +1,48 @@
+"""World-size-2 gloo test of the multi-GPU host logic (sharding + optional gather) on CPU."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from gator_b200.dist import gather_meshes, shard_range
+
+
+def test_shard_range_partitions():
+    for total in (0, 1, 7, 4096, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def _worker(rank, world, port, total, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    full = torch.arange(total * 5 * 3, dtype=torch.float32).reshape(total, 5, 3)
+    lo, hi = shard_range(total, world, rank)
+    got = gather_meshes(full[lo:hi].clone(), total)
+    q.put((rank, bool(torch.equal(got, full))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('total', [8, 7])
+def test_gather_world2_gloo(total):
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, total, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]

@@ -1,0 +1,212 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the reference golden vectors.
+
+Tolerances: fp32 path <= 1e-4 m max-abs vertex error (north_star); pose3d is in millimetres (|x| ~ 300)
+so its bound is 1e-4 m = 0.1 mm.  In practice the fp32 path lands ~1e-6 m.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import (CONFIGS, build_b200_gator, build_b200_smpl, golden, oracle_setup, orc, regressor,
+                     synthetic)
+
+pytestmark = pytest.mark.gpu
+TOL_M = 1e-4
+DEV = 'cuda:0'
+
+
+@pytest.fixture(scope='module')
+def models():
+    from gator_b200 import build
+    build.build()
+    return {tag: build_b200_gator(tag, DEV) for tag in CONFIGS}
+
+
+def _gemm(A, W, bias=None, bias_rows=None, R=None, act=0, ldc=None):
+    from gator_b200 import _lib
+    M, K = A.shape
+    N = W.shape[0]
+    ldc = ldc or N
+    Cbuf = torch.zeros((M, ldc), device=DEV)
+    a = _lib.GemmArgs(M=M, N=N, K=K, lda=A.stride(0), ldw=W.stride(0), ldc=ldc, ldr=R.stride(0) if R is not None else 0,
+                      act=act, bias_period=bias_rows.shape[0] if bias_rows is not None else 0, precision=0,
+                      A=_lib.ptr(A), W=_lib.ptr(W), bias=_lib.ptr(bias), bias_rows=_lib.ptr(bias_rows),
+                      R=_lib.ptr(R), C=_lib.ptr(Cbuf))
+    _lib.check(_lib.lib().gator_gemm(a, _lib.stream_ptr()), 'gator_gemm')
+    return Cbuf[:, :N]
+
+
+@pytest.mark.parametrize('M,N,K', [(1, 64, 64), (77, 51, 2176), (300, 144, 128), (129, 6890, 1296), (1000, 28, 64),
+                                   (513, 384, 128), (19, 57, 2432)])
+def test_gemm_f32(models, M, N, K):
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g)
+    W = torch.randn(N, K, generator=g) / K ** 0.5
+    bias = torch.randn(N, generator=g)
+    rows = torch.randn(5, N, generator=g)
+    R = torch.randn(M, N, generator=g)
+    ref = torch.nn.functional.gelu(A.double() @ W.double().t() + bias.double() + rows.double()[torch.arange(M) % 5]) + R.double()
+    out = _gemm(A.to(DEV), W.to(DEV), bias.to(DEV), rows.to(DEV), R.to(DEV), act=1)
+    assert (out.cpu().double() - ref).abs().max() < 2e-5
+    out = _gemm(A.to(DEV), W.to(DEV))
+    assert (out.cpu().double() - A.double() @ W.double().t()).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize('tag', ['h36m', 'coco'])
+def test_gator_forward_matches_reference_golden(models, tag):
+    """BASELINE configs 1/2 inputs: reference outputs stored in tests/golden/gator.npz."""
+    g = golden('gator')
+    m = models[tag]
+    x = torch.from_numpy(g[f'{tag}/pose2d']).to(DEV)
+    with torch.no_grad():
+        mesh, pose3d = m(x)
+    assert mesh.shape == (len(x), 6890, 3) and pose3d.shape == (len(x), m.num_joint, 3)
+    err = np.abs(mesh.cpu().numpy() - g[f'{tag}/mesh']).max()
+    perr = np.abs(pose3d.cpu().numpy() - g[f'{tag}/pose3d']).max()
+    print(f'{tag}: mesh max-abs err {err:.3e} m, pose3d err {perr:.3e} mm')
+    assert err <= TOL_M and perr <= 0.1
+    # stage outputs
+    p3, feat = m.pose_lifter(x.view(len(x), -1))
+    assert np.abs(feat.cpu().numpy() - g[f'{tag}/feat']).max() <= 1e-4
+    _, coarse = m.pose2mesh.forward_parts(x, p3.view(len(x), -1, 3), feat, want_coarse=True)
+    assert np.abs(coarse.cpu().numpy() - g[f'{tag}/trace/mdr_coarse']).max() <= 1e-4
+    # demo path (run.py:140-141): called without no_grad, then J-regressed
+    mesh2, _ = m(x)
+    assert torch.equal(mesh2, mesh)
+
+
+@pytest.mark.parametrize('tag', ['h36m', 'coco'])
+def test_gator_forward_batch64_vs_oracle(models, tag):
+    """BASELINE config 2: batch 64 fp32 tolerance check against the CPU oracle on the same weights."""
+    sd, gc, mc, alpha = oracle_setup(tag)
+    J = gc['J']
+    x = torch.from_numpy(synthetic.poses2d(64, J, seed=11))
+    with torch.no_grad():
+        ref_mesh, ref_p3 = orc.gator_forward(sd, gc, mc, x, alpha)
+        mesh, p3 = models[tag](x.to(DEV))
+    err = (mesh.cpu() - ref_mesh).abs().max().item()
+    print(f'{tag} B=64: mesh max-abs err {err:.3e} m')
+    assert err <= TOL_M
+    assert (p3.cpu() - ref_p3).abs().max().item() <= 0.1
+
+
+def test_edge_batches_and_chunking(models):
+    """Empty batch, batch 1, ragged chunking: per-sample results do not depend on how the batch is cut."""
+    m = models['h36m']
+    x = torch.from_numpy(synthetic.poses2d(7, 17, seed=5)).to(DEV)
+    mesh, p3 = m(x)
+    e_mesh, e_p3 = m(x[:0])
+    assert e_mesh.shape == (0, 6890, 3) and e_p3.shape == (0, 17, 3)
+    one, _ = m(x[3:4])
+    assert torch.equal(one[0], mesh[3])
+    m.pose_lifter.chunk, m.pose2mesh.chunk = 3, 2
+    try:
+        mesh_c, p3_c = m(x)
+    finally:
+        m.pose_lifter.chunk, m.pose2mesh.chunk = 0, 0
+    assert torch.equal(mesh_c, mesh) and torch.equal(p3_c, p3)
+    # non-contiguous / (B, 2J) views as LiftTester passes them (base.py:348-349)
+    p3v, _ = m.pose_lifter(x.view(7, -1))
+    assert torch.equal(p3v.view(7, 17, 3), p3)
+
+
+def test_full_size_batch_is_sample_independent(models):
+    """BASELINE config 4 size (B=4096): every sample equals its own batch-1 forward (bit-exact), finite."""
+    m = models['coco']
+    base = golden('fixtures')['demo_pose19']
+    x = torch.from_numpy(synthetic.coco_poses2d(base, 4096)).to(DEV)
+    mesh, p3 = m(x)
+    assert torch.isfinite(mesh).all() and torch.isfinite(p3).all()
+    for i in (0, 147, 148, 2047, 4095):
+        mi, pi = m(x[i:i + 1])
+        assert torch.equal(mi[0], mesh[i]) and torch.equal(pi[0], p3[i])
+
+
+def test_state_dict_reload_repacks(models):
+    m = models['h36m']
+    x = torch.from_numpy(synthetic.poses2d(2, 17)).to(DEV)
+    a, _ = m(x)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    sd2 = dict(sd)
+    sd2['pose2mesh.upsample_conv.bias'] = sd['pose2mesh.upsample_conv.bias'] + 1.0
+    m.load_state_dict(sd2, strict=True)
+    b, _ = m(x)
+    m.load_state_dict(sd, strict=True)
+    c, _ = m(x)
+    assert torch.allclose(b, a + 1.0, atol=1e-5) and torch.equal(c, a)
+
+
+def test_smpl_layer_matches_reference_golden():
+    s = golden('smpl')
+    pose, betas, trans = [torch.from_numpy(a).to(DEV) for a in synthetic.smpl_inputs(4)]
+    layer = build_b200_smpl(device=DEV)
+    v, j = layer(pose, betas, trans)
+    assert np.abs(v.cpu().numpy() - s['full/verts']).max() <= 1e-5 and np.abs(j.cpu().numpy() - s['full/jtr']).max() <= 1e-5
+    v, j = layer(pose)
+    assert np.abs(v.cpu().numpy()[:2] - s['nobetas/verts']).max() <= 1e-5 and np.abs(j.cpu().numpy() - s['nobetas/jtr']).max() <= 1e-5
+    layer_c = build_b200_smpl(center_idx=0, device=DEV)
+    v, j = layer_c(pose, betas)
+    assert np.abs(v.cpu().numpy()[:2] - s['center/verts']).max() <= 1e-5 and np.abs(j.cpu().numpy() - s['center/jtr']).max() <= 1e-5
+
+
+def test_smpl_layer_zero_norm_switches_and_chunks():
+    """smpl_layer.py:87,148: all-zero betas fall back to th_betas; all-zero trans enables centring.
+    B=600 crosses the 512-sample workspace chunk."""
+    buf = {k: torch.from_numpy(v) for k, v in synthetic.smpl_buffers().items()}
+    buf['th_betas'] = torch.full((1, 10), 0.3)
+    from gator_b200.smpl_layer import SMPL_Layer
+    layer = SMPL_Layer.from_buffers(buf, synthetic.SMPL_PARENTS, center_idx=3).eval().to(DEV)
+    pose, betas, trans = [torch.from_numpy(a) for a in synthetic.smpl_inputs(600)]
+    for bt, tr in ((betas, trans), (torch.zeros_like(betas), trans), (betas, torch.zeros_like(trans)), (betas, None)):
+        rv, rj, _ = orc.smpl_forward(buf, synthetic.SMPL_PARENTS, pose, bt, tr, center_idx=3)
+        args = [pose.to(DEV), bt.to(DEV)] + ([tr.to(DEV)] if tr is not None else [])
+        v, j = layer(*args)
+        assert (v.cpu() - rv).abs().max() <= 2e-5 and (j.cpu() - rj).abs().max() <= 2e-5
+    e_v, e_j = layer(pose[:0].to(DEV))
+    assert e_v.shape == (0, 6890, 3) and e_j.shape == (0, 24, 3)
+
+
+def test_smpl_full_size_properties():
+    """BASELINE config 3 size (B=16384): zero pose + zero betas reproduces the template exactly up to the
+    joint-transform round trip; translation is additive."""
+    layer = build_b200_smpl(device=DEV)
+    B = 16384
+    pose, betas, trans = [torch.from_numpy(a).to(DEV) for a in synthetic.smpl_inputs(B)]
+    v0, j0 = layer(pose, betas)
+    v1, j1 = layer(pose, betas, trans)
+    assert torch.isfinite(v0).all()
+    assert (v1 - trans[:, None] - v0).abs().max() <= 1e-5 and (j1 - trans[:, None] - j0).abs().max() <= 1e-5
+    zv, _ = layer(torch.zeros(3, 72, device=DEV))
+    assert (zv - layer.th_v_template).abs().max() <= 1e-5
+
+
+def test_mesh_resampling_matches_reference_golden():
+    import os
+    from gator_b200.mesh import Mesh
+    from helpers import base_data_root
+    mesh = Mesh(os.path.join(base_data_root(), 'data', 'base_data', 'mesh_downsampling.npz'), device=torch.device(DEV))
+    m = golden('mesh')
+    x = torch.from_numpy(m['x']).to(DEV)
+    d1 = mesh.downsample(x)
+    d2 = mesh.downsample(d1, n1=1, n2=2)
+    u1 = mesh.upsample(d2, n1=2, n2=1)
+    u0 = mesh.upsample(u1, n1=1, n2=0)
+    for a, k in ((d1, 'down1'), (d2, 'down2'), (u1, 'up1'), (u0, 'up0')):
+        assert np.abs(a.cpu().numpy() - m[k]).max() <= 1e-6, k
+    assert np.abs(mesh.downsample(x[0], n1=0, n2=2).cpu().numpy() - m['down2d']).max() <= 1e-6
+    assert mesh.upsample(d2[:0], n1=2, n2=0).shape == (0, 6890, 3)
+    # idempotence-style property at size: up(down(up(c))) == up(c) because D selects vertices U reproduces?
+    # (not guaranteed for synthetic U/D) -> use linearity instead
+    big = torch.randn(4096, 431, 3, device=DEV)
+    a, b = mesh.upsample(big, n1=2, n2=0), mesh.upsample(2.0 * big, n1=2, n2=0)
+    assert torch.allclose(b, 2.0 * a, atol=1e-5)
+
+
+def test_joint_regression_post_step(models):
+    from gator_b200.ops import JointRegressor
+    g = golden('gator')
+    reg = JointRegressor(regressor('h36m'), device=DEV)
+    mesh = torch.from_numpy(g['h36m/mesh']).to(DEV)
+    j = reg(mesh)
+    assert np.abs(j.cpu().numpy() - g['h36m/joints']).max() <= 1e-6
+    assert torch.allclose(reg(mesh, scale=1000.0), j * 1000.0, rtol=1e-6)
