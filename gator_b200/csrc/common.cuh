@@ -46,6 +46,19 @@ struct Epilogue {
 int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
              const Epilogue& epi, cudaStream_t stream);
 
+// Same contract on the tensor cores: A fp32 (converted to bf16 in-kernel), W pre-packed bf16 in the UMMA
+// shared-memory image (see umma_weight_layout / gator_b200/packing.py), fp32 accumulate in TMEM.
+int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, float* C, int ldc, int M, int N, int K,
+                   const Epilogue& epi, cudaStream_t stream);
+void umma_weight_layout(int N, int K, int* BN, int* n_tiles, int* K_pad);
+
+// precision dispatch used by the stage drivers: bf16 only if a packed weight exists for the slot
+inline int gemm(int precision, const float* A, int lda, const float* W, int ldw, const void* Wpacked, float* C, int ldc,
+                int M, int N, int K, const Epilogue& epi, cudaStream_t stream) {
+  if (precision == GATOR_PREC_BF16 && Wpacked) return gemm_bf16_umma(A, lda, Wpacked, C, ldc, M, N, K, epi, stream);
+  return gemm_f32(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
+}
+
 // LayerNorm over the last dim (C = 64 or 128).  mode 0: nn.LayerNorm (eps 1e-5, biased var);
 // mode 1: a*(x-mean)/(std_unbiased+1e-6)+b (vanilla_transformer_encoder.py:31-34).  gelu: apply after.
 int layernorm_rows(const float* x, float* y, const float* w, const float* b, int rows, int C, int mode,

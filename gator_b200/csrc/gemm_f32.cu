@@ -177,7 +177,6 @@ int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc
 extern "C" int gator_gemm(const gator_gemm_args* a, void* stream) {
   using namespace gator;
   GATOR_REQUIRE(a, "gator_gemm: null args");
-  GATOR_REQUIRE(a->precision == GATOR_PREC_FP32, "gator_gemm: only GATOR_PREC_FP32 is routed here");
   Epilogue e;
   e.bias = a->bias;
   e.bias_rows = a->bias_rows;
@@ -185,5 +184,8 @@ extern "C" int gator_gemm(const gator_gemm_args* a, void* stream) {
   e.act = a->act;
   e.R = a->R;
   e.ldr = a->ldr;
-  return gemm_f32(a->A, a->lda, a->W, a->ldw, a->C, a->ldc, a->M, a->N, a->K, e, (cudaStream_t)stream);
+  if (a->precision == GATOR_PREC_BF16)   // W = bf16 weights packed by gator_b200.packing.pack_umma_weight
+    return gemm_bf16_umma(a->A, a->lda, a->W, a->C, a->ldc, a->M, a->N, a->K, e, (cudaStream_t)stream);
+  GATOR_REQUIRE(a->precision == GATOR_PREC_FP32, "gator_gemm: bad precision");
+  return gemm_f32(a->A, a->lda, static_cast<const float*>(a->W), a->ldw, a->C, a->ldc, a->M, a->N, a->K, e, (cudaStream_t)stream);
 }

@@ -29,7 +29,7 @@ class GATOR(nn.Module):
     def forward(self, pose2d):
         """pose2d (B,J,2) -> (cam_mesh (B,6890,3) metres, pose3d (B,J,3) millimetres)  (GATOR.py:16-22).
         The (B,J,133) concat is never materialised; the /1000 happens inside the MDR embedding kernel."""
-        pose3d, pose3d_feat = self.pose_lifter(pose2d.reshape(len(pose2d), -1))
+        pose3d, pose3d_feat = self.pose_lifter(pose2d.reshape(len(pose2d), self.num_joint * 2))
         pose3d = pose3d.reshape(-1, self.num_joint, 3)
         cam_mesh = self.pose2mesh.forward_parts(pose2d, pose3d, pose3d_feat)
         return cam_mesh, pose3d

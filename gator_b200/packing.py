@@ -1,0 +1,28 @@
+"""Weight packing for the tcgen05 kernels (run once per pack(), on the device, with torch ops)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def umma_weight_layout(N: int, K: int):
+    """(BN, n_tiles, K_pad) as chosen by the library (csrc/umma_gemm.cu: umma_weight_layout)."""
+    bn, nt, kp = C.c_int32(), C.c_int32(), C.c_int32()
+    _lib.check(_lib.lib().gator_umma_weight_layout(N, K, C.byref(bn), C.byref(nt), C.byref(kp)), 'gator_umma_weight_layout')
+    return bn.value, nt.value, kp.value
+
+
+@torch.no_grad()
+def pack_umma_weight(W: torch.Tensor) -> torch.Tensor:
+    """W (N,K) float -> bf16 [N_pad/8, K_pad/8, 8, 8]: 8x8 core matrices, K-major, no swizzle - exactly the
+    shared-memory image tcgen05.mma reads, so the kernel stages it with linear 16-byte copies."""
+    N, K = W.shape
+    BN, n_tiles, K_pad = umma_weight_layout(N, K)
+    N_pad = BN * n_tiles
+    Wp = torch.zeros((N_pad, K_pad), dtype=torch.float32, device=W.device)
+    Wp[:N, :K] = W.float()
+    Wp = Wp.reshape(N_pad // 8, 8, K_pad // 8, 8).permute(0, 2, 1, 3).contiguous()
+    return Wp.to(torch.bfloat16).contiguous()

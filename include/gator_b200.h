@@ -252,7 +252,7 @@ typedef struct {
   int32_t bias_period;         /* rows of bias_rows (0 = unused)                         */
   int32_t precision;
   const float* A;
-  const float* W;
+  const void* W;               /* fp32 (N,K) for GATOR_PREC_FP32; packed bf16 (see below) for GATOR_PREC_BF16 */
   const float* bias;           /* (N) or NULL                                            */
   const float* bias_rows;      /* (bias_period, N) or NULL                               */
   const float* R;              /* (M, ldr) residual or NULL (may alias C)                */
@@ -260,6 +260,10 @@ typedef struct {
 } gator_gemm_args;
 
 int gator_gemm(const gator_gemm_args* a, void* stream);
+
+/* Layout of a bf16 weight packed for the tcgen05 GEMM: W (N,K) is zero-padded to (n_tiles*BN, K_pad) and
+ * stored as [N_pad/8][K_pad/8][8][8] bf16 (8x8 core matrices, the UMMA K-major no-swizzle smem image). */
+int gator_umma_weight_layout(int32_t N, int32_t K, int32_t* BN, int32_t* n_tiles, int32_t* K_pad);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,65 @@
+"""GPU probe for the tcgen05 GEMM: compares against an exact product of the bf16-rounded operands and,
+on mismatch, prints where the result goes wrong (layout debugging aid)."""
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gator_b200 import _lib
+from gator_b200.packing import pack_umma_weight, umma_weight_layout
+
+dev = 'cuda:0'
+
+
+def run(M, N, K, act=0, bias=True, res=True, rows=0):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    b = torch.randn(N, generator=g).to(dev) if bias else None
+    R = torch.randn(M, N, generator=g).to(dev) if res else None
+    br = torch.randn(rows, N, generator=g).to(dev) if rows else None
+    Wp = pack_umma_weight(W)
+    C = torch.full((M, N), float('nan'), device=dev)
+    a = _lib.GemmArgs(M=M, N=N, K=K, lda=K, ldw=K, ldc=N, ldr=N if res else 0, act=act, bias_period=rows, precision=1,
+                      A=_lib.ptr(A), W=_lib.ptr(Wp), bias=_lib.ptr(b), bias_rows=_lib.ptr(br), R=_lib.ptr(R), C=_lib.ptr(C))
+    _lib.check(_lib.lib().gator_gemm(a, _lib.stream_ptr()), 'gator_gemm')
+    torch.cuda.synchronize()
+    ref = A.bfloat16().double() @ W.bfloat16().double().t()
+    if bias: ref = ref + b.double()
+    if rows: ref = ref + br.double()[torch.arange(M, device=dev) % rows]
+    if act: ref = torch.nn.functional.gelu(ref)
+    if res: ref = ref + R.double()
+    err = (C.double() - ref).abs()
+    bad = ~(err < 2e-3)
+    print(f'M={M} N={N} K={K} layout={umma_weight_layout(N, K)} max_err={err.nan_to_num(9e9).max().item():.3e} bad={int(bad.sum())}/{M*N}')
+    if bad.any():
+        rows_bad = bad.any(1).nonzero().flatten()[:8].tolist()
+        cols_bad = bad.any(0).nonzero().flatten()[:8].tolist()
+        print('   first bad rows', rows_bad, 'cols', cols_bad)
+        print('   C[0,:8]  ', C[0, :8].tolist())
+        print('   ref[0,:8]', ref[0, :8].float().tolist())
+        # does C match a permutation of rows/cols?  correlate row 0 of C against all ref rows
+        c0 = C[0].double().nan_to_num(0)
+        corr = (ref - ref.mean(1, keepdim=True)) @ (c0 - c0.mean())
+        print('   row of ref best matching C[0]:', int(corr.argmax()))
+    return not bad.any()
+
+
+ok = True
+for shp in [(128, 64, 64), (128, 32, 64), (256, 64, 128), (300, 192, 64), (1000, 64, 256), (77, 144, 128), (500, 512, 128),
+            (130, 128, 512), (64, 57, 2432), (444, 6890, 1296), (100, 20670, 220), (431 * 8, 28, 64)]:
+    ok &= run(*shp, act=0, bias=False, res=False)
+ok &= run(300, 192, 64, act=1, bias=True, res=True, rows=5)
+ok &= run(1000, 28, 64, act=0, bias=True, res=False)
+print('ALL OK' if ok else 'FAILURES')
+# timing
+for (M, N, K) in [(148 * 431, 64, 64), (148 * 431, 256, 64), (148 * 431, 64, 256), (12288, 6890, 1296), (16384, 20670, 220)]:
+    A = torch.randn(M, K, device=dev); W = torch.randn(N, K, device=dev); Wp = pack_umma_weight(W); C = torch.empty(M, N, device=dev)
+    for prec, Wx, ldw in ((1, Wp, K), (0, W, K)):
+        a = _lib.GemmArgs(M=M, N=N, K=K, lda=K, ldw=ldw, ldc=N, ldr=0, act=0, bias_period=0, precision=prec,
+                          A=_lib.ptr(A), W=_lib.ptr(Wx), bias=None, bias_rows=None, R=None, C=_lib.ptr(C))
+        for _ in range(2): _lib.lib().gator_gemm(a, _lib.stream_ptr())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10): _lib.lib().gator_gemm(a, _lib.stream_ptr())
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f'  M={M} N={N} K={K} prec={prec}: {ms*1e3:.1f} us  {2*M*N*K/ms/1e9:.1f} TFLOP/s  {(M*K+M*N)*4/ms/1e6:.0f} GB/s')
