@@ -21,14 +21,16 @@ c_int_p = C.POINTER(C.c_int32)
 class GatArgs(C.Structure):
     _fields_ = [('num_joint', C.c_int32), ('depth', C.c_int32), ('batch', C.c_int32), ('chunk', C.c_int32),
                 ('precision', C.c_int32), ('reserved', C.c_int32),
-                ('weights', C.POINTER(C.c_void_p)), ('pose2d', C.c_void_p), ('pose3d', C.c_void_p),
+                ('weights', C.POINTER(C.c_void_p)), ('weights_bf16', C.POINTER(C.c_void_p)),
+                ('pose2d', C.c_void_p), ('pose3d', C.c_void_p),
                 ('feat', C.c_void_p), ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
 
 
 class MdrArgs(C.Structure):
     _fields_ = [('num_joint', C.c_int32), ('batch', C.c_int32), ('chunk', C.c_int32), ('alpha', C.c_int32),
                 ('precision', C.c_int32), ('reserved', C.c_int32),
-                ('weights', C.POINTER(C.c_void_p)), ('pose2d', C.c_void_p), ('pose3d', C.c_void_p),
+                ('weights', C.POINTER(C.c_void_p)), ('weights_bf16', C.POINTER(C.c_void_p)),
+                ('pose2d', C.c_void_p), ('pose3d', C.c_void_p),
                 ('feat', C.c_void_p), ('mesh', C.c_void_p), ('coarse', C.c_void_p),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
 
@@ -38,7 +40,8 @@ class SmplArgs(C.Structure):
                 ('check_zero_norm', C.c_int32), ('weights_per_vertex', C.c_int32), ('precision', C.c_int32),
                 ('reserved', C.c_int32),
                 ('parents', C.c_void_p), ('j_template', C.c_void_p), ('j_shapedirs', C.c_void_p),
-                ('default_betas', C.c_void_p), ('blend_w', C.c_void_p), ('v_template', C.c_void_p),
+                ('default_betas', C.c_void_p), ('blend_w', C.c_void_p), ('blend_w_bf16', C.c_void_p),
+                ('v_template', C.c_void_p),
                 ('skin_idx', C.c_void_p), ('skin_w', C.c_void_p), ('pose', C.c_void_p), ('betas', C.c_void_p),
                 ('trans', C.c_void_p), ('verts', C.c_void_p), ('jtr', C.c_void_p),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]

@@ -231,6 +231,8 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
     return GATOR_ERR_WORKSPACE;
   }
   auto G = [&](int s) { return static_cast<const float*>(a->weights[s]); };
+  auto GB = [&](int s) -> const void* { return a->weights_bf16 ? a->weights_bf16[s] : nullptr; };
+  const int prec = a->precision;
   const int cb = resolve_chunk(B, a->chunk);
   const size_t rows_max = (size_t)cb * J;
   float* ws = static_cast<float*>(a->workspace);
@@ -257,13 +259,14 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
     for (int l = 0; l < a->depth; ++l) {
       const int base = GAT_NUM_GLOBAL + l * GATB_NUM;
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
+      auto WB = [&](int s) -> const void* { return a->weights_bf16 ? a->weights_bf16[base + s] : nullptr; };
       GATOR_TRY(layernorm_rows(x, n, W(GATB_LN1_W), W(GATB_LN1_B), M, C, 0, 0, stream));
       Epilogue e;
       e.bias = W(GATB_QKV_B);
-      GATOR_TRY(gemm_f32(n, C, W(GATB_QKV_W), C, big, 3 * C, M, 3 * C, C, e, stream));
+      GATOR_TRY(gemm(prec, n, C, W(GATB_QKV_W), C, WB(GATB_QKV_W), big, 3 * C, M, 3 * C, C, e, stream));
       gat_attn_kernel<<<nb, 256, attn_smem, stream>>>(big, G(GAT_ATTN_BIAS), o, J);
       GATOR_TRY(check_launch("gat_attn"));
-      GATOR_TRY(gemm_f32(n, C, W(GATB_GCN_W01), C, h, 2 * C, M, 2 * C, C, Epilogue(), stream));
+      GATOR_TRY(gemm(prec, n, C, W(GATB_GCN_W01), C, WB(GATB_GCN_W01), h, 2 * C, M, 2 * C, C, Epilogue(), stream));
       gat_gcn_mix_kernel<<<nb, 128, 0, stream>>>(h, W(GATB_GCN_M), W(GATB_GCN_ADIAG), W(GATB_GCN_AOFF),
                                                  W(GATB_GCN_BIAS), g, J);
       GATOR_TRY(check_launch("gat_gcn_mix"));
@@ -272,11 +275,11 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
       e.bias = W(GATB_PROJ_B);
       e.R = g;
       e.ldr = C;
-      GATOR_TRY(gemm_f32(o, C, W(GATB_PROJ_W), C, n, C, M, C, C, e, stream));
+      GATOR_TRY(gemm(prec, o, C, W(GATB_PROJ_W), C, WB(GATB_PROJ_W), n, C, M, C, C, e, stream));
       // y = [L0(s) | L1(s)] -> h (ld 144)
       e = Epilogue();
       e.bias = W(GATB_XF_B01);
-      GATOR_TRY(gemm_f32(n, C, W(GATB_XF_W01), C, h, 144, M, 144, C, e, stream));
+      GATOR_TRY(gemm(prec, n, C, W(GATB_XF_W01), C, WB(GATB_XF_W01), h, 144, M, 144, C, e, stream));
       gat_hop_mix_kernel<<<nb, 160, 0, stream>>>(h, G(GAT_HOP_MASK1), G(GAT_HOP_MASK2), big, J);
       GATOR_TRY(check_launch("gat_hop_mix"));
       // x = x + linearback(f)
@@ -284,24 +287,24 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
       e.bias = W(GATB_XF_BB);
       e.R = x;
       e.ldr = C;
-      GATOR_TRY(gemm_f32(big, 144, W(GATB_XF_WB), 144, x, C, M, C, 144, e, stream));
+      GATOR_TRY(gemm(prec, big, 144, W(GATB_XF_WB), 144, WB(GATB_XF_WB), x, C, M, C, 144, e, stream));
       // x = x + fc2(gelu(fc1(LN2(x))))
       GATOR_TRY(layernorm_rows(x, n, W(GATB_LN2_W), W(GATB_LN2_B), M, C, 0, 0, stream));
       e = Epilogue();
       e.bias = W(GATB_FC1_B);
       e.act = 1;
-      GATOR_TRY(gemm_f32(n, C, W(GATB_FC1_W), C, big, 4 * C, M, 4 * C, C, e, stream));
+      GATOR_TRY(gemm(prec, n, C, W(GATB_FC1_W), C, WB(GATB_FC1_W), big, 4 * C, M, 4 * C, C, e, stream));
       e = Epilogue();
       e.bias = W(GATB_FC2_B);
       e.R = x;
       e.ldr = C;
-      GATOR_TRY(gemm_f32(big, 4 * C, W(GATB_FC2_W), 4 * C, x, C, M, C, 4 * C, e, stream));
+      GATOR_TRY(gemm(prec, big, 4 * C, W(GATB_FC2_W), 4 * C, WB(GATB_FC2_W), x, C, M, C, 4 * C, e, stream));
     }
     float* feat = a->feat + (size_t)b0 * J * C;
     GATOR_TRY(layernorm_rows(x, feat, G(GAT_NORM_W), G(GAT_NORM_B), M, C, 0, 1, stream));
     Epilogue e;
     e.bias = G(GAT_LIFT_B);
-    GATOR_TRY(gemm_f32(feat, J * C, G(GAT_LIFT_W), J * C, a->pose3d + (size_t)b0 * 3 * J, 3 * J, nb, 3 * J, J * C, e, stream));
+    GATOR_TRY(gemm(prec, feat, J * C, G(GAT_LIFT_W), J * C, GB(GAT_LIFT_W), a->pose3d + (size_t)b0 * 3 * J, 3 * J, nb, 3 * J, J * C, e, stream));
   }
   return GATOR_OK;
 }

@@ -388,8 +388,9 @@ int launch_self_attn(const float* qkv, float* out, int nb, cudaStream_t stream) 
 extern "C" int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_t precision, void* stream) {
   using namespace gator;
   GATOR_REQUIRE(qkv && out && batch >= 0, "gator_mdr_self_attention: bad argument");
-  GATOR_REQUIRE(precision == GATOR_PREC_FP32, "gator_mdr_self_attention: precision %d has no kernel yet", precision);
+  GATOR_REQUIRE(precision == GATOR_PREC_FP32 || precision == GATOR_PREC_BF16, "gator_mdr_self_attention: bad precision %d", precision);
   if (batch == 0) return GATOR_OK;
+  if (precision == GATOR_PREC_BF16) return launch_self_attn_umma(qkv, out, batch, (cudaStream_t)stream);
   return launch_self_attn(qkv, out, batch, (cudaStream_t)stream);
 }
 
@@ -414,6 +415,8 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     return GATOR_ERR_WORKSPACE;
   }
   auto G = [&](int s) { return static_cast<const float*>(a->weights[s]); };
+  auto GB = [&](int s) -> const void* { return a->weights_bf16 ? a->weights_bf16[s] : nullptr; };
+  const int prec = a->precision;
   const int cb = resolve_chunk(B, a->chunk);
   Ws w = carve(static_cast<float*>(a->workspace), cb, J);
 
@@ -429,49 +432,51 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     e.bias_period = J;
     e.R = w.jf;
     e.ldr = E;
-    GATOR_TRY(gemm_f32(a->feat + (size_t)b0 * J * 128, 128, G(MDR_JF_WFEAT), 128, w.jf, E, Mj, E, 128, e, stream));
+    GATOR_TRY(gemm(prec, a->feat + (size_t)b0 * J * 128, 128, G(MDR_JF_WFEAT), 128, GB(MDR_JF_WFEAT), w.jf, E, Mj, E, 128, e, stream));
 
     for (int l = 0; l < GATOR_MDR_LAYERS; ++l) {
       const int base = MDR_NUM_GLOBAL + l * MDRL_NUM;
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
+      auto WB = [&](int s) -> const void* { return a->weights_bf16 ? a->weights_bf16[base + s] : nullptr; };
       // CrossAttentionBlock
       GATOR_TRY(layernorm_rows(w.x, w.y, W(MDRL_N1_W), W(MDRL_N1_B), Mv, E, 0, 0, stream));
       GATOR_TRY(layernorm_rows(w.jf, w.yj, W(MDRL_N1_W), W(MDRL_N1_B), Mj, E, 0, 0, stream));
-      GATOR_TRY(gemm_f32(w.y, E, W(MDRL_WQ), E, w.q, E, Mv, E, E, Epilogue(), stream));
-      GATOR_TRY(gemm_f32(w.yj, E, W(MDRL_WKV), E, w.kv, 2 * E, Mj, 2 * E, E, Epilogue(), stream));
+      GATOR_TRY(gemm(prec, w.y, E, W(MDRL_WQ), E, WB(MDRL_WQ), w.q, E, Mv, E, E, Epilogue(), stream));
+      GATOR_TRY(gemm(prec, w.yj, E, W(MDRL_WKV), E, WB(MDRL_WKV), w.kv, 2 * E, Mj, 2 * E, E, Epilogue(), stream));
       mdr_cross_attn_kernel<<<nb, 256, 0, stream>>>(w.q, w.kv, w.y, J);
       GATOR_TRY(check_launch("mdr_cross_attn"));
       e = Epilogue();
       e.bias = W(MDRL_PROJ_B);
       e.R = w.x;
       e.ldr = E;
-      GATOR_TRY(gemm_f32(w.y, E, W(MDRL_PROJ_W), E, w.x, E, Mv, E, E, e, stream));
+      GATOR_TRY(gemm(prec, w.y, E, W(MDRL_PROJ_W), E, WB(MDRL_PROJ_W), w.x, E, Mv, E, E, e, stream));
       GATOR_TRY(layernorm_rows(w.x, w.y, W(MDRL_N2_W), W(MDRL_N2_B), Mv, E, 0, 0, stream));
       e = Epilogue();
       e.bias = W(MDRL_FC1_B);
       e.act = 1;
-      GATOR_TRY(gemm_f32(w.y, E, W(MDRL_FC1_W), E, w.hid, 256, Mv, 256, E, e, stream));
+      GATOR_TRY(gemm(prec, w.y, E, W(MDRL_FC1_W), E, WB(MDRL_FC1_W), w.hid, 256, Mv, 256, E, e, stream));
       e = Epilogue();
       e.bias = W(MDRL_FC2_B);
       e.R = w.x;
       e.ldr = E;
-      GATOR_TRY(gemm_f32(w.hid, 256, W(MDRL_FC2_W), 256, w.x, E, Mv, E, 256, e, stream));
+      GATOR_TRY(gemm(prec, w.hid, 256, W(MDRL_FC2_W), 256, WB(MDRL_FC2_W), w.x, E, Mv, E, 256, e, stream));
       // unbiased-std LayerNorm, then x = x3 + selfatt(x3)
       GATOR_TRY(layernorm_rows(w.x, w.q, W(MDRL_CLN_A), W(MDRL_CLN_B), Mv, E, 1, 0, stream));
       e = Epilogue();
       e.bias = W(MDRL_SQKV_B);
-      GATOR_TRY(gemm_f32(w.q, E, W(MDRL_SQKV_W), E, w.hid, 3 * E, Mv, 3 * E, E, e, stream));
-      GATOR_TRY(launch_self_attn(w.hid, w.y, nb, stream));
+      GATOR_TRY(gemm(prec, w.q, E, W(MDRL_SQKV_W), E, WB(MDRL_SQKV_W), w.hid, 3 * E, Mv, 3 * E, E, e, stream));
+      if (prec == GATOR_PREC_BF16) GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, stream));
+      else GATOR_TRY(launch_self_attn(w.hid, w.y, nb, stream));
       e = Epilogue();
       e.bias = W(MDRL_SO_B);
       e.R = w.q;
       e.ldr = E;
-      GATOR_TRY(gemm_f32(w.y, E, W(MDRL_SO_W), E, w.x, E, Mv, E, E, e, stream));
+      GATOR_TRY(gemm(prec, w.y, E, W(MDRL_SO_W), E, WB(MDRL_SO_W), w.x, E, Mv, E, E, e, stream));
     }
     // head
     e = Epilogue();
     e.bias = G(MDR_HEAD_B);
-    GATOR_TRY(gemm_f32(w.x, E, G(MDR_HEAD_W), E, w.hd, HEADN, Mv, HEADN, E, e, stream));
+    GATOR_TRY(gemm(prec, w.x, E, G(MDR_HEAD_W), E, GB(MDR_HEAD_W), w.hd, HEADN, Mv, HEADN, E, e, stream));
     mdr_head_kernel<<<nb, 256, 0, stream>>>(w.hd, G(MDR_BNORM_SCALE), G(MDR_BNORM_SHIFT), G(MDR_BCONV_W),
                                             G(MDR_BCONV_B), a->alpha, a->coarse ? a->coarse + (size_t)b0 * V * 3 : nullptr, w.a3);
     GATOR_TRY(check_launch("mdr_head"));
@@ -479,7 +484,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     e = Epilogue();
     e.conv3 = 1;
     e.bias_rows = G(MDR_UP_BIAST);
-    GATOR_TRY(gemm_f32(w.a3, UPK, G(MDR_UP_W), UPK, a->mesh + (size_t)b0 * VF * 3, 0, nb * 3, VF, UPK, e, stream));
+    GATOR_TRY(gemm(prec, w.a3, UPK, G(MDR_UP_W), UPK, GB(MDR_UP_W), a->mesh + (size_t)b0 * VF * 3, 0, nb * 3, VF, UPK, e, stream));
   }
   return GATOR_OK;
 }

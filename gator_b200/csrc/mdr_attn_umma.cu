@@ -1,0 +1,215 @@
+// MDR 431x431 self-attention core (lib/models/vanilla_transformer_encoder.py:36-46) on tcgen05:
+//   out = softmax(q k^T / sqrt(32)) v      per (sample, head), q/k/v from the fused qkv projection.
+// One CTA per (sample, head).  K (432 x 32) and V^T (32 x 432) are staged once as bf16 in the UMMA
+// K-major canonical layout; the 431 queries go through 4 M-tiles of 128.  Per tile:
+//   S = Q K^T      -> TMEM columns [0,432)   (2 MMAs of N = 224 / 208, K = 32)
+//   softmax        -> 256 threads: thread = (row, column half); the whole key range of a row sits in TMEM,
+//                     so it is a plain two-pass softmax (row max, then exp2 / row sum), no online rescale
+//   P (bf16)       -> shared memory as the A operand (128 x 432)
+//   O = P V        -> TMEM columns [432,464) (27 MMAs of N = 32, K = 16), scaled by 1/rowsum on the way out
+// The 431 x 431 score matrix never leaves the SM.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace gator {
+namespace {
+
+using namespace umma;
+
+constexpr int V = GATOR_V_COARSE;   // 431
+constexpr int VP = 432;             // padded keys
+constexpr int DK = 32;
+constexpr int E = 64;
+constexpr int QT = 128;             // query rows per tile
+constexpr int KCH = VP / 8;         // 54 key chunks
+constexpr int HALF = VP / 2;        // 216 columns per thread half
+constexpr int N0 = 224, N1 = 208;   // S = two MMAs (N <= 256, multiple of 16)
+
+constexpr int SK_BYTES = VP * DK * 2;        // 27 648  K   [kg 54][kc 4][8][8]
+constexpr int SVT_BYTES = DK * VP * 2;       // 27 648  V^T [dg 4][kc 54][8][8]
+constexpr int SQ_BYTES = QT * DK * 2;        //  8 192  Q   [rg 16][kc 4][8][8]
+constexpr int SP_BYTES = QT * VP * 2;        // 110 592 P   [rg 16][kc 54][8][8]
+constexpr int SMEM_BYTES = SK_BYTES + SVT_BYTES + SQ_BYTES + SP_BYTES;   // 174 080
+
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__global__ void __launch_bounds__(256, 1)
+mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar_s, bar_o;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float red_max[2][QT];
+  __shared__ float red_sum[2][QT];
+  uint8_t* sK = smem;
+  uint8_t* sVT = sK + SK_BYTES;
+  uint8_t* sQ = sVT + SVT_BYTES;
+  uint8_t* sP = sQ + SQ_BYTES;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x >> 1, h = blockIdx.x & 1;
+  const float* base = qkv + (size_t)b * V * 3 * E;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 32) {
+    mbar_init(&bar_s, 1);
+    mbar_init(&bar_o, 1);
+    mbar_init_fence();
+  }
+  // ---- stage K: chunk c = (kg, kc, r) -> key = kg*8 + r, d = kc*8 ----
+  for (int c = tid; c < VP * 4; c += 256) {
+    const int r = c & 7, kc = (c >> 3) & 3, kg = c >> 5;
+    const int key = kg * 8 + r;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
+    if (key < V) {
+      const float* src = base + (size_t)key * 3 * E + E + h * DK + kc * 8;
+      a = *reinterpret_cast<const float4*>(src);
+      bb = *reinterpret_cast<const float4*>(src + 4);
+    }
+    reinterpret_cast<uint4*>(sK)[c] = cvt8(a, bb);
+  }
+  // ---- stage V^T: warp takes a group of 8 keys, lane = d; chunk (dg, kc, r): d = dg*8 + r ----
+  for (int kc = warp; kc < KCH; kc += 8) {
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int key = kc * 8 + i;
+      v[i] = key < V ? base[(size_t)key * 3 * E + 2 * E + h * DK + lane] : 0.f;
+    }
+    const int dg = lane >> 3, r = lane & 7;
+    *reinterpret_cast<uint4*>(sVT + (size_t)dg * (KCH * 128) + kc * 128 + r * 16) =
+        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t tmem_o = tmem + VP;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const int half = warp >> 2;                       // which 216-column half of the row this thread owns
+  const int row = (warp & 3) * 32 + lane;           // row within the tile = TMEM lane
+  const float c_log2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32)
+
+  for (int qt = 0; qt < 4; ++qt) {
+    // ---- stage Q tile ----
+    for (int c = tid; c < QT * 4; c += 256) {
+      const int r = c & 7, kc = (c >> 3) & 3, rg = c >> 5;
+      const int q = qt * QT + rg * 8 + r;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
+      if (q < V) {
+        const float* src = base + (size_t)q * 3 * E + h * DK + kc * 8;
+        a = *reinterpret_cast<const float4*>(src);
+        bb = *reinterpret_cast<const float4*>(src + 4);
+      }
+      reinterpret_cast<uint4*>(sQ)[c] = cvt8(a, bb);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK);
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        const uint64_t ad = smem_desc(q0 + ks * 256, 128, 4 * 128);
+        mma_bf16(tmem, ad, smem_desc(k0 + ks * 256, 128, 4 * 128), idesc_bf16(QT, N0), ks);
+        mma_bf16(tmem + N0, ad, smem_desc(k0 + (N0 / 8) * 512 + ks * 256, 128, 4 * 128), idesc_bf16(QT, N1), ks);
+      }
+      mma_commit(&bar_s);
+    }
+    mbar_wait(&bar_s, qt & 1);
+    tc_fence_after();
+
+    // ---- pass 1: row max over this thread's 216 columns ----
+    float mx = -INFINITY;
+    for (int j = 0; j < HALF / 8; ++j) {
+      float s[8];
+      tmem_ld8(tmem + lane_addr + half * HALF + j * 8, s);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int col = half * HALF + j * 8 + i;
+        mx = fmaxf(mx, col < V ? s[i] : -INFINITY);
+      }
+    }
+    red_max[half][row] = mx;
+    __syncthreads();
+    mx = fmaxf(red_max[0][row], red_max[1][row]) * c_log2;
+
+    // ---- pass 2: p = exp2(s*c - max*c), row sum, P -> smem (bf16, A-operand layout) ----
+    float sum = 0.f;
+    uint8_t* prow = sP + (size_t)(row >> 3) * (KCH * 128) + (row & 7) * 16;
+    for (int j = 0; j < HALF / 8; ++j) {
+      float s[8];
+      tmem_ld8(tmem + lane_addr + half * HALF + j * 8, s);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int col = half * HALF + j * 8 + i;
+        s[i] = col < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
+        sum += s[i];
+      }
+      *reinterpret_cast<uint4*>(prow + (half * (HALF / 8) + j) * 128) =
+          make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+    }
+    red_sum[half][row] = sum;
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sVT);
+#pragma unroll 1
+      for (int ks = 0; ks < VP / 16; ++ks)
+        mma_bf16(tmem_o, smem_desc(p0 + ks * 256, 128, KCH * 128), smem_desc(v0 + ks * 256, 128, KCH * 128),
+                 idesc_bf16(QT, DK), ks);
+      mma_commit(&bar_o);
+    }
+    mbar_wait(&bar_o, qt & 1);
+    tc_fence_after();
+    // ---- O tile out: thread = (row, 16-column half) ----
+    {
+      float o[16];
+      tmem_ld16(tmem_o + lane_addr + half * 16, o);
+      tmem_ld_wait();
+      const float inv = 1.0f / (red_sum[0][row] + red_sum[1][row]);
+      const int q = qt * QT + row;
+      if (q < V) {
+        float* dst = out + ((size_t)b * V + q) * E + h * DK + half * 16;
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();   // S / O / red_* / sQ / sP may be overwritten by the next tile
+  }
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace
+
+int launch_self_attn_umma(const float* qkv, float* out, int nb, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(mdr_self_attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_done = true;
+  }
+  mdr_self_attn_umma_kernel<<<nb * 2, 256, SMEM_BYTES, stream>>>(qkv, out);
+  return check_launch("mdr_self_attn_umma");
+}
+
+}  // namespace gator

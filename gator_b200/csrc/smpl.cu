@@ -313,7 +313,7 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     GATOR_TRY(check_launch("smpl_pose"));
     Epilogue e;
     e.bias = a->v_template;
-    GATOR_TRY(gemm_f32(w.aop, KB, a->blend_w, KB, w.vposed, NV3, nb, NV3, KB, e, stream));
+    GATOR_TRY(gemm(a->precision, w.aop, KB, a->blend_w, KB, a->blend_w_bf16, w.vposed, NV3, nb, NV3, KB, e, stream));
     dim3 grid(ceil_div(NV, SK_VT), ceil_div(nb, SK_SG));
     smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w,
                                                  a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb);

@@ -18,6 +18,10 @@ import torch
 import torch.nn as nn
 
 from .. import _lib, config, graph
+from ..packing import pack_umma_weight
+
+_BF16_GLOBAL = {'LIFT_W'}
+_BF16_BLOCK = {'QKV_W', 'PROJ_W', 'GCN_W01', 'XF_W01', 'XF_WB', 'FC1_W', 'FC2_W'}
 
 _HEADS = 8
 _EMBED = 128
@@ -214,6 +218,7 @@ class GAT(nn.Module):
         }
         gnames, bnames = _lib.slot_names('gat')
         tensors = [t[n] for n in gnames]
+        packed = [pack_umma_weight(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
         eye = torch.eye(J, device=dev)
         for blk in self.blocks:
             adj = blk.adj.to(dev) + blk.gcn.adj2                                         # modules.py:247-249
@@ -233,8 +238,10 @@ class GAT(nn.Module):
                 'FC2_W': f(blk.mlp.fc2.weight), 'FC2_B': f(blk.mlp.fc2.bias),
             }
             tensors += [b[n] for n in bnames]
+            packed += [pack_umma_weight(b[n]) if n in _BF16_BLOCK else None for n in bnames]
         table = (ctypes.c_void_p * len(tensors))(*[t_.data_ptr() for t_ in tensors])
-        self._packed = (tensors, table, dev)
+        table16 = (ctypes.c_void_p * len(packed))(*[(t_.data_ptr() if t_ is not None else None) for t_ in packed])
+        self._packed = ((tensors, packed, table16), table, dev)
         return self
 
     def _workspace(self, batch, dev):
@@ -250,7 +257,7 @@ class GAT(nn.Module):
             raise NotImplementedError('gator_b200.GAT implements the eval() forward only')
         if self._packed is None:
             self.pack()
-        tensors, table, dev = self._packed
+        (_, _, table16), table, dev = self._packed
         if not pose2d.is_cuda:
             raise RuntimeError('gator_b200.GAT: input must be a CUDA tensor (no CPU fallback)')
         B = pose2d.shape[0]
@@ -262,7 +269,7 @@ class GAT(nn.Module):
             return pose3d, feat
         ws = self._workspace(B, dev)
         a = _lib.GatArgs(num_joint=J, depth=self.depth, batch=B, chunk=self.chunk, precision=self.precision,
-                         reserved=0, weights=table, pose2d=_lib.ptr(x), pose3d=_lib.ptr(pose3d),
+                         reserved=0, weights=table, weights_bf16=table16, pose2d=_lib.ptr(x), pose3d=_lib.ptr(pose3d),
                          feat=_lib.ptr(feat), workspace=_lib.ptr(ws), workspace_bytes=ws.numel())
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gator_gat_forward(a, _lib.stream_ptr()), 'gator_gat_forward')

@@ -16,6 +16,10 @@ import torch.nn as nn
 
 from .. import _lib, config, graph
 from ..mesh import Mesh
+from ..packing import pack_umma_weight
+
+_BF16_GLOBAL = {'JF_WFEAT', 'HEAD_W', 'UP_W'}
+_BF16_LAYER = {'WQ', 'WKV', 'PROJ_W', 'FC1_W', 'FC2_W', 'SQKV_W', 'SO_W'}
 
 V_COARSE, V_FULL, UP_K = 431, 6890, 1296
 
@@ -175,6 +179,7 @@ class MDR(nn.Module):
         }
         gnames, lnames = _lib.slot_names('mdr')
         tensors = [t[n] for n in gnames]
+        packed = [pack_umma_weight(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
         for sfx in ('', '_1', '_2'):
             enc, sa, cln = getattr(self, 'encoder' + sfx), getattr(self, 'selfatt' + sfx), getattr(self, 'norm' + sfx)
             l = {
@@ -190,8 +195,10 @@ class MDR(nn.Module):
                 'SO_W': f(sa.linears[3].weight), 'SO_B': f(sa.linears[3].bias),
             }
             tensors += [l[n] for n in lnames]
+            packed += [pack_umma_weight(l[n]) if n in _BF16_LAYER else None for n in lnames]
         table = (ctypes.c_void_p * len(tensors))(*[t_.data_ptr() for t_ in tensors])
-        self._packed = (tensors, table, dev)
+        table16 = (ctypes.c_void_p * len(packed))(*[(t_.data_ptr() if t_ is not None else None) for t_ in packed])
+        self._packed = ((tensors, packed, table16), table, dev)
         return self
 
     def _workspace(self, batch, dev):
@@ -207,7 +214,7 @@ class MDR(nn.Module):
             raise NotImplementedError('gator_b200.MDR implements the eval() forward only')
         if self._packed is None:
             self.pack()
-        tensors, table, dev = self._packed
+        (_, _, table16), table, dev = self._packed
         for t_ in (pose2d, pose3d_mm, feat):
             if not t_.is_cuda:
                 raise RuntimeError('gator_b200.MDR: inputs must be CUDA tensors (no CPU fallback)')
@@ -220,7 +227,7 @@ class MDR(nn.Module):
         if B > 0:
             ws = self._workspace(B, dev)
             a = _lib.MdrArgs(num_joint=J, batch=B, chunk=self.chunk, alpha=int(self.alpha), precision=self.precision,
-                             reserved=0, weights=table, pose2d=_lib.ptr(p2), pose3d=_lib.ptr(p3), feat=_lib.ptr(ft),
+                             reserved=0, weights=table, weights_bf16=table16, pose2d=_lib.ptr(p2), pose3d=_lib.ptr(p3), feat=_lib.ptr(ft),
                              mesh=_lib.ptr(mesh), coarse=_lib.ptr(coarse), workspace=_lib.ptr(ws),
                              workspace_bytes=ws.numel())
             with torch.cuda.device(dev):

@@ -102,6 +102,8 @@ typedef struct {
   int32_t precision;           /* gator_precision                                      */
   int32_t reserved;
   const void* const* weights;  /* HOST array of GAT_NUM_GLOBAL + depth*GATB_NUM device pointers */
+  const void* const* weights_bf16; /* same indexing: tcgen05-packed bf16 copy of each *_W matrix slot (see
+                                  gator_umma_weight_layout), NULL entries / NULL table = fp32 kernel */
   const float* pose2d;         /* (B,J,2)                                              */
   float* pose3d;               /* (B,3J)   x_out, millimetres                          */
   float* feat;                 /* (B,J,128) GELU(LN(x)) - second return of GAT.forward */
@@ -165,6 +167,7 @@ typedef struct {
   int32_t precision;           /* gator_precision                                       */
   int32_t reserved;
   const void* const* weights;  /* HOST array of MDR_NUM_GLOBAL + 3*MDRL_NUM device pointers */
+  const void* const* weights_bf16; /* same indexing, tcgen05-packed bf16 matrices (may be NULL) */
   const float* pose2d;         /* (B,J,2)                                               */
   const float* pose3d;         /* (B,J,3) millimetres (divided by 1000 inside)          */
   const float* feat;           /* (B,J,128)                                             */
@@ -203,6 +206,7 @@ typedef struct {
   const float* j_shapedirs;    /* (24,3,10) J_regressor @ shapedirs                       */
   const float* default_betas;  /* (10)      th_betas buffer                               */
   const float* blend_w;        /* (20670,220) [shapedirs | posedirs | 0] rows = (vertex,xyz) */
+  const void* blend_w_bf16;    /* tcgen05-packed bf16 copy of blend_w, or NULL              */
   const float* v_template;     /* (20670)                                                 */
   const int32_t* skin_idx;     /* (6890, weights_per_vertex) joint ids                    */
   const float* skin_w;         /* (6890, weights_per_vertex)                              */
