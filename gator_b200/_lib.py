@@ -12,7 +12,8 @@ import threading
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, '_C', 'libgator_b200.so')
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_BF16X3 = 0, 1, 2
+PRECISIONS = {'fp32': PREC_FP32, 'bf16': PREC_BF16, 'bf16x3': PREC_BF16X3}
 
 c_float_p = C.POINTER(C.c_float)
 c_int_p = C.POINTER(C.c_int32)
@@ -22,6 +23,7 @@ class GatArgs(C.Structure):
     _fields_ = [('num_joint', C.c_int32), ('depth', C.c_int32), ('batch', C.c_int32), ('chunk', C.c_int32),
                 ('precision', C.c_int32), ('reserved', C.c_int32),
                 ('weights', C.POINTER(C.c_void_p)), ('weights_bf16', C.POINTER(C.c_void_p)),
+                ('weights_bf16_lo', C.POINTER(C.c_void_p)),
                 ('pose2d', C.c_void_p), ('pose3d', C.c_void_p),
                 ('feat', C.c_void_p), ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
 
@@ -30,6 +32,7 @@ class MdrArgs(C.Structure):
     _fields_ = [('num_joint', C.c_int32), ('batch', C.c_int32), ('chunk', C.c_int32), ('alpha', C.c_int32),
                 ('precision', C.c_int32), ('reserved', C.c_int32),
                 ('weights', C.POINTER(C.c_void_p)), ('weights_bf16', C.POINTER(C.c_void_p)),
+                ('weights_bf16_lo', C.POINTER(C.c_void_p)),
                 ('pose2d', C.c_void_p), ('pose3d', C.c_void_p),
                 ('feat', C.c_void_p), ('mesh', C.c_void_p), ('coarse', C.c_void_p),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
@@ -40,7 +43,7 @@ class SmplArgs(C.Structure):
                 ('check_zero_norm', C.c_int32), ('weights_per_vertex', C.c_int32), ('precision', C.c_int32),
                 ('reserved', C.c_int32),
                 ('parents', C.c_void_p), ('j_template', C.c_void_p), ('j_shapedirs', C.c_void_p),
-                ('default_betas', C.c_void_p), ('blend_w', C.c_void_p), ('blend_w_bf16', C.c_void_p),
+                ('default_betas', C.c_void_p), ('blend_w', C.c_void_p), ('blend_w_bf16', C.c_void_p), ('blend_w_bf16_lo', C.c_void_p),
                 ('v_template', C.c_void_p),
                 ('skin_idx', C.c_void_p), ('skin_w', C.c_void_p), ('pose', C.c_void_p), ('betas', C.c_void_p),
                 ('trans', C.c_void_p), ('verts', C.c_void_p), ('jtr', C.c_void_p),
@@ -58,7 +61,7 @@ class GemmArgs(C.Structure):
     _fields_ = [('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32),
                 ('lda', C.c_int32), ('ldw', C.c_int32), ('ldc', C.c_int32), ('ldr', C.c_int32),
                 ('act', C.c_int32), ('bias_period', C.c_int32), ('precision', C.c_int32),
-                ('A', C.c_void_p), ('W', C.c_void_p), ('bias', C.c_void_p), ('bias_rows', C.c_void_p),
+                ('A', C.c_void_p), ('W', C.c_void_p), ('W_lo', C.c_void_p), ('bias', C.c_void_p), ('bias_rows', C.c_void_p),
                 ('R', C.c_void_p), ('C', C.c_void_p)]
 
 

@@ -48,14 +48,20 @@ int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc
 
 // Same contract on the tensor cores: A fp32 (converted to bf16 in-kernel), W pre-packed bf16 in the UMMA
 // shared-memory image (see umma_weight_layout / gator_b200/packing.py), fp32 accumulate in TMEM.
-int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, float* C, int ldc, int M, int N, int K,
-                   const Epilogue& epi, cudaStream_t stream);
+// Wpacked_lo != null selects the 3-term split (a_hi w_hi + a_lo w_hi + a_hi w_lo): ~2^-17 relative error.
+int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, const void* Wpacked_lo, float* C, int ldc, int M,
+                   int N, int K, const Epilogue& epi, cudaStream_t stream);
 void umma_weight_layout(int N, int K, int* BN, int* n_tiles, int* K_pad);
 
 // precision dispatch used by the stage drivers: bf16 only if a packed weight exists for the slot
-inline int gemm(int precision, const float* A, int lda, const float* W, int ldw, const void* Wpacked, float* C, int ldc,
+struct PackedW {
+  const void* hi = nullptr;
+  const void* lo = nullptr;
+};
+inline int gemm(int precision, const float* A, int lda, const float* W, int ldw, PackedW pw, float* C, int ldc,
                 int M, int N, int K, const Epilogue& epi, cudaStream_t stream) {
-  if (precision == GATOR_PREC_BF16 && Wpacked) return gemm_bf16_umma(A, lda, Wpacked, C, ldc, M, N, K, epi, stream);
+  if (precision == GATOR_PREC_BF16 && pw.hi) return gemm_bf16_umma(A, lda, pw.hi, nullptr, C, ldc, M, N, K, epi, stream);
+  if (precision == GATOR_PREC_BF16X3 && pw.hi && pw.lo) return gemm_bf16_umma(A, lda, pw.hi, pw.lo, C, ldc, M, N, K, epi, stream);
   return gemm_f32(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
 }
 

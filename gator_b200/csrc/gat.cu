@@ -219,7 +219,7 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
   const int J = a->num_joint, B = a->batch;
   GATOR_REQUIRE(J >= 2 && J <= MAXJ, "gator_gat_forward: num_joint=%d out of range [2,%d]", J, MAXJ);
   GATOR_REQUIRE(a->depth >= 0 && a->depth <= 64, "gator_gat_forward: bad depth %d", a->depth);
-  GATOR_REQUIRE(a->precision == GATOR_PREC_FP32 || a->precision == GATOR_PREC_BF16, "gator_gat_forward: bad precision");
+  GATOR_REQUIRE(a->precision >= GATOR_PREC_FP32 && a->precision <= GATOR_PREC_BF16X3, "gator_gat_forward: bad precision");
   if (B == 0) return GATOR_OK;
   GATOR_REQUIRE(B > 0 && a->weights && a->pose2d && a->pose3d && a->feat, "gator_gat_forward: null buffer");
   const int nslots = GAT_NUM_GLOBAL + a->depth * GATB_NUM;
@@ -231,7 +231,7 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
     return GATOR_ERR_WORKSPACE;
   }
   auto G = [&](int s) { return static_cast<const float*>(a->weights[s]); };
-  auto GB = [&](int s) -> const void* { return a->weights_bf16 ? a->weights_bf16[s] : nullptr; };
+  auto GB = [&](int s) { PackedW w; w.hi = a->weights_bf16 ? a->weights_bf16[s] : nullptr; w.lo = a->weights_bf16_lo ? a->weights_bf16_lo[s] : nullptr; return w; };
   const int prec = a->precision;
   const int cb = resolve_chunk(B, a->chunk);
   const size_t rows_max = (size_t)cb * J;
@@ -259,7 +259,7 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
     for (int l = 0; l < a->depth; ++l) {
       const int base = GAT_NUM_GLOBAL + l * GATB_NUM;
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
-      auto WB = [&](int s) -> const void* { return a->weights_bf16 ? a->weights_bf16[base + s] : nullptr; };
+      auto WB = [&](int s) { return GB(base + s); };
       GATOR_TRY(layernorm_rows(x, n, W(GATB_LN1_W), W(GATB_LN1_B), M, C, 0, 0, stream));
       Epilogue e;
       e.bias = W(GATB_QKV_B);

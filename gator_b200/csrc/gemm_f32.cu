@@ -185,7 +185,11 @@ extern "C" int gator_gemm(const gator_gemm_args* a, void* stream) {
   e.R = a->R;
   e.ldr = a->ldr;
   if (a->precision == GATOR_PREC_BF16)   // W = bf16 weights packed by gator_b200.packing.pack_umma_weight
-    return gemm_bf16_umma(a->A, a->lda, a->W, a->C, a->ldc, a->M, a->N, a->K, e, (cudaStream_t)stream);
+    return gemm_bf16_umma(a->A, a->lda, a->W, nullptr, a->C, a->ldc, a->M, a->N, a->K, e, (cudaStream_t)stream);
+  if (a->precision == GATOR_PREC_BF16X3) {
+    GATOR_REQUIRE(a->W_lo, "gator_gemm: GATOR_PREC_BF16X3 needs W_lo");
+    return gemm_bf16_umma(a->A, a->lda, a->W, a->W_lo, a->C, a->ldc, a->M, a->N, a->K, e, (cudaStream_t)stream);
+  }
   GATOR_REQUIRE(a->precision == GATOR_PREC_FP32, "gator_gemm: bad precision");
   return gemm_f32(a->A, a->lda, static_cast<const float*>(a->W), a->ldw, a->C, a->ldc, a->M, a->N, a->K, e, (cudaStream_t)stream);
 }

@@ -388,9 +388,9 @@ int launch_self_attn(const float* qkv, float* out, int nb, cudaStream_t stream) 
 extern "C" int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_t precision, void* stream) {
   using namespace gator;
   GATOR_REQUIRE(qkv && out && batch >= 0, "gator_mdr_self_attention: bad argument");
-  GATOR_REQUIRE(precision == GATOR_PREC_FP32 || precision == GATOR_PREC_BF16, "gator_mdr_self_attention: bad precision %d", precision);
+  GATOR_REQUIRE(precision >= GATOR_PREC_FP32 && precision <= GATOR_PREC_BF16X3, "gator_mdr_self_attention: bad precision %d", precision);
   if (batch == 0) return GATOR_OK;
-  if (precision == GATOR_PREC_BF16) return launch_self_attn_umma(qkv, out, batch, (cudaStream_t)stream);
+  if (precision != GATOR_PREC_FP32) return launch_self_attn_umma(qkv, out, batch, (cudaStream_t)stream);
   return launch_self_attn(qkv, out, batch, (cudaStream_t)stream);
 }
 
@@ -400,7 +400,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   GATOR_REQUIRE(a, "gator_mdr_forward: null args");
   const int J = a->num_joint, B = a->batch;
   GATOR_REQUIRE(J >= 2 && J <= MAXJ, "gator_mdr_forward: num_joint=%d out of range [2,%d]", J, MAXJ);
-  GATOR_REQUIRE(a->precision == GATOR_PREC_FP32 || a->precision == GATOR_PREC_BF16, "gator_mdr_forward: bad precision");
+  GATOR_REQUIRE(a->precision >= GATOR_PREC_FP32 && a->precision <= GATOR_PREC_BF16X3, "gator_mdr_forward: bad precision");
   if (B == 0) return GATOR_OK;
   GATOR_REQUIRE(B > 0 && a->weights && a->pose2d && a->pose3d && a->feat && a->mesh, "gator_mdr_forward: null buffer");
   const int nslots = MDR_NUM_GLOBAL + GATOR_MDR_LAYERS * MDRL_NUM;
@@ -415,8 +415,12 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     return GATOR_ERR_WORKSPACE;
   }
   auto G = [&](int s) { return static_cast<const float*>(a->weights[s]); };
-  auto GB = [&](int s) -> const void* { return a->weights_bf16 ? a->weights_bf16[s] : nullptr; };
-  const int prec = a->precision;
+  auto GB = [&](int s) { PackedW w; w.hi = a->weights_bf16 ? a->weights_bf16[s] : nullptr; w.lo = a->weights_bf16_lo ? a->weights_bf16_lo[s] : nullptr; return w; };
+  // debug/ablation: `reserved` is a bit mask of the groups that take the bf16 kernels (0 = all):
+  //   2 layer GEMMs, 4 self-attention, 8 head GEMM, 16 upsample_conv, 32 joint-feature GEMM
+  const int mask = a->reserved ? a->reserved : ~0;
+  auto P = [&](int bit) { return (a->precision != GATOR_PREC_FP32 && (mask & bit)) ? a->precision : (int)GATOR_PREC_FP32; };
+  const int prec = P(2);
   const int cb = resolve_chunk(B, a->chunk);
   Ws w = carve(static_cast<float*>(a->workspace), cb, J);
 
@@ -432,12 +436,12 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     e.bias_period = J;
     e.R = w.jf;
     e.ldr = E;
-    GATOR_TRY(gemm(prec, a->feat + (size_t)b0 * J * 128, 128, G(MDR_JF_WFEAT), 128, GB(MDR_JF_WFEAT), w.jf, E, Mj, E, 128, e, stream));
+    GATOR_TRY(gemm(P(32), a->feat + (size_t)b0 * J * 128, 128, G(MDR_JF_WFEAT), 128, GB(MDR_JF_WFEAT), w.jf, E, Mj, E, 128, e, stream));
 
     for (int l = 0; l < GATOR_MDR_LAYERS; ++l) {
       const int base = MDR_NUM_GLOBAL + l * MDRL_NUM;
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
-      auto WB = [&](int s) -> const void* { return a->weights_bf16 ? a->weights_bf16[base + s] : nullptr; };
+      auto WB = [&](int s) { return GB(base + s); };
       // CrossAttentionBlock
       GATOR_TRY(layernorm_rows(w.x, w.y, W(MDRL_N1_W), W(MDRL_N1_B), Mv, E, 0, 0, stream));
       GATOR_TRY(layernorm_rows(w.jf, w.yj, W(MDRL_N1_W), W(MDRL_N1_B), Mj, E, 0, 0, stream));
@@ -465,7 +469,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
       e = Epilogue();
       e.bias = W(MDRL_SQKV_B);
       GATOR_TRY(gemm(prec, w.q, E, W(MDRL_SQKV_W), E, WB(MDRL_SQKV_W), w.hid, 3 * E, Mv, 3 * E, E, e, stream));
-      if (prec == GATOR_PREC_BF16) GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, stream));
+      if (P(4) != GATOR_PREC_FP32) GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, stream));
       else GATOR_TRY(launch_self_attn(w.hid, w.y, nb, stream));
       e = Epilogue();
       e.bias = W(MDRL_SO_B);
@@ -476,7 +480,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     // head
     e = Epilogue();
     e.bias = G(MDR_HEAD_B);
-    GATOR_TRY(gemm(prec, w.x, E, G(MDR_HEAD_W), E, GB(MDR_HEAD_W), w.hd, HEADN, Mv, HEADN, E, e, stream));
+    GATOR_TRY(gemm(P(8), w.x, E, G(MDR_HEAD_W), E, GB(MDR_HEAD_W), w.hd, HEADN, Mv, HEADN, E, e, stream));
     mdr_head_kernel<<<nb, 256, 0, stream>>>(w.hd, G(MDR_BNORM_SCALE), G(MDR_BNORM_SHIFT), G(MDR_BCONV_W),
                                             G(MDR_BCONV_B), a->alpha, a->coarse ? a->coarse + (size_t)b0 * V * 3 : nullptr, w.a3);
     GATOR_TRY(check_launch("mdr_head"));
@@ -484,7 +488,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     e = Epilogue();
     e.conv3 = 1;
     e.bias_rows = G(MDR_UP_BIAST);
-    GATOR_TRY(gemm(prec, w.a3, UPK, G(MDR_UP_W), UPK, GB(MDR_UP_W), a->mesh + (size_t)b0 * VF * 3, 0, nb * 3, VF, UPK, e, stream));
+    GATOR_TRY(gemm(P(16), w.a3, UPK, G(MDR_UP_W), UPK, GB(MDR_UP_W), a->mesh + (size_t)b0 * VF * 3, 0, nb * 3, VF, UPK, e, stream));
   }
   return GATOR_OK;
 }

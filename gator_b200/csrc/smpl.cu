@@ -278,7 +278,7 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
   GATOR_REQUIRE(a->center_idx >= -1 && a->center_idx < NJ, "gator_smpl_forward: bad center_idx");
   GATOR_REQUIRE(!a->has_betas || a->betas, "gator_smpl_forward: has_betas without betas");
   GATOR_REQUIRE(!a->has_trans || a->trans, "gator_smpl_forward: has_trans without trans");
-  GATOR_REQUIRE(a->precision == GATOR_PREC_FP32 || a->precision == GATOR_PREC_BF16, "gator_smpl_forward: bad precision");
+  GATOR_REQUIRE(a->precision >= GATOR_PREC_FP32 && a->precision <= GATOR_PREC_BF16X3, "gator_smpl_forward: bad precision");
   const size_t need = gator_smpl_workspace_bytes(B);
   if (!a->workspace || a->workspace_bytes < need) {
     set_error("gator_smpl_forward: workspace %zu < %zu bytes", a->workspace_bytes, need);
@@ -313,7 +313,7 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     GATOR_TRY(check_launch("smpl_pose"));
     Epilogue e;
     e.bias = a->v_template;
-    GATOR_TRY(gemm(a->precision, w.aop, KB, a->blend_w, KB, a->blend_w_bf16, w.vposed, NV3, nb, NV3, KB, e, stream));
+    GATOR_TRY(gemm(a->precision, w.aop, KB, a->blend_w, KB, PackedW{a->blend_w_bf16, a->blend_w_bf16_lo}, w.vposed, NV3, nb, NV3, KB, e, stream));
     dim3 grid(ceil_div(NV, SK_VT), ceil_div(nb, SK_SG));
     smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w,
                                                  a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb);

@@ -126,5 +126,13 @@ __device__ __forceinline__ uint4 cvt8(const float4& a, const float4& b) {
   return make_uint4(pack_bf16(a.x, a.y), pack_bf16(a.z, a.w), pack_bf16(b.x, b.y), pack_bf16(b.z, b.w));
 }
 
+// the bf16 residual of the same 8 values: lo = bf16(x - float(hi)), for the 3-term split product
+__device__ __forceinline__ float bf16_lo_f(uint32_t packed) { return __uint_as_float(packed << 16); }
+__device__ __forceinline__ float bf16_hi_f(uint32_t packed) { return __uint_as_float(packed & 0xffff0000u); }
+__device__ __forceinline__ uint4 cvt8_residual(const float4& a, const float4& b, const uint4& hi) {
+  return make_uint4(pack_bf16(a.x - bf16_lo_f(hi.x), a.y - bf16_hi_f(hi.x)), pack_bf16(a.z - bf16_lo_f(hi.y), a.w - bf16_hi_f(hi.y)),
+                    pack_bf16(b.x - bf16_lo_f(hi.z), b.y - bf16_hi_f(hi.z)), pack_bf16(b.z - bf16_lo_f(hi.w), b.w - bf16_hi_f(hi.w)));
+}
+
 }  // namespace umma
 }  // namespace gator

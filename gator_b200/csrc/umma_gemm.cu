@@ -34,9 +34,10 @@ constexpr int STG_BYTES = BM * STG_LD * 4; // 18 KB per slab
 
 struct UmmaGemmParams {
   const float* A;
-  const __nv_bfloat16* Wp;
+  const __nv_bfloat16* Wp;     // hi part (or the only part)
+  const __nv_bfloat16* Wlo;    // lo part for the 3-term split, else null
   float* C;
-  int lda, ldc, M, N, K, K_pad, BN;
+  int lda, ldc, M, N, K, K_pad, BN;   // BN = columns per CTA (the packed tile width, halved in split mode if > 128)
   Epilogue epi;
   int vec;
 };
@@ -47,9 +48,12 @@ umma_gemm_kernel(UmmaGemmParams p) {
   __shared__ uint64_t mbar[2];
   __shared__ uint32_t tmem_slot;
   const int BN = p.BN;
+  const bool split = p.Wlo != nullptr;
   const int w_stage = BN * BKE * 2;
-  uint8_t* sA = smem;                          // [2][A_STAGE]
-  uint8_t* sW = smem + 2 * A_STAGE;            // [2][w_stage]
+  const int a_stride = split ? 2 * A_STAGE : A_STAGE;      // [hi | lo] per stage
+  const int w_stride = split ? 2 * w_stage : w_stage;
+  uint8_t* sA = smem;                          // [2][a_stride]
+  uint8_t* sW = smem + 2 * a_stride;           // [2][w_stride]
   float* stg = reinterpret_cast<float*>(smem); // epilogue staging aliases the operand buffers: [2][BM][STG_LD]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -76,7 +80,8 @@ umma_gemm_kernel(UmmaGemmParams p) {
     if (kb >= 2) mbar_wait(&mbar[buf], ((kb >> 1) - 1) & 1);
     // ---- stage A: 128 rows x 64 k, fp32 -> bf16, chunk c = (rg, kc, r) stored linearly ----
     {
-      uint4* dst = reinterpret_cast<uint4*>(sA + buf * A_STAGE);
+      uint4* dst = reinterpret_cast<uint4*>(sA + buf * a_stride);
+      uint4* dst_lo = reinterpret_cast<uint4*>(sA + buf * a_stride + A_STAGE);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int c = i * 256 + tid;
@@ -88,29 +93,43 @@ umma_gemm_kernel(UmmaGemmParams p) {
           if (k < p.K) a = *reinterpret_cast<const float4*>(src);
           if (k + 4 < p.K) b = *reinterpret_cast<const float4*>(src + 4);
         }
-        dst[c] = cvt8(a, b);
+        const uint4 hi = cvt8(a, b);
+        dst[c] = hi;
+        if (split) dst_lo[c] = cvt8_residual(a, b, hi);
       }
     }
     // ---- stage W: BN/8 row groups x 1 KB (8 k-chunks), already in the smem image ----
     {
-      uint4* dst = reinterpret_cast<uint4*>(sW + buf * w_stage);
+      uint4* dst = reinterpret_cast<uint4*>(sW + buf * w_stride);
+      uint4* dst_lo = reinterpret_cast<uint4*>(sW + buf * w_stride + w_stage);
       const uint4* src = reinterpret_cast<const uint4*>(p.Wp);
+      const uint4* src_lo = reinterpret_cast<const uint4*>(p.Wlo);
       const int total = BN * 8;   // 16-byte chunks
       for (int c = tid; c < total; c += 256) {
         const int ng = c >> 6, j = c & 63;
-        dst[c] = __ldg(src + ((size_t)(n0 / 8 + ng) * kgroups + kb * 8) * 8 + j);
+        const size_t off = ((size_t)(n0 / 8 + ng) * kgroups + kb * 8) * 8 + j;
+        dst[c] = __ldg(src + off);
+        if (split) dst_lo[c] = __ldg(src_lo + off);
       }
     }
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
       tc_fence_after();
-      const uint32_t a0 = smem_u32(sA + buf * A_STAGE), b0 = smem_u32(sW + buf * w_stage);
+      const uint32_t a0 = smem_u32(sA + buf * a_stride), b0 = smem_u32(sW + buf * w_stride);
 #pragma unroll
       for (int ks = 0; ks < BKE / 16; ++ks) {
         const uint64_t ad = smem_desc(a0 + ks * 256, 128, BKE * 16);
         const uint64_t bd = smem_desc(b0 + ks * 256, 128, BKE * 16);
-        mma_bf16(tmem, ad, bd, idesc, (kb | ks) != 0);
+        if (split) {   // a*w ~= a_lo*w_hi + a_hi*w_lo + a_hi*w_hi  (the dropped a_lo*w_lo term is ~2^-18 relative)
+          const uint64_t adl = smem_desc(a0 + A_STAGE + ks * 256, 128, BKE * 16);
+          const uint64_t bdl = smem_desc(b0 + w_stage + ks * 256, 128, BKE * 16);
+          mma_bf16(tmem, adl, bd, idesc, (kb | ks) != 0);
+          mma_bf16(tmem, ad, bdl, idesc, 1);
+          mma_bf16(tmem, ad, bd, idesc, 1);
+        } else {
+          mma_bf16(tmem, ad, bd, idesc, (kb | ks) != 0);
+        }
       }
       mma_commit(&mbar[buf]);
     }
@@ -120,7 +139,7 @@ umma_gemm_kernel(UmmaGemmParams p) {
   __syncthreads();   // every thread is past its last operand-buffer use: staging may alias them
 
   // ---- epilogue ----
-  const int slabs = BN / 32;
+  const int slabs = (BN + 31) / 32;
   const Epilogue& e = p.epi;
   for (int s0 = 0; s0 < slabs; s0 += 2) {
     const int my = s0 + (warp >> 2);
@@ -142,7 +161,7 @@ umma_gemm_kernel(UmmaGemmParams p) {
         const int idx = tid + i * 256;
         const int r = idx >> 3, c4 = (idx & 7) * 4;
         const int m = m0 + r, n = n0 + slab * 32 + c4;
-        if (m >= p.M || n >= p.N) continue;
+        if (m >= p.M || n >= p.N || n >= n0 + BN) continue;
         const float4 t = *reinterpret_cast<const float4*>(stg + (size_t)h * BM * STG_LD + r * STG_LD + c4);
         float v[4] = {t.x, t.y, t.z, t.w};
         if (e.conv3) {
@@ -187,8 +206,8 @@ inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 
 
 }  // namespace
 
-int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, float* C, int ldc, int M, int N, int K,
-                   const Epilogue& epi, cudaStream_t stream) {
+int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, const void* Wpacked_lo, float* C, int ldc, int M,
+                   int N, int K, const Epilogue& epi, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return GATOR_OK;
   GATOR_REQUIRE(A && Wpacked && C, "gemm_bf16_umma: null operand");
   GATOR_REQUIRE(K > 0 && K % 4 == 0 && lda % 4 == 0, "gemm_bf16_umma: K=%d lda=%d must be multiples of 4", K, lda);
@@ -196,17 +215,21 @@ int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, float* C, int l
   UmmaGemmParams p;
   int n_tiles;
   umma_weight_layout(N, K, &p.BN, &n_tiles, &p.K_pad);
-  p.A = A; p.Wp = static_cast<const __nv_bfloat16*>(Wpacked); p.C = C;
+  p.A = A; p.Wp = static_cast<const __nv_bfloat16*>(Wpacked); p.Wlo = static_cast<const __nv_bfloat16*>(Wpacked_lo); p.C = C;
+  if (p.Wlo && p.BN > 128) {   // split mode doubles the operand footprint: halve the CTA's column tile
+    p.BN /= 2;
+    n_tiles *= 2;
+  }
   p.lda = lda; p.ldc = ldc; p.M = M; p.N = N; p.K = K;
   p.epi = epi;
   p.vec = (!epi.conv3 && ldc % 4 == 0 && aligned16(C) && (!epi.R || (epi.ldr % 4 == 0 && aligned16(epi.R))) &&
            (!epi.bias || aligned16(epi.bias)) && (!epi.bias_rows || (aligned16(epi.bias_rows) && N % 4 == 0))) ? 1 : 0;
-  const int operand = 2 * A_STAGE + 2 * p.BN * BKE * 2;
+  const int operand = (p.Wlo ? 2 : 1) * (2 * A_STAGE + 2 * p.BN * BKE * 2);
   const int smem = operand > 2 * STG_BYTES ? operand : 2 * STG_BYTES;
   static int max_set = 0;
   if (smem > max_set) {
-    cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * A_STAGE + 2 * 256 * BKE * 2);
-    max_set = 2 * A_STAGE + 2 * 256 * BKE * 2;
+    cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * A_STAGE + 2 * 128 * BKE * 2));
+    max_set = 2 * (2 * A_STAGE + 2 * 128 * BKE * 2);
   }
   dim3 grid(ceil_div(M, BM), n_tiles);
   umma_gemm_kernel<<<grid, 256, smem, stream>>>(p);

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib, config, graph
-from ..packing import pack_umma_weight
+from ..packing import pack_umma_weight_pair
 
 _BF16_GLOBAL = {'LIFT_W'}
 _BF16_BLOCK = {'QKV_W', 'PROJ_W', 'GCN_W01', 'XF_W01', 'XF_WB', 'FC1_W', 'FC2_W'}
@@ -218,7 +218,7 @@ class GAT(nn.Module):
         }
         gnames, bnames = _lib.slot_names('gat')
         tensors = [t[n] for n in gnames]
-        packed = [pack_umma_weight(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
+        packed = [pack_umma_weight_pair(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
         eye = torch.eye(J, device=dev)
         for blk in self.blocks:
             adj = blk.adj.to(dev) + blk.gcn.adj2                                         # modules.py:247-249
@@ -238,10 +238,11 @@ class GAT(nn.Module):
                 'FC2_W': f(blk.mlp.fc2.weight), 'FC2_B': f(blk.mlp.fc2.bias),
             }
             tensors += [b[n] for n in bnames]
-            packed += [pack_umma_weight(b[n]) if n in _BF16_BLOCK else None for n in bnames]
+            packed += [pack_umma_weight_pair(b[n]) if n in _BF16_BLOCK else None for n in bnames]
         table = (ctypes.c_void_p * len(tensors))(*[t_.data_ptr() for t_ in tensors])
-        table16 = (ctypes.c_void_p * len(packed))(*[(t_.data_ptr() if t_ is not None else None) for t_ in packed])
-        self._packed = ((tensors, packed, table16), table, dev)
+        table16 = (ctypes.c_void_p * len(packed))(*[(t_[0].data_ptr() if t_ is not None else None) for t_ in packed])
+        table16lo = (ctypes.c_void_p * len(packed))(*[(t_[1].data_ptr() if t_ is not None else None) for t_ in packed])
+        self._packed = ((tensors, packed, table16, table16lo), table, dev)
         return self
 
     def _workspace(self, batch, dev):
@@ -257,7 +258,7 @@ class GAT(nn.Module):
             raise NotImplementedError('gator_b200.GAT implements the eval() forward only')
         if self._packed is None:
             self.pack()
-        (_, _, table16), table, dev = self._packed
+        (_, _, table16, table16lo), table, dev = self._packed
         if not pose2d.is_cuda:
             raise RuntimeError('gator_b200.GAT: input must be a CUDA tensor (no CPU fallback)')
         B = pose2d.shape[0]
@@ -269,7 +270,7 @@ class GAT(nn.Module):
             return pose3d, feat
         ws = self._workspace(B, dev)
         a = _lib.GatArgs(num_joint=J, depth=self.depth, batch=B, chunk=self.chunk, precision=self.precision,
-                         reserved=0, weights=table, weights_bf16=table16, pose2d=_lib.ptr(x), pose3d=_lib.ptr(pose3d),
+                         reserved=0, weights=table, weights_bf16=table16, weights_bf16_lo=table16lo, pose2d=_lib.ptr(x), pose3d=_lib.ptr(pose3d),
                          feat=_lib.ptr(feat), workspace=_lib.ptr(ws), workspace_bytes=ws.numel())
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gator_gat_forward(a, _lib.stream_ptr()), 'gator_gat_forward')

@@ -19,9 +19,10 @@ class GATOR(nn.Module):
         self.pose2mesh = MDR.get_model(num_joint, embed_dim)
 
     def set_precision(self, precision: str):
-        """'fp32' (FFMA parity path) or 'bf16' (tcgen05 tensor-core path where a kernel exists)."""
+        """'fp32' (FFMA parity path), 'bf16x3' (tcgen05: 3-term bf16 split GEMMs + bf16 attention cores) or
+        'bf16' (tcgen05, single bf16 products)."""
         from .. import _lib
-        p = {'fp32': _lib.PREC_FP32, 'bf16': _lib.PREC_BF16}[precision]
+        p = _lib.PRECISIONS[precision]
         self.pose_lifter.precision = p
         self.pose2mesh.precision = p
         return self

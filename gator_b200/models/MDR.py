@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from .. import _lib, config, graph
 from ..mesh import Mesh
-from ..packing import pack_umma_weight
+from ..packing import pack_umma_weight_pair
 
 _BF16_GLOBAL = {'JF_WFEAT', 'HEAD_W', 'UP_W'}
 _BF16_LAYER = {'WQ', 'WKV', 'PROJ_W', 'FC1_W', 'FC2_W', 'SQKV_W', 'SO_W'}
@@ -133,6 +133,7 @@ class MDR(nn.Module):
         self._ws = None
         self.precision = _lib.PREC_FP32
         self.chunk = 0
+        self.bf16_mask = 0      # ablation: which kernel groups use bf16 (0 = all), see csrc/mdr.cu
         self.register_load_state_dict_post_hook(_invalidate_hook)
 
     def invalidate(self):
@@ -179,7 +180,7 @@ class MDR(nn.Module):
         }
         gnames, lnames = _lib.slot_names('mdr')
         tensors = [t[n] for n in gnames]
-        packed = [pack_umma_weight(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
+        packed = [pack_umma_weight_pair(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
         for sfx in ('', '_1', '_2'):
             enc, sa, cln = getattr(self, 'encoder' + sfx), getattr(self, 'selfatt' + sfx), getattr(self, 'norm' + sfx)
             l = {
@@ -195,10 +196,11 @@ class MDR(nn.Module):
                 'SO_W': f(sa.linears[3].weight), 'SO_B': f(sa.linears[3].bias),
             }
             tensors += [l[n] for n in lnames]
-            packed += [pack_umma_weight(l[n]) if n in _BF16_LAYER else None for n in lnames]
+            packed += [pack_umma_weight_pair(l[n]) if n in _BF16_LAYER else None for n in lnames]
         table = (ctypes.c_void_p * len(tensors))(*[t_.data_ptr() for t_ in tensors])
-        table16 = (ctypes.c_void_p * len(packed))(*[(t_.data_ptr() if t_ is not None else None) for t_ in packed])
-        self._packed = ((tensors, packed, table16), table, dev)
+        table16 = (ctypes.c_void_p * len(packed))(*[(t_[0].data_ptr() if t_ is not None else None) for t_ in packed])
+        table16lo = (ctypes.c_void_p * len(packed))(*[(t_[1].data_ptr() if t_ is not None else None) for t_ in packed])
+        self._packed = ((tensors, packed, table16, table16lo), table, dev)
         return self
 
     def _workspace(self, batch, dev):
@@ -214,7 +216,7 @@ class MDR(nn.Module):
             raise NotImplementedError('gator_b200.MDR implements the eval() forward only')
         if self._packed is None:
             self.pack()
-        (_, _, table16), table, dev = self._packed
+        (_, _, table16, table16lo), table, dev = self._packed
         for t_ in (pose2d, pose3d_mm, feat):
             if not t_.is_cuda:
                 raise RuntimeError('gator_b200.MDR: inputs must be CUDA tensors (no CPU fallback)')
@@ -227,7 +229,7 @@ class MDR(nn.Module):
         if B > 0:
             ws = self._workspace(B, dev)
             a = _lib.MdrArgs(num_joint=J, batch=B, chunk=self.chunk, alpha=int(self.alpha), precision=self.precision,
-                             reserved=0, weights=table, weights_bf16=table16, pose2d=_lib.ptr(p2), pose3d=_lib.ptr(p3), feat=_lib.ptr(ft),
+                             reserved=self.bf16_mask, weights=table, weights_bf16=table16, weights_bf16_lo=table16lo, pose2d=_lib.ptr(p2), pose3d=_lib.ptr(p3), feat=_lib.ptr(ft),
                              mesh=_lib.ptr(mesh), coarse=_lib.ptr(coarse), workspace=_lib.ptr(ws),
                              workspace_bytes=ws.numel())
             with torch.cuda.device(dev):

@@ -26,3 +26,12 @@ def pack_umma_weight(W: torch.Tensor) -> torch.Tensor:
     Wp[:N, :K] = W.float()
     Wp = Wp.reshape(N_pad // 8, 8, K_pad // 8, 8).permute(0, 2, 1, 3).contiguous()
     return Wp.to(torch.bfloat16).contiguous()
+
+
+@torch.no_grad()
+def pack_umma_weight_pair(W: torch.Tensor):
+    """(hi, lo) packed bf16 tensors with W ~= hi + lo (lo = bf16 of the rounding residual), for the 3-term
+    split product of GATOR_PREC_BF16X3."""
+    Wf = W.float()
+    hi = Wf.to(torch.bfloat16).float()
+    return pack_umma_weight(hi), pack_umma_weight(Wf - hi)

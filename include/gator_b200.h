@@ -41,7 +41,9 @@ typedef enum {
 /* precision of the matrix products (accumulation is always fp32) */
 typedef enum {
   GATOR_PREC_FP32 = 0,         /* FFMA everywhere: the <=1e-4 m parity path */
-  GATOR_PREC_BF16 = 1          /* tcgen05 bf16 operands where a tensor-core kernel exists */
+  GATOR_PREC_BF16 = 1,         /* tcgen05, single bf16 product per term                    */
+  GATOR_PREC_BF16X3 = 2        /* tcgen05, 3-term bf16 split in the GEMMs (a_hi w_hi + a_lo w_hi + a_hi w_lo,
+                                  ~2^-17 relative), bf16 operands in the attention cores: the default fast path */
 } gator_precision;
 
 int gator_abi_version(void);
@@ -104,6 +106,7 @@ typedef struct {
   const void* const* weights;  /* HOST array of GAT_NUM_GLOBAL + depth*GATB_NUM device pointers */
   const void* const* weights_bf16; /* same indexing: tcgen05-packed bf16 copy of each *_W matrix slot (see
                                   gator_umma_weight_layout), NULL entries / NULL table = fp32 kernel */
+  const void* const* weights_bf16_lo; /* packed bf16 residuals W - bf16(W) for GATOR_PREC_BF16X3 (may be NULL) */
   const float* pose2d;         /* (B,J,2)                                              */
   float* pose3d;               /* (B,3J)   x_out, millimetres                          */
   float* feat;                 /* (B,J,128) GELU(LN(x)) - second return of GAT.forward */
@@ -168,6 +171,7 @@ typedef struct {
   int32_t reserved;
   const void* const* weights;  /* HOST array of MDR_NUM_GLOBAL + 3*MDRL_NUM device pointers */
   const void* const* weights_bf16; /* same indexing, tcgen05-packed bf16 matrices (may be NULL) */
+  const void* const* weights_bf16_lo; /* packed residuals for GATOR_PREC_BF16X3 (may be NULL) */
   const float* pose2d;         /* (B,J,2)                                               */
   const float* pose3d;         /* (B,J,3) millimetres (divided by 1000 inside)          */
   const float* feat;           /* (B,J,128)                                             */
@@ -207,6 +211,7 @@ typedef struct {
   const float* default_betas;  /* (10)      th_betas buffer                               */
   const float* blend_w;        /* (20670,220) [shapedirs | posedirs | 0] rows = (vertex,xyz) */
   const void* blend_w_bf16;    /* tcgen05-packed bf16 copy of blend_w, or NULL              */
+  const void* blend_w_bf16_lo; /* packed residual for GATOR_PREC_BF16X3, or NULL            */
   const float* v_template;     /* (20670)                                                 */
   const int32_t* skin_idx;     /* (6890, weights_per_vertex) joint ids                    */
   const float* skin_w;         /* (6890, weights_per_vertex)                              */
@@ -256,7 +261,8 @@ typedef struct {
   int32_t bias_period;         /* rows of bias_rows (0 = unused)                         */
   int32_t precision;
   const float* A;
-  const void* W;               /* fp32 (N,K) for GATOR_PREC_FP32; packed bf16 (see below) for GATOR_PREC_BF16 */
+  const void* W;               /* fp32 (N,K) for GATOR_PREC_FP32; packed bf16 (see below) otherwise */
+  const void* W_lo;            /* packed bf16 residual for GATOR_PREC_BF16X3, else NULL   */
   const float* bias;           /* (N) or NULL                                            */
   const float* bias_rows;      /* (bias_period, N) or NULL                               */
   const float* R;              /* (M, ldr) residual or NULL (may alias C)                */

@@ -46,7 +46,7 @@ for tag in ('h36m', 'coco'):
     with torch.no_grad():
         ref_mesh, ref_p3 = orc.gator_forward(sd, gc, mc, x, alpha)
     m = build_b200_gator(tag, dev)
-    for prec in ('fp32', 'bf16'):
+    for prec in ('fp32', 'bf16', 'bf16x3'):
         m.set_precision(prec)
         mesh, p3 = m(x.to(dev))
         torch.cuda.synchronize()
@@ -56,7 +56,7 @@ for tag in ('h36m', 'coco'):
               f'MPJPE drift {mp:.4f} mm, PA-MPJPE drift {pa:.4f} mm, nan {int(torch.isnan(mesh).sum())}')
     if tag == 'coco':
         xb = torch.from_numpy(synthetic.coco_poses2d(golden('fixtures')['demo_pose19'], 4096)).to(dev)
-        for prec in ('fp32', 'bf16'):
+        for prec in ('fp32', 'bf16', 'bf16x3'):
             m.set_precision(prec)
             for _ in range(2): m(xb)
             torch.cuda.synchronize(); t0 = time.perf_counter()
@@ -74,7 +74,7 @@ buf = {k: torch.from_numpy(v) for k, v in synthetic.smpl_buffers().items()}
 pose, betas, trans = [torch.from_numpy(a) for a in synthetic.smpl_inputs(64)]
 rv, rj, _ = orc.smpl_forward(buf, synthetic.SMPL_PARENTS, pose, betas, trans)
 layer = build_b200_smpl(device=dev)
-for prec in ('fp32', 'bf16'):
+for prec in ('fp32', 'bf16', 'bf16x3'):
     layer.set_precision(prec)
     v, j = layer(pose.to(dev), betas.to(dev), trans.to(dev))
     print(f'SMPL {prec}: verts max-abs {(v.cpu()-rv).abs().max().item():.3e} m, jtr {(j.cpu()-rj).abs().max().item():.3e}')

@@ -4,7 +4,7 @@ import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from gator_b200 import _lib
-from gator_b200.packing import pack_umma_weight, umma_weight_layout
+from gator_b200.packing import pack_umma_weight, pack_umma_weight_pair, umma_weight_layout
 
 dev = 'cuda:0'
 
@@ -43,7 +43,26 @@ def run(M, N, K, act=0, bias=True, res=True, rows=0):
     return not bad.any()
 
 
+def run_x3(M, N, K):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g).to(dev)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).to(dev)
+    hi, lo = pack_umma_weight_pair(W)
+    C = torch.full((M, N), float('nan'), device=dev)
+    a = _lib.GemmArgs(M=M, N=N, K=K, lda=K, ldw=K, ldc=N, ldr=0, act=0, bias_period=0, precision=2,
+                      A=_lib.ptr(A), W=_lib.ptr(hi), W_lo=_lib.ptr(lo), bias=None, bias_rows=None, R=None, C=_lib.ptr(C))
+    _lib.check(_lib.lib().gator_gemm(a, _lib.stream_ptr()), 'gator_gemm x3')
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().t()
+    err = (C.double() - ref).abs().nan_to_num(9e9).max().item()
+    ref32 = (A @ W.t()).double()
+    print(f'x3 M={M} N={N} K={K}: max err vs fp64 {err:.3e} (torch fp32 matmul: {(ref32 - ref).abs().max().item():.3e})')
+    return err < 5e-5
+
+
 ok = True
+for shp in [(300, 64, 64), (500, 192, 64), (500, 512, 128), (444, 6890, 1296), (100, 20670, 220), (64, 57, 2432)]:
+    ok &= run_x3(*shp)
 for shp in [(128, 64, 64), (128, 32, 64), (256, 64, 128), (300, 192, 64), (1000, 64, 256), (77, 144, 128), (500, 512, 128),
             (130, 128, 512), (64, 57, 2432), (444, 6890, 1296), (100, 20670, 220), (431 * 8, 28, 64)]:
     ok &= run(*shp, act=0, bias=False, res=False)
