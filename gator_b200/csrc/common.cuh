@@ -66,7 +66,7 @@ inline int gemm(int precision, const float* A, int lda, const float* W, int ldw,
 }
 
 // tcgen05 version of the MDR self-attention core: qkv (nb*431, 192) -> out (nb*431, 64)
-int launch_self_attn_umma(const float* qkv, float* out, int nb, cudaStream_t stream);
+int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream);
 
 // LayerNorm over the last dim (C = 64 or 128).  mode 0: nn.LayerNorm (eps 1e-5, biased var);
 // mode 1: a*(x-mean)/(std_unbiased+1e-6)+b (vanilla_transformer_encoder.py:31-34).  gelu: apply after.

@@ -390,7 +390,7 @@ extern "C" int gator_mdr_self_attention(const float* qkv, float* out, int32_t ba
   GATOR_REQUIRE(qkv && out && batch >= 0, "gator_mdr_self_attention: bad argument");
   GATOR_REQUIRE(precision >= GATOR_PREC_FP32 && precision <= GATOR_PREC_BF16X3, "gator_mdr_self_attention: bad precision %d", precision);
   if (batch == 0) return GATOR_OK;
-  if (precision != GATOR_PREC_FP32) return launch_self_attn_umma(qkv, out, batch, (cudaStream_t)stream);
+  if (precision != GATOR_PREC_FP32) return launch_self_attn_umma(qkv, out, batch, precision == GATOR_PREC_BF16X3, (cudaStream_t)stream);
   return launch_self_attn(qkv, out, batch, (cudaStream_t)stream);
 }
 
@@ -469,7 +469,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
       e = Epilogue();
       e.bias = W(MDRL_SQKV_B);
       GATOR_TRY(gemm(prec, w.q, E, W(MDRL_SQKV_W), E, WB(MDRL_SQKV_W), w.hid, 3 * E, Mv, 3 * E, E, e, stream));
-      if (P(4) != GATOR_PREC_FP32) GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, stream));
+      if (P(4) != GATOR_PREC_FP32) GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, P(4) == GATOR_PREC_BF16X3, stream));
       else GATOR_TRY(launch_self_attn(w.hid, w.y, nb, stream));
       e = Epilogue();
       e.bias = W(MDRL_SO_B);

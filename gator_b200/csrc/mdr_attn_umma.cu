@@ -2,12 +2,14 @@
 //   out = softmax(q k^T / sqrt(32)) v      per (sample, head), q/k/v from the fused qkv projection.
 // One CTA per (sample, head).  K (432 x 32) and V^T (32 x 432) are staged once as bf16 in the UMMA
 // K-major canonical layout; the 431 queries go through 4 M-tiles of 128.  Per tile:
-//   S = Q K^T      -> TMEM columns [0,432)   (2 MMAs of N = 224 / 208, K = 32)
-//   softmax        -> 256 threads: thread = (row, column half); the whole key range of a row sits in TMEM,
-//                     so it is a plain two-pass softmax (row max, then exp2 / row sum), no online rescale
-//   P (bf16)       -> shared memory as the A operand (128 x 432)
-//   O = P V        -> TMEM columns [432,464) (27 MMAs of N = 32, K = 16), scaled by 1/rowsum on the way out
-// The 431 x 431 score matrix never leaves the SM.
+//   S = Q K^T      -> TMEM columns [0,432)   (MMAs of N = 224 / 208, K = 32)
+//   row max        -> 256 threads, thread = (row, column half); the whole key range of a row sits in TMEM,
+//                     so it is a plain two-pass softmax - no online rescaling
+//   for each third of the keys (144): P = exp2(.) as bf16 -> shared memory (A operand), O += P V
+//   O (TMEM columns [432,464)) scaled by 1/rowsum on the way out.
+// SPLIT mode (GATOR_PREC_BF16X3) carries bf16 residuals of Q, K, V and P as well and issues the 3-term
+// product for both GEMMs, which brings the kernel to ~1e-5 absolute error (fp32-parity on tensor cores);
+// without it the operands are plain bf16.  The 431 x 431 score matrix never leaves the SM.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -22,14 +24,18 @@ constexpr int DK = 32;
 constexpr int E = 64;
 constexpr int QT = 128;             // query rows per tile
 constexpr int KCH = VP / 8;         // 54 key chunks
-constexpr int HALF = VP / 2;        // 216 columns per thread half
+constexpr int HALF = VP / 2;        // 216 columns per thread half (row-max pass)
 constexpr int N0 = 224, N1 = 208;   // S = two MMAs (N <= 256, multiple of 16)
+constexpr int PARTS = 3;
+constexpr int PK = VP / PARTS;      // 144 keys per P part
+constexpr int PCH = PK / 8;         // 18 chunks
+constexpr int PHALF = PK / 2;       // 72 columns per thread in the exp pass
 
 constexpr int SK_BYTES = VP * DK * 2;        // 27 648  K   [kg 54][kc 4][8][8]
 constexpr int SVT_BYTES = DK * VP * 2;       // 27 648  V^T [dg 4][kc 54][8][8]
 constexpr int SQ_BYTES = QT * DK * 2;        //  8 192  Q   [rg 16][kc 4][8][8]
-constexpr int SP_BYTES = QT * VP * 2;        // 110 592 P   [rg 16][kc 54][8][8]
-constexpr int SMEM_BYTES = SK_BYTES + SVT_BYTES + SQ_BYTES + SP_BYTES;   // 174 080
+constexpr int SP_BYTES = QT * PK * 2;        // 36 864  P   [rg 16][kc 18][8][8]
+constexpr int smem_bytes(bool split) { return (split ? 2 : 1) * (SK_BYTES + SVT_BYTES + SQ_BYTES + SP_BYTES); }
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -47,6 +53,15 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ uint4 pack8_residual(const float* v, const uint4& hi) {
+  return make_uint4(pack_bf16(v[0] - bf16_lo_f(hi.x), v[1] - bf16_hi_f(hi.x)), pack_bf16(v[2] - bf16_lo_f(hi.y), v[3] - bf16_hi_f(hi.y)),
+                    pack_bf16(v[4] - bf16_lo_f(hi.z), v[5] - bf16_hi_f(hi.z)), pack_bf16(v[6] - bf16_lo_f(hi.w), v[7] - bf16_hi_f(hi.w)));
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(256, 1)
 mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -54,10 +69,12 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   __shared__ uint32_t tmem_slot;
   __shared__ float red_max[2][QT];
   __shared__ float red_sum[2][QT];
+  // hi images first, lo images (SPLIT only) after them
   uint8_t* sK = smem;
   uint8_t* sVT = sK + SK_BYTES;
   uint8_t* sQ = sVT + SVT_BYTES;
   uint8_t* sP = sQ + SQ_BYTES;
+  constexpr int LO = SK_BYTES + SVT_BYTES + SQ_BYTES + SP_BYTES;   // offset of the residual images
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x >> 1, h = blockIdx.x & 1;
@@ -79,7 +96,9 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
       a = *reinterpret_cast<const float4*>(src);
       bb = *reinterpret_cast<const float4*>(src + 4);
     }
-    reinterpret_cast<uint4*>(sK)[c] = cvt8(a, bb);
+    const uint4 hi = cvt8(a, bb);
+    reinterpret_cast<uint4*>(sK)[c] = hi;
+    if (SPLIT) reinterpret_cast<uint4*>(sK + LO)[c] = cvt8_residual(a, bb, hi);
   }
   // ---- stage V^T: warp takes a group of 8 keys, lane = d; chunk (dg, kc, r): d = dg*8 + r ----
   for (int kc = warp; kc < KCH; kc += 8) {
@@ -90,8 +109,10 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
       v[i] = key < V ? base[(size_t)key * 3 * E + 2 * E + h * DK + lane] : 0.f;
     }
     const int dg = lane >> 3, r = lane & 7;
-    *reinterpret_cast<uint4*>(sVT + (size_t)dg * (KCH * 128) + kc * 128 + r * 16) =
-        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    const size_t off = (size_t)dg * (KCH * 128) + kc * 128 + r * 16;
+    const uint4 hi = pack8(v);
+    *reinterpret_cast<uint4*>(sVT + off) = hi;
+    if (SPLIT) *reinterpret_cast<uint4*>(sVT + LO + off) = pack8_residual(v, hi);
   }
   tc_fence_before();
   __syncthreads();
@@ -99,9 +120,10 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   const uint32_t tmem = tmem_slot;
   const uint32_t tmem_o = tmem + VP;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-  const int half = warp >> 2;                       // which 216-column half of the row this thread owns
+  const int half = warp >> 2;                       // which column half of the row this thread owns
   const int row = (warp & 3) * 32 + lane;           // row within the tile = TMEM lane
   const float c_log2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32)
+  uint32_t phase_o = 0;
 
   for (int qt = 0; qt < 4; ++qt) {
     // ---- stage Q tile ----
@@ -114,7 +136,9 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
         a = *reinterpret_cast<const float4*>(src);
         bb = *reinterpret_cast<const float4*>(src + 4);
       }
-      reinterpret_cast<uint4*>(sQ)[c] = cvt8(a, bb);
+      const uint4 hi = cvt8(a, bb);
+      reinterpret_cast<uint4*>(sQ)[c] = hi;
+      if (SPLIT) reinterpret_cast<uint4*>(sQ + LO)[c] = cvt8_residual(a, bb, hi);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -122,11 +146,25 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     if (tid == 0) {
       tc_fence_after();
       const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK);
+      const uint32_t i0 = idesc_bf16(QT, N0), i1 = idesc_bf16(QT, N1);
+      const uint32_t kofs = (N0 / 8) * 512;
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks) {
-        const uint64_t ad = smem_desc(q0 + ks * 256, 128, 4 * 128);
-        mma_bf16(tmem, ad, smem_desc(k0 + ks * 256, 128, 4 * 128), idesc_bf16(QT, N0), ks);
-        mma_bf16(tmem + N0, ad, smem_desc(k0 + (N0 / 8) * 512 + ks * 256, 128, 4 * 128), idesc_bf16(QT, N1), ks);
+        const uint64_t ad = smem_desc(q0 + ks * 256, 128, 512);
+        const uint64_t b0d = smem_desc(k0 + ks * 256, 128, 512), b1d = smem_desc(k0 + kofs + ks * 256, 128, 512);
+        if (SPLIT) {
+          const uint64_t adl = smem_desc(q0 + LO + ks * 256, 128, 512);
+          const uint64_t b0l = smem_desc(k0 + LO + ks * 256, 128, 512), b1l = smem_desc(k0 + LO + kofs + ks * 256, 128, 512);
+          mma_bf16(tmem, adl, b0d, i0, ks);
+          mma_bf16(tmem, ad, b0l, i0, 1);
+          mma_bf16(tmem, ad, b0d, i0, 1);
+          mma_bf16(tmem + N0, adl, b1d, i1, ks);
+          mma_bf16(tmem + N0, ad, b1l, i1, 1);
+          mma_bf16(tmem + N0, ad, b1d, i1, 1);
+        } else {
+          mma_bf16(tmem, ad, b0d, i0, ks);
+          mma_bf16(tmem + N0, ad, b1d, i1, ks);
+        }
       }
       mma_commit(&bar_s);
     }
@@ -149,37 +187,53 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     __syncthreads();
     mx = fmaxf(red_max[0][row], red_max[1][row]) * c_log2;
 
-    // ---- pass 2: p = exp2(s*c - max*c), row sum, P -> smem (bf16, A-operand layout) ----
+    // ---- pass 2, one third of the keys at a time: P = exp2(s*c - max*c) -> smem, O += P V ----
     float sum = 0.f;
-    uint8_t* prow = sP + (size_t)(row >> 3) * (KCH * 128) + (row & 7) * 16;
-    for (int j = 0; j < HALF / 8; ++j) {
-      float s[8];
-      tmem_ld8(tmem + lane_addr + half * HALF + j * 8, s);
-      tmem_ld_wait();
+    for (int part = 0; part < PARTS; ++part) {
+      uint8_t* prow = sP + (size_t)(row >> 3) * (PCH * 128) + (row & 7) * 16;
+#pragma unroll 3
+      for (int j = 0; j < PHALF / 8; ++j) {
+        float s[8];
+        const int col0 = part * PK + half * PHALF + j * 8;
+        tmem_ld8(tmem + lane_addr + col0, s);
+        tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int col = half * HALF + j * 8 + i;
-        s[i] = col < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
-        sum += s[i];
+        for (int i = 0; i < 8; ++i) {
+          s[i] = (col0 + i) < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
+          sum += s[i];
+        }
+        const uint4 hi = pack8(s);
+        const int kc = half * (PHALF / 8) + j;
+        *reinterpret_cast<uint4*>(prow + kc * 128) = hi;
+        if (SPLIT) *reinterpret_cast<uint4*>(prow + LO + kc * 128) = pack8_residual(s, hi);
       }
-      *reinterpret_cast<uint4*>(prow + (half * (HALF / 8) + j) * 128) =
-          make_uint4(pack_bf16(s[0], s[1]), pack_bf16(s[2], s[3]), pack_bf16(s[4], s[5]), pack_bf16(s[6], s[7]));
+      fence_proxy_async();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+        const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sVT) + part * (PCH * 128);
+        const uint32_t io = idesc_bf16(QT, DK);
+#pragma unroll 1
+        for (int ks = 0; ks < PK / 16; ++ks) {
+          const uint32_t acc = (part | ks) != 0;
+          const uint64_t pd = smem_desc(p0 + ks * 256, 128, PCH * 128), vd = smem_desc(v0 + ks * 256, 128, KCH * 128);
+          if (SPLIT) {
+            mma_bf16(tmem_o, smem_desc(p0 + LO + ks * 256, 128, PCH * 128), vd, io, acc);
+            mma_bf16(tmem_o, pd, smem_desc(v0 + LO + ks * 256, 128, KCH * 128), io, 1);
+            mma_bf16(tmem_o, pd, vd, io, 1);
+          } else {
+            mma_bf16(tmem_o, pd, vd, io, acc);
+          }
+        }
+        mma_commit(&bar_o);
+      }
+      mbar_wait(&bar_o, phase_o);     // P buffer free again / O complete
+      phase_o ^= 1;
+      tc_fence_after();
     }
     red_sum[half][row] = sum;
-    fence_proxy_async();
-    tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sVT);
-#pragma unroll 1
-      for (int ks = 0; ks < VP / 16; ++ks)
-        mma_bf16(tmem_o, smem_desc(p0 + ks * 256, 128, KCH * 128), smem_desc(v0 + ks * 256, 128, KCH * 128),
-                 idesc_bf16(QT, DK), ks);
-      mma_commit(&bar_o);
-    }
-    mbar_wait(&bar_o, qt & 1);
-    tc_fence_after();
     // ---- O tile out: thread = (row, 16-column half) ----
     {
       float o[16];
@@ -202,13 +256,15 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
 
 }  // namespace
 
-int launch_self_attn_umma(const float* qkv, float* out, int nb, cudaStream_t stream) {
+int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(mdr_self_attn_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(mdr_self_attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(false));
+    cudaFuncSetAttribute(mdr_self_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true));
     attr_done = true;
   }
-  mdr_self_attn_umma_kernel<<<nb * 2, 256, SMEM_BYTES, stream>>>(qkv, out);
+  if (split) mdr_self_attn_umma_kernel<true><<<nb * 2, 256, smem_bytes(true), stream>>>(qkv, out);
+  else mdr_self_attn_umma_kernel<false><<<nb * 2, 256, smem_bytes(false), stream>>>(qkv, out);
   return check_launch("mdr_self_attn_umma");
 }
 

@@ -16,11 +16,14 @@ qkv = (torch.randn(nb * 431, 192, generator=g) * 1.5).to(dev)
 o32 = torch.zeros(nb * 431, 64, device=dev); o16 = torch.full((nb * 431, 64), float('nan'), device=dev)
 _lib.check(L.gator_mdr_self_attention(qkv.data_ptr(), o32.data_ptr(), nb, 0, _lib.stream_ptr()), 'sa32')
 _lib.check(L.gator_mdr_self_attention(qkv.data_ptr(), o16.data_ptr(), nb, 1, _lib.stream_ptr()), 'sa16')
+o48 = torch.full((nb * 431, 64), float('nan'), device=dev)
+_lib.check(L.gator_mdr_self_attention(qkv.data_ptr(), o48.data_ptr(), nb, 2, _lib.stream_ptr()), 'sa48')
 torch.cuda.synchronize()
 q, k, v = [t.view(nb, 431, 2, 32).transpose(1, 2).double() for t in qkv.cpu().split(64, dim=1)]
 ref = (torch.softmax(q @ k.transpose(-1, -2) / 32 ** 0.5, -1) @ v).transpose(1, 2).reshape(nb * 431, 64)
 print('self-attn fp32 kernel max err', (o32.cpu().double() - ref).abs().max().item())
 e16 = (o16.cpu().double() - ref).abs()
+print('self-attn umma x3 kernel max err', (o48.cpu().double() - ref).abs().nan_to_num(9e9).max().item())
 print('self-attn umma kernel max err', e16.nan_to_num(9e9).max().item(), 'mean', e16.nan_to_num(0).mean().item(), 'nan', int(torch.isnan(o16).sum()))
 if e16.nan_to_num(9e9).max() > 0.05:
     bad = (e16 > 0.05)
@@ -29,7 +32,7 @@ if e16.nan_to_num(9e9).max() > 0.05:
 
 for nbt in (148, 296):
     qkv = torch.randn(nbt * 431, 192, device=dev); o = torch.empty(nbt * 431, 64, device=dev)
-    for prec in (0, 1):
+    for prec in (0, 1, 2):
         for _ in range(2): L.gator_mdr_self_attention(qkv.data_ptr(), o.data_ptr(), nbt, prec, _lib.stream_ptr())
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
