@@ -225,25 +225,38 @@ def run_b200(args):
         peaks = measured_peaks()
         # ---- dominant kernel alone: MDR self-attention core ----
         nb = 148
+        pcode = _lib.PRECISIONS[args.precision]
         qkv = torch.randn(nb * 431, 192, device=dev)
         out = torch.empty(nb * 431, 64, device=dev)
         s = _lib.stream_ptr()
         for _ in range(3):
-            L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, 0, s)
+            L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, pcode, s)
         torch.cuda.synchronize()
         reps = 20
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, 0, s)
+            L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, pcode, s)
         e1.record()
         torch.cuda.synchronize()
         k_ms = e0.elapsed_time(e1) / reps
         achieved = SA_FLOP_PER_SAMPLE * nb / (k_ms * 1e-3) / 1e12
-        roofline = {'kernel': 'mdr_self_attn_kernel', 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'],
+        kname = 'mdr_self_attn_kernel (fp32 FFMA)' if pcode == 0 else f'mdr_self_attn_umma_kernel<{"true" if pcode == 2 else "false"}> (tcgen05)'
+        roofline = {'kernel': kname, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'],
                     'unit': 'TFLOP/s', 'frac': achieved / peaks['bf16_tflops'], 'traffic': None,
                     'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)', 'launch_ms': k_ms,
-                    'note': 'fp32 FFMA kernel (parity path); flops = 2 heads x (QK^T + PV) x 148 samples per launch'}
+                    'note': 'algorithmic flops = 2 heads x (QK^T + PV) x 2*MAC x 148 samples per launch (47.6 MFLOP/sample-layer); '
+                            'the 3-term split issues 3x that many tensor-core MACs, which are not counted'}
+        # parity of this very configuration against the CPU oracle (64 samples)
+        from helpers import oracle_setup, orc, regressor
+        sd, gc, mc, alpha = oracle_setup(TAG)
+        xs = torch.from_numpy(make_inputs(64, seed=7))
+        with torch.no_grad():
+            ref_mesh, _ = orc.gator_forward(sd, gc, mc, xs, alpha)
+            got, _ = model(xs.to(dev))
+        mp, pa = orc.mpjpe_pa(got.cpu().numpy(), ref_mesh.numpy(), regressor('h36m'))
+        parity = {'max_abs_vertex_err_m': (got.cpu() - ref_mesh).abs().max().item(), 'mpjpe_drift_mm': mp,
+                  'pa_mpjpe_drift_mm': pa, 'samples': 64, 'tolerance_m': 1e-4}
         threads = os.cpu_count() or 1
         cpu_v, cpu_med, cpu_n = cpu_forward_rate(64, 12.0, threads)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
@@ -259,7 +272,7 @@ def run_b200(args):
                 'gpu_launches': int(launches),
                 'tflops_effective': FLOP_PER_MESH * value / 1e12,
                 'wall_s_timed_region': t_wall,
-                'roofline': roofline,
+                'roofline': roofline, 'parity': parity,
                 'cpu_baseline': {'value': cpu_v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                  'sample': f'{cpu_n} forwards of batch 64 (median {cpu_med * 1e3:.0f} ms), oracle port of the reference forward'}}
     if world > 1:
@@ -276,7 +289,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--batch', type=int, default=4096, help='samples per GPU')
-    ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default='bf16x3', choices=['fp32', 'bf16', 'bf16x3'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
     if args.impl == 'reference':
