@@ -68,6 +68,10 @@ inline int gemm(int precision, const float* A, int lda, const float* W, int ldw,
 // tcgen05 version of the MDR self-attention core: qkv (nb*431, 192) -> out (nb*431, 64)
 int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream);
 
+// Fused row-wise chain of one MDR layer (csrc/mdr_chain_umma.cu): x3_prev/att_prev -> x3, qkv
+int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
+                     float* x3_out, float* qkv_out, int nb, int J, bool split, cudaStream_t stream);
+
 // LayerNorm over the last dim (C = 64 or 128).  mode 0: nn.LayerNorm (eps 1e-5, biased var);
 // mode 1: a*(x-mean)/(std_unbiased+1e-6)+b (vanilla_transformer_encoder.py:31-34).  gelu: apply after.
 int layernorm_rows(const float* x, float* y, const float* w, const float* b, int rows, int C, int mode,

@@ -320,7 +320,7 @@ const char* kGlobalNames[MDR_NUM_GLOBAL] = {
     "BNORM_SCALE", "BNORM_SHIFT", "BCONV_W", "BCONV_B", "UP_W", "UP_BIAST"};
 const char* kLayerNames[MDRL_NUM] = {
     "N1_W", "N1_B", "WQ", "WKV", "PROJ_W", "PROJ_B", "N2_W", "N2_B", "FC1_W", "FC1_B", "FC2_W", "FC2_B",
-    "CLN_A", "CLN_B", "SQKV_W", "SQKV_B", "SO_W", "SO_B"};
+    "CLN_A", "CLN_B", "SQKV_W", "SQKV_B", "SO_W", "SO_B", "CHAIN"};
 
 constexpr int kDefaultChunk = 148;   // 296 (sample, head) self-attention CTAs = one wave at 2 CTAs / SM
 
@@ -404,11 +404,14 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   if (B == 0) return GATOR_OK;
   GATOR_REQUIRE(B > 0 && a->weights && a->pose2d && a->pose3d && a->feat && a->mesh, "gator_mdr_forward: null buffer");
   const int nslots = MDR_NUM_GLOBAL + GATOR_MDR_LAYERS * MDRL_NUM;
+  bool have_chain = true;
   for (int i = 0; i < nslots; ++i) {
-    if (i == MDR_HEAD_W || a->weights[i]) continue;
-    GATOR_REQUIRE(false, "gator_mdr_forward: weight slot %d is null", i);
+    if (i >= MDR_NUM_GLOBAL && (i - MDR_NUM_GLOBAL) % MDRL_NUM == MDRL_CHAIN) {
+      have_chain = have_chain && a->weights[i] != nullptr;
+      continue;
+    }
+    GATOR_REQUIRE(a->weights[i], "gator_mdr_forward: weight slot %d is null", i);
   }
-  GATOR_REQUIRE(a->weights[MDR_HEAD_W], "gator_mdr_forward: HEAD_W is null");
   const size_t need = gator_mdr_workspace_bytes(B, J, a->chunk);
   if (!a->workspace || a->workspace_bytes < need) {
     set_error("gator_mdr_forward: workspace %zu < %zu bytes", a->workspace_bytes, need);
@@ -438,7 +441,30 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     e.ldr = E;
     GATOR_TRY(gemm(P(32), a->feat + (size_t)b0 * J * 128, 128, G(MDR_JF_WFEAT), 128, GB(MDR_JF_WFEAT), w.jf, E, Mj, E, 128, e, stream));
 
-    for (int l = 0; l < GATOR_MDR_LAYERS; ++l) {
+    // bit 64 of the ablation mask disables the fused layer kernel
+    const bool fused = a->precision != GATOR_PREC_FP32 && have_chain && a->reserved == 0;
+    for (int l = 0; fused && l < GATOR_MDR_LAYERS; ++l) {
+      const int base = MDR_NUM_GLOBAL + l * MDRL_NUM;
+      auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
+      auto WB = [&](int s) { return GB(base + s); };
+      const int pbase = MDR_NUM_GLOBAL + (l > 0 ? l - 1 : l) * MDRL_NUM;     // previous layer's linears.3 bias
+      GATOR_TRY(layernorm_rows(w.jf, w.yj, W(MDRL_N1_W), W(MDRL_N1_B), Mj, E, 0, 0, stream));
+      GATOR_TRY(gemm(prec, w.yj, E, W(MDRL_WKV), E, WB(MDRL_WKV), w.kv, 2 * E, Mj, 2 * E, E, Epilogue(), stream));
+      const float* prm[11] = {static_cast<const float*>(a->weights[pbase + MDRL_SO_B]), W(MDRL_N1_W), W(MDRL_N1_B),
+                              W(MDRL_PROJ_B), W(MDRL_N2_W), W(MDRL_N2_B), W(MDRL_FC1_B), W(MDRL_FC2_B),
+                              W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
+      GATOR_TRY(launch_mdr_chain(l == 0 ? w.x : w.q, l == 0 ? nullptr : w.y, w.kv, a->weights[base + MDRL_CHAIN], prm,
+                                 w.q, w.hid, nb, J, a->precision == GATOR_PREC_BF16X3, stream));
+      GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, a->precision == GATOR_PREC_BF16X3, stream));
+      if (l == GATOR_MDR_LAYERS - 1) {   // last layer: x = x3 + linears.3(att) + b, then the head
+        Epilogue e2;
+        e2.bias = W(MDRL_SO_B);
+        e2.R = w.q;
+        e2.ldr = E;
+        GATOR_TRY(gemm(prec, w.y, E, W(MDRL_SO_W), E, WB(MDRL_SO_W), w.x, E, Mv, E, E, e2, stream));
+      }
+    }
+    for (int l = 0; !fused && l < GATOR_MDR_LAYERS; ++l) {
       const int base = MDR_NUM_GLOBAL + l * MDRL_NUM;
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
       auto WB = [&](int s) { return GB(base + s); };

@@ -1,0 +1,352 @@
+// Fused MDR layer "chain" (lib/models/MDR.py:140-153 minus the 431x431 softmax core):
+// everything that is row-wise between two self-attention cores runs in ONE kernel with the token rows
+// resident on the SM:
+//
+//   x   = x3_prev + selfatt_prev.linears[3](att_prev) + b          (vanilla_transformer_encoder.py:94)   [layers 1,2]
+//   q   = LayerNorm1(x) Wq^T                                        (MDR.py:65, :37)
+//   a   = softmax_J(q k^T / sqrt(32)) v     per head, k/v of the sample's J joints in shared memory  (:40-43)
+//   x  += a Wproj^T + b                                             (:44, :66)
+//   x  += fc2(GELU(fc1(LayerNorm2(x))))                             (:68)
+//   x3  = a2 (x - mean) / (std_unbiased + 1e-6) + b2                (vanilla_transformer_encoder.py:31-34)
+//   qkv = x3 [Wq;Wk;Wv]^T + b                                       (:88-90)          -> x3, qkv to HBM
+//
+// One CTA = 256 consecutive vertex rows of one sample (two M=128 tiles), 256 threads, thread = row: the fp32
+// residual row x lives in that thread's registers, every GEMM is a sequence of 64x64 "units"
+// (A: 128 x 64 bf16 hi/lo image written by the row owners, W: 64 x 64 bf16 hi/lo image streamed from L2 with
+// cp.async into a 3-slot ring, D: 64 TMEM columns per tile), LayerNorm / GELU / the cross-attention run on the
+// rows straight out of TMEM.  14 units per layer; per row only x3_prev + att_prev are read and x3 + qkv
+// written (1.5 KB instead of 8.7 KB for the kernel-per-op pipeline).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace gator {
+namespace {
+
+using namespace umma;
+
+constexpr int V = GATOR_V_COARSE;   // 431
+constexpr int E = 64;
+constexpr int DK = 32;
+constexpr int MAXJ = 32;
+constexpr int UNIT_IMG = 64 * 64 * 2;          // 8 KB: one 64x64 bf16 image
+constexpr int UNIT_BYTES = 2 * UNIT_IMG;       // hi | lo
+constexpr int A_IMG = 128 * 64 * 2;            // 16 KB: 128 rows x 64 k
+constexpr int A_BUF = 2 * A_IMG;               // hi | lo
+constexpr int NUNITS = 14;
+enum { U_SO = 0, U_Q = 1, U_PROJ = 2, U_FC1 = 3, U_FC2 = 7, U_QKV = 11 };
+
+// shared memory map
+constexpr int OFF_A = 0;                              // [tile 2][buf 2][A_BUF]        = 131072
+constexpr int OFF_W = OFF_A + 4 * A_BUF;              // [slot 3][UNIT_BYTES]          =  49152
+constexpr int OFF_KV = OFF_W + 3 * UNIT_BYTES;        // [MAXJ][128] fp32              =  16384
+constexpr int OFF_PRM = OFF_KV + MAXJ * 128 * 4;      // parameters                    =   4352
+constexpr int PRM_FLOATS = 1088;
+constexpr int SMEM_BYTES = OFF_PRM + PRM_FLOATS * 4;  // 200 960
+// parameter offsets (floats)
+enum { P_SO_B = 0, P_N1W = 64, P_N1B = 128, P_PROJ_B = 192, P_N2W = 256, P_N2B = 320, P_FC1_B = 384, P_FC2_B = 640,
+       P_CLN_A = 704, P_CLN_B = 768, P_QKV_B = 832 };
+
+struct ChainParams {
+  const float* x_in;      // (nb*431, 64): layer 0: embedded vertices; layers 1,2: x3 of the previous layer
+  const float* att_in;    // (nb*431, 64) self-attention output of the previous layer, or null (layer 0)
+  const float* kv;        // (nb*J, 128) this layer's cross-attention K | V
+  const uint8_t* blob;    // NUNITS x UNIT_BYTES packed bf16 weight images (unit 0 = previous layer's linears[3])
+  const float* prm[11];   // so_b, n1w, n1b, proj_b, n2w, n2b, fc1_b, fc2_b, cln_a, cln_b, qkv_b
+  float* x3_out;          // (nb*431, 64)
+  float* qkv_out;         // (nb*431, 192)
+  int J;
+  int split;              // 1: 3-term bf16 split products
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ uint4 pack8f(const float* v) {
+  return make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+}
+__device__ __forceinline__ uint4 pack8f_res(const float* v, const uint4& hi) {
+  return make_uint4(pack_bf16(v[0] - bf16_lo_f(hi.x), v[1] - bf16_hi_f(hi.x)), pack_bf16(v[2] - bf16_lo_f(hi.y), v[3] - bf16_hi_f(hi.y)),
+                    pack_bf16(v[4] - bf16_lo_f(hi.z), v[5] - bf16_hi_f(hi.z)), pack_bf16(v[6] - bf16_lo_f(hi.w), v[7] - bf16_hi_f(hi.w)));
+}
+
+// row owner writes 8*NCH consecutive k-values of its row into an A image pair (hi, lo), starting at chunk kc0
+template <int NCH>
+__device__ __forceinline__ void write_a(uint8_t* abuf, int row, int kc0, const float* v) {
+  uint8_t* base = abuf + (row >> 3) * 1024 + (row & 7) * 16;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const uint4 hi = pack8f(v + 8 * c);
+    *reinterpret_cast<uint4*>(base + (kc0 + c) * 128) = hi;
+    *reinterpret_cast<uint4*>(base + A_IMG + (kc0 + c) * 128) = pack8f_res(v + 8 * c, hi);
+  }
+}
+
+__device__ __forceinline__ void ld_acc64(uint32_t taddr, float* v) {
+  tmem_ld32(taddr, v);
+  tmem_ld32(taddr + 32, v + 32);
+  tmem_ld_wait();
+}
+
+__global__ void __launch_bounds__(256, 1)
+mdr_chain_kernel(ChainParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.x >> 1, half = blockIdx.x & 1;
+  const int tile = warp >> 2;                      // 0/1: which M=128 tile of the CTA
+  const int row = (warp & 3) * 32 + lane;          // row in tile = TMEM lane
+  const int vrow = half * 256 + tile * 128 + row;  // vertex index in the sample
+  const bool valid = vrow < V;
+  const size_t grow = (size_t)b * V + (valid ? vrow : 0);
+  uint8_t* a0 = smem + OFF_A + tile * 2 * A_BUF;   // this tile's buffer 0 (n / generic) ...
+  uint8_t* a1 = a0 + A_BUF;                        // ... and buffer 1 (GELU(fc1) quarter)
+  float* skv = reinterpret_cast<float*>(smem + OFF_KV);
+  float* prm = reinterpret_cast<float*>(smem + OFF_PRM);
+  const int J = p.J;
+
+  auto prefetch_w = [&](int unit, int slot) {
+    const uint8_t* src = p.blob + (size_t)unit * UNIT_BYTES;
+    const uint32_t dst = smem_u32(smem + OFF_W + slot * UNIT_BYTES);
+#pragma unroll
+    for (int i = 0; i < UNIT_BYTES / 16 / 256; ++i) cp_async16(dst + (i * 256 + tid) * 16, src + (i * 256 + tid) * 16);
+    cp_async_commit();
+  };
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (tid == 32) {
+    mbar_init(&bar, 1);
+    mbar_init_fence();
+  }
+  const int first_unit = p.att_in ? U_SO : U_Q;
+  prefetch_w(first_unit, 0);
+  for (int i = tid; i < J * 128; i += 256) skv[i] = p.kv[(size_t)b * J * 128 + i];
+  {
+    const int sizes[11] = {64, 64, 64, 64, 64, 64, 256, 64, 64, 64, 192};
+    int off = 0;
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+      for (int i = tid; i < sizes[k]; i += 256) prm[off + i] = p.prm[k][i];
+      off += sizes[k];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+  const uint32_t acc = tmem + lane_addr + tile * 128;        // this tile's unit accumulator (64 cols)
+  const uint32_t acc2 = acc + 64;                            // fc2 accumulator (64 cols)
+  const uint32_t idesc = idesc_bf16(128, 64);
+  uint32_t phase = 0;
+  int slot = 0;
+
+  // One 64x64 unit for both tiles: D[tile] (+)= A[tile][buf] . W[slot]^T, then prefetch the next unit's weights.
+  auto run_unit = [&](int abuf_idx, int dcol, bool accumulate, int next_unit) {
+    cp_async_wait_all();        // this unit's weights have landed (this thread's part)
+    fence_proxy_async();        // A operand written by the row owners + W copies -> async proxy
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      const uint32_t w0 = smem_u32(smem + OFF_W + slot * UNIT_BYTES);
+#pragma unroll
+      for (int t = 0; t < 2; ++t) {
+        const uint32_t abase = smem_u32(smem + OFF_A + (t * 2 + abuf_idx) * A_BUF);
+        const uint32_t d = tmem + t * 128 + dcol;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t ad = smem_desc(abase + ks * 256, 128, 1024), wd = smem_desc(w0 + ks * 256, 128, 1024);
+          const uint32_t accf = (accumulate || ks > 0) ? 1u : 0u;
+          if (p.split) {
+            mma_bf16(d, smem_desc(abase + A_IMG + ks * 256, 128, 1024), wd, idesc, accf);
+            mma_bf16(d, ad, smem_desc(w0 + UNIT_IMG + ks * 256, 128, 1024), idesc, 1);
+            mma_bf16(d, ad, wd, idesc, 1);
+          } else {
+            mma_bf16(d, ad, wd, idesc, accf);
+          }
+        }
+      }
+      mma_commit(&bar);
+    }
+    slot = (slot + 1) % 3;
+    if (next_unit >= 0) prefetch_w(next_unit, slot);   // slot was last read two units ago: its MMAs were waited for
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+  };
+
+  // ---- residual row ----
+  float x[E];
+  {
+    const float4* src = reinterpret_cast<const float4*>(p.x_in + grow * E);
+#pragma unroll
+    for (int i = 0; i < E / 4; ++i) {
+      const float4 t = valid ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+    }
+  }
+  float v[E];
+  if (p.att_in) {   // x = x3_prev + att_prev Wo^T + b
+    const float4* src = reinterpret_cast<const float4*>(p.att_in + grow * E);
+#pragma unroll
+    for (int i = 0; i < E / 4; ++i) {
+      const float4 t = valid ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+    write_a<8>(a0, row, 0, v);
+    run_unit(0, 0, false, U_Q);
+    ld_acc64(acc, v);
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] += v[i] + prm[P_SO_B + i];
+  }
+  // ---- LayerNorm1 -> q ----
+  {
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) mean += x[i];
+    mean *= (1.0f / E);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
+    const float rstd = rsqrtf(var * (1.0f / E) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < E; ++i) v[i] = (x[i] - mean) * rstd * prm[P_N1W + i] + prm[P_N1B + i];
+    write_a<8>(a0, row, 0, v);
+  }
+  run_unit(0, 0, false, U_PROJ);
+  // ---- cross attention against the sample's J joints, one head at a time ----
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    float q[DK];
+    tmem_ld32(acc + h * DK, q);
+    tmem_ld_wait();
+    float s[MAXJ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      if (j < J) {
+        const float4* kr = reinterpret_cast<const float4*>(skv + j * 128 + h * DK);
+        float a = 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < DK / 4; ++d4) {
+          const float4 kk = kr[d4];
+          a = fmaf(q[4 * d4], kk.x, a); a = fmaf(q[4 * d4 + 1], kk.y, a);
+          a = fmaf(q[4 * d4 + 2], kk.z, a); a = fmaf(q[4 * d4 + 3], kk.w, a);
+        }
+        s[j] = a * 0.17677669529663687f;
+        mx = fmaxf(mx, s[j]);
+      }
+    }
+    float l = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j)
+      if (j < J) { s[j] = expf(s[j] - mx); l += s[j]; }
+    const float inv = 1.0f / l;
+    float o[DK];
+#pragma unroll
+    for (int d = 0; d < DK; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < MAXJ; ++j) {
+      if (j < J) {
+        const float pj = s[j] * inv;
+        const float4* vr = reinterpret_cast<const float4*>(skv + j * 128 + E + h * DK);
+#pragma unroll
+        for (int d4 = 0; d4 < DK / 4; ++d4) {
+          const float4 vv = vr[d4];
+          o[4 * d4] = fmaf(pj, vv.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pj, vv.y, o[4 * d4 + 1]);
+          o[4 * d4 + 2] = fmaf(pj, vv.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, vv.w, o[4 * d4 + 3]);
+        }
+      }
+    }
+    write_a<4>(a0, row, h * 4, o);
+  }
+  run_unit(0, 0, false, U_FC1);
+  ld_acc64(acc, v);
+#pragma unroll
+  for (int i = 0; i < E; ++i) x[i] += v[i] + prm[P_PROJ_B + i];
+  // ---- LayerNorm2 -> MLP ----
+  {
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) mean += x[i];
+    mean *= (1.0f / E);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
+    const float rstd = rsqrtf(var * (1.0f / E) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < E; ++i) v[i] = (x[i] - mean) * rstd * prm[P_N2W + i] + prm[P_N2B + i];
+    write_a<8>(a0, row, 0, v);
+  }
+#pragma unroll 1
+  for (int qd = 0; qd < 4; ++qd) {
+    run_unit(0, 0, false, U_FC2 + qd);                     // fc1 quarter qd from LN2(x) (buffer 0 stays intact)
+    ld_acc64(acc, v);
+#pragma unroll
+    for (int i = 0; i < E; ++i) v[i] = gelu_erf(v[i] + prm[P_FC1_B + qd * 64 + i]);
+    write_a<8>(a1, row, 0, v);
+    run_unit(1, 64, qd > 0, qd < 3 ? U_FC1 + qd + 1 : U_QKV);   // fc2 += GELU(.) W2[:, quarter]
+  }
+  ld_acc64(acc2, v);
+#pragma unroll
+  for (int i = 0; i < E; ++i) x[i] += v[i] + prm[P_FC2_B + i];
+  // ---- unbiased-std LayerNorm -> x3 ----
+  {
+    float mean = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) mean += x[i];
+    mean *= (1.0f / E);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
+    const float denom = sqrtf(var * (1.0f / (E - 1))) + 1e-6f;
+#pragma unroll
+    for (int i = 0; i < E; ++i) x[i] = prm[P_CLN_A + i] * (x[i] - mean) / denom + prm[P_CLN_B + i];
+    write_a<8>(a0, row, 0, x);
+    if (valid) {
+      float4* dst = reinterpret_cast<float4*>(p.x3_out + grow * E);
+#pragma unroll
+      for (int i = 0; i < E / 4; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+    }
+  }
+  // ---- q | k | v projections of the self-attention that follows ----
+#pragma unroll 1
+  for (int t3 = 0; t3 < 3; ++t3) {
+    run_unit(0, 0, false, t3 < 2 ? U_QKV + t3 + 1 : -1);
+    ld_acc64(acc, v);
+    if (valid) {
+      float4* dst = reinterpret_cast<float4*>(p.qkv_out + grow * 3 * E + t3 * E);
+#pragma unroll
+      for (int i = 0; i < E / 4; ++i)
+        dst[i] = make_float4(v[4 * i] + prm[P_QKV_B + t3 * E + 4 * i], v[4 * i + 1] + prm[P_QKV_B + t3 * E + 4 * i + 1],
+                             v[4 * i + 2] + prm[P_QKV_B + t3 * E + 4 * i + 2], v[4 * i + 3] + prm[P_QKV_B + t3 * E + 4 * i + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+}  // namespace
+
+// x_in / att_in / kv / outputs as in ChainParams; prm = 11 device pointers (so_b of the PREVIOUS layer first).
+int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
+                     float* x3_out, float* qkv_out, int nb, int J, bool split, cudaStream_t stream) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(mdr_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    attr_done = true;
+  }
+  ChainParams p;
+  p.x_in = x_in; p.att_in = att_in; p.kv = kv; p.blob = static_cast<const uint8_t*>(blob);
+  for (int i = 0; i < 11; ++i) p.prm[i] = prm[i];
+  p.x3_out = x3_out; p.qkv_out = qkv_out; p.J = J; p.split = split ? 1 : 0;
+  mdr_chain_kernel<<<nb * 2, 256, SMEM_BYTES, stream>>>(p);
+  return check_launch("mdr_chain");
+}
+
+}  // namespace gator

@@ -181,6 +181,7 @@ class MDR(nn.Module):
         gnames, lnames = _lib.slot_names('mdr')
         tensors = [t[n] for n in gnames]
         packed = [pack_umma_weight_pair(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
+        prev_so = None
         for sfx in ('', '_1', '_2'):
             enc, sa, cln = getattr(self, 'encoder' + sfx), getattr(self, 'selfatt' + sfx), getattr(self, 'norm' + sfx)
             l = {
@@ -195,6 +196,17 @@ class MDR(nn.Module):
                 'SQKV_B': f(torch.cat([sa.linears[i].bias for i in range(3)], 0)),
                 'SO_W': f(sa.linears[3].weight), 'SO_B': f(sa.linears[3].bias),
             }
+            # 64x64 units of the fused layer kernel (csrc/mdr_chain_umma.cu), each as [hi | lo] tcgen05 images
+            fc1, fc2 = f(enc.mlp.fc1.weight), f(enc.mlp.fc2.weight)
+            units = [prev_so if prev_so is not None else torch.zeros(E, E, device=dev), l['WQ'], l['PROJ_W']]
+            units += [fc1[64 * q:64 * q + 64] for q in range(4)] + [fc2[:, 64 * q:64 * q + 64] for q in range(4)]
+            units += [f(sa.linears[i].weight) for i in range(3)]
+            blob = []
+            for u in units:
+                hi, lo = pack_umma_weight_pair(u.contiguous())
+                blob += [hi.reshape(-1), lo.reshape(-1)]
+            l['CHAIN'] = torch.cat(blob).contiguous()
+            prev_so = l['SO_W']
             tensors += [l[n] for n in lnames]
             packed += [pack_umma_weight_pair(l[n]) if n in _BF16_LAYER else None for n in lnames]
         table = (ctypes.c_void_p * len(tensors))(*[t_.data_ptr() for t_ in tensors])

@@ -154,6 +154,9 @@ typedef enum {
   MDRL_CLN_A, MDRL_CLN_B,           /* (64) norm.a_2, norm.b_2 (unbiased-std LayerNorm)   */
   MDRL_SQKV_W, MDRL_SQKV_B,         /* (192,64),(192) selfatt.linears.0 ; 1 ; 2           */
   MDRL_SO_W, MDRL_SO_B,             /* (64,64),(64)   selfatt.linears.3                   */
+  MDRL_CHAIN,                       /* bf16 blob for the fused layer kernel: 14 units x [hi 8 KB | lo 8 KB] of 64x64
+                                       tcgen05 images: previous layer's linears.3 (zeros for layer 0), wq, proj,
+                                       fc1 row quarters x4, fc2 column quarters x4, selfatt linears.0/1/2; may be NULL */
   MDRL_NUM
 } gator_mdr_layer_slot;
 
