@@ -3,7 +3,7 @@
 // One CTA per (sample, head).  K (432 x 32) and V^T (32 x 432) are staged once as bf16 in the UMMA
 // K-major canonical layout; the 431 queries go through 4 M-tiles of 128.  Per tile:
 //   S = Q K^T      -> TMEM columns [0,432)   (MMAs of N = 224 / 208, K = 32)
-//   row max        -> 256 threads, thread = (row, column half); the whole key range of a row sits in TMEM,
+//   row max        -> 512 threads, thread = (row, column quarter); the whole key range of a row sits in TMEM,
 //                     so it is a plain two-pass softmax - no online rescaling
 //   for each third of the keys (144): P = exp2(.) as bf16 -> shared memory (A operand), O += P V
 //   O (TMEM columns [432,464)) scaled by 1/rowsum on the way out.
@@ -24,12 +24,10 @@ constexpr int DK = 32;
 constexpr int E = 64;
 constexpr int QT = 128;             // query rows per tile
 constexpr int KCH = VP / 8;         // 54 key chunks
-constexpr int HALF = VP / 2;        // 216 columns per thread half (row-max pass)
 constexpr int N0 = 224, N1 = 208;   // S = two MMAs (N <= 256, multiple of 16)
 constexpr int PARTS = 3;
 constexpr int PK = VP / PARTS;      // 144 keys per P part
 constexpr int PCH = PK / 8;         // 18 chunks
-constexpr int PHALF = PK / 2;       // 72 columns per thread in the exp pass
 
 constexpr int SK_BYTES = VP * DK * 2;        // 27 648  K   [kg 54][kc 4][8][8]
 constexpr int SVT_BYTES = DK * VP * 2;       // 27 648  V^T [dg 4][kc 54][8][8]
@@ -61,14 +59,16 @@ __device__ __forceinline__ uint4 pack8_residual(const float* v, const uint4& hi)
                     pack_bf16(v[4] - bf16_lo_f(hi.z), v[5] - bf16_hi_f(hi.z)), pack_bf16(v[6] - bf16_lo_f(hi.w), v[7] - bf16_hi_f(hi.w)));
 }
 
+constexpr int NT = 512;   // 16 warps: (lane quarter 4) x (column quarter 4): 4 threads share a score row
+
 template <bool SPLIT>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(NT, 1)
 mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_s, bar_o;
   __shared__ uint32_t tmem_slot;
-  __shared__ float red_max[2][QT];
-  __shared__ float red_sum[2][QT];
+  __shared__ float red_max[4][QT];
+  __shared__ float red_sum[4][QT];
   // hi images first, lo images (SPLIT only) after them
   uint8_t* sK = smem;
   uint8_t* sVT = sK + SK_BYTES;
@@ -87,7 +87,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     mbar_init_fence();
   }
   // ---- stage K: chunk c = (kg, kc, r) -> key = kg*8 + r, d = kc*8 ----
-  for (int c = tid; c < VP * 4; c += 256) {
+  for (int c = tid; c < VP * 4; c += NT) {
     const int r = c & 7, kc = (c >> 3) & 3, kg = c >> 5;
     const int key = kg * 8 + r;
     float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
@@ -101,7 +101,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     if (SPLIT) reinterpret_cast<uint4*>(sK + LO)[c] = cvt8_residual(a, bb, hi);
   }
   // ---- stage V^T: warp takes a group of 8 keys, lane = d; chunk (dg, kc, r): d = dg*8 + r ----
-  for (int kc = warp; kc < KCH; kc += 8) {
+  for (int kc = warp; kc < KCH; kc += NT / 32) {
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -120,14 +120,16 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   const uint32_t tmem = tmem_slot;
   const uint32_t tmem_o = tmem + VP;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-  const int half = warp >> 2;                       // which column half of the row this thread owns
+  const int cq = warp >> 2;                         // which column quarter of the row this thread owns
+  const int p1_lo = cq < 2 ? cq * 14 : 28 + (cq - 2) * 13, p1_n = cq < 2 ? 14 : 13;   // row-max pass: 54 chunks of 8
+  const int p2_lo = cq < 2 ? cq * 5 : 10 + (cq - 2) * 4, p2_n = cq < 2 ? 5 : 4;        // exp pass: 18 chunks per part
   const int row = (warp & 3) * 32 + lane;           // row within the tile = TMEM lane
   const float c_log2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32)
   uint32_t phase_o = 0;
 
   for (int qt = 0; qt < 4; ++qt) {
     // ---- stage Q tile ----
-    for (int c = tid; c < QT * 4; c += 256) {
+    for (int c = tid; c < QT * 4; c += NT) {
       const int r = c & 7, kc = (c >> 3) & 3, rg = c >> 5;
       const int q = qt * QT + rg * 8 + r;
       float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
@@ -173,28 +175,25 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
 
     // ---- pass 1: row max over this thread's 216 columns ----
     float mx = -INFINITY;
-    for (int j = 0; j < HALF / 8; ++j) {
+    for (int j = 0; j < p1_n; ++j) {
       float s[8];
-      tmem_ld8(tmem + lane_addr + half * HALF + j * 8, s);
+      const int col0 = (p1_lo + j) * 8;
+      tmem_ld8(tmem + lane_addr + col0, s);
       tmem_ld_wait();
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int col = half * HALF + j * 8 + i;
-        mx = fmaxf(mx, col < V ? s[i] : -INFINITY);
-      }
+      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, (col0 + i) < V ? s[i] : -INFINITY);
     }
-    red_max[half][row] = mx;
+    red_max[cq][row] = mx;
     __syncthreads();
-    mx = fmaxf(red_max[0][row], red_max[1][row]) * c_log2;
+    mx = fmaxf(fmaxf(red_max[0][row], red_max[1][row]), fmaxf(red_max[2][row], red_max[3][row])) * c_log2;
 
     // ---- pass 2, one third of the keys at a time: P = exp2(s*c - max*c) -> smem, O += P V ----
     float sum = 0.f;
     for (int part = 0; part < PARTS; ++part) {
       uint8_t* prow = sP + (size_t)(row >> 3) * (PCH * 128) + (row & 7) * 16;
-#pragma unroll 3
-      for (int j = 0; j < PHALF / 8; ++j) {
+      for (int j = 0; j < p2_n; ++j) {
         float s[8];
-        const int col0 = part * PK + half * PHALF + j * 8;
+        const int col0 = part * PK + (p2_lo + j) * 8;
         tmem_ld8(tmem + lane_addr + col0, s);
         tmem_ld_wait();
 #pragma unroll
@@ -203,7 +202,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
           sum += s[i];
         }
         const uint4 hi = pack8(s);
-        const int kc = half * (PHALF / 8) + j;
+        const int kc = p2_lo + j;
         *reinterpret_cast<uint4*>(prow + kc * 128) = hi;
         if (SPLIT) *reinterpret_cast<uint4*>(prow + LO + kc * 128) = pack8_residual(s, hi);
       }
@@ -232,20 +231,19 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
       phase_o ^= 1;
       tc_fence_after();
     }
-    red_sum[half][row] = sum;
+    red_sum[cq][row] = sum;
     __syncthreads();
-    // ---- O tile out: thread = (row, 16-column half) ----
+    // ---- O tile out: thread = (row, 8-column quarter) ----
     {
-      float o[16];
-      tmem_ld16(tmem_o + lane_addr + half * 16, o);
+      float o[8];
+      tmem_ld8(tmem_o + lane_addr + cq * 8, o);
       tmem_ld_wait();
-      const float inv = 1.0f / (red_sum[0][row] + red_sum[1][row]);
+      const float inv = 1.0f / ((red_sum[0][row] + red_sum[1][row]) + (red_sum[2][row] + red_sum[3][row]));
       const int q = qt * QT + row;
       if (q < V) {
-        float* dst = out + ((size_t)b * V + q) * E + h * DK + half * 16;
-#pragma unroll
-        for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(dst + i) = make_float4(o[i] * inv, o[i + 1] * inv, o[i + 2] * inv, o[i + 3] * inv);
+        float* dst = out + ((size_t)b * V + q) * E + h * DK + cq * 8;
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0] * inv, o[1] * inv, o[2] * inv, o[3] * inv);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4] * inv, o[5] * inv, o[6] * inv, o[7] * inv);
       }
     }
     tc_fence_before();
@@ -263,8 +261,8 @@ int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cuda
     cudaFuncSetAttribute(mdr_self_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true));
     attr_done = true;
   }
-  if (split) mdr_self_attn_umma_kernel<true><<<nb * 2, 256, smem_bytes(true), stream>>>(qkv, out);
-  else mdr_self_attn_umma_kernel<false><<<nb * 2, 256, smem_bytes(false), stream>>>(qkv, out);
+  if (split) mdr_self_attn_umma_kernel<true><<<nb * 2, NT, smem_bytes(true), stream>>>(qkv, out);
+  else mdr_self_attn_umma_kernel<false><<<nb * 2, NT, smem_bytes(false), stream>>>(qkv, out);
   return check_launch("mdr_self_attn_umma");
 }
 

@@ -10,8 +10,8 @@
 //   x3  = a2 (x - mean) / (std_unbiased + 1e-6) + b2                (vanilla_transformer_encoder.py:31-34)
 //   qkv = x3 [Wq;Wk;Wv]^T + b                                       (:88-90)          -> x3, qkv to HBM
 //
-// One CTA = 256 consecutive vertex rows of one sample (two M=128 tiles), 256 threads, thread = row: the fp32
-// residual row x lives in that thread's registers, every GEMM is a sequence of 64x64 "units"
+// One CTA = 256 consecutive vertex rows of one sample (two M=128 tiles), 512 threads, two threads per row (one
+// 32-column half each): the fp32 residual row x lives in those threads' registers, every GEMM is a sequence of 64x64 "units"
 // (A: 128 x 64 bf16 hi/lo image written by the row owners, W: 64 x 64 bf16 hi/lo image streamed from L2 with
 // cp.async into a 3-slot ring, D: 64 TMEM columns per tile), LayerNorm / GELU / the cross-attention run on the
 // rows straight out of TMEM.  14 units per layer; per row only x3_prev + att_prev are read and x3 + qkv
@@ -84,35 +84,39 @@ __device__ __forceinline__ void write_a(uint8_t* abuf, int row, int kc0, const f
   }
 }
 
-__device__ __forceinline__ void ld_acc64(uint32_t taddr, float* v) {
-  tmem_ld32(taddr, v);
-  tmem_ld32(taddr + 32, v + 32);
-  tmem_ld_wait();
-}
+constexpr int NT = 512;   // 16 warps: (tile 2) x (column half 2) x (lane quarter 4)
 
-__global__ void __launch_bounds__(256, 1)
+__device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+// LayerNorm statistics of a 64-wide row held as two 32-wide halves by two threads (different warps): each half does
+// its own two-pass mean / M2 and the halves are combined with the parallel-variance formula (see `stats` below).
+__global__ void __launch_bounds__(NT, 1)
 mdr_chain_kernel(ChainParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
+  __shared__ float2 xch_buf[3][2][128][2];          // [LayerNorm #][tile][row][{mine, partner} by column half]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x >> 1, half = blockIdx.x & 1;
-  const int tile = warp >> 2;                      // 0/1: which M=128 tile of the CTA
+  const int tile = warp >> 3;                      // 0/1: which M=128 tile of the CTA
+  const int ch = (warp >> 2) & 1;                  // which 32-column half of the 64-wide row this thread owns
   const int row = (warp & 3) * 32 + lane;          // row in tile = TMEM lane
   const int vrow = half * 256 + tile * 128 + row;  // vertex index in the sample
   const bool valid = vrow < V;
   const size_t grow = (size_t)b * V + (valid ? vrow : 0);
+  const int pair_id = 1 + tile * 4 + (warp & 3);   // named barrier shared by the two warps that own the same rows
   uint8_t* a0 = smem + OFF_A + tile * 2 * A_BUF;   // this tile's buffer 0 (n / generic) ...
   uint8_t* a1 = a0 + A_BUF;                        // ... and buffer 1 (GELU(fc1) quarter)
   float* skv = reinterpret_cast<float*>(smem + OFF_KV);
   float* prm = reinterpret_cast<float*>(smem + OFF_PRM);
   const int J = p.J;
+  const int c0 = ch * 32;                          // first column of this thread's half
 
   auto prefetch_w = [&](int unit, int slot) {
     const uint8_t* src = p.blob + (size_t)unit * UNIT_BYTES;
     const uint32_t dst = smem_u32(smem + OFF_W + slot * UNIT_BYTES);
 #pragma unroll
-    for (int i = 0; i < UNIT_BYTES / 16 / 256; ++i) cp_async16(dst + (i * 256 + tid) * 16, src + (i * 256 + tid) * 16);
+    for (int i = 0; i < UNIT_BYTES / 16 / NT; ++i) cp_async16(dst + (i * NT + tid) * 16, src + (i * NT + tid) * 16);
     cp_async_commit();
   };
 
@@ -123,13 +127,13 @@ mdr_chain_kernel(ChainParams p) {
   }
   const int first_unit = p.att_in ? U_SO : U_Q;
   prefetch_w(first_unit, 0);
-  for (int i = tid; i < J * 128; i += 256) skv[i] = p.kv[(size_t)b * J * 128 + i];
+  for (int i = tid; i < J * 128; i += NT) skv[i] = p.kv[(size_t)b * J * 128 + i];
   {
     const int sizes[11] = {64, 64, 64, 64, 64, 64, 256, 64, 64, 64, 192};
     int off = 0;
 #pragma unroll
     for (int k = 0; k < 11; ++k) {
-      for (int i = tid; i < sizes[k]; i += 256) prm[off + i] = p.prm[k][i];
+      for (int i = tid; i < sizes[k]; i += NT) prm[off + i] = p.prm[k][i];
       off += sizes[k];
     }
   }
@@ -138,8 +142,8 @@ mdr_chain_kernel(ChainParams p) {
   tc_fence_after();
   const uint32_t tmem = tmem_slot;
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-  const uint32_t acc = tmem + lane_addr + tile * 128;        // this tile's unit accumulator (64 cols)
-  const uint32_t acc2 = acc + 64;                            // fc2 accumulator (64 cols)
+  const uint32_t acc = tmem + lane_addr + tile * 128 + c0;   // this thread's 32 columns of the unit accumulator
+  const uint32_t acc2 = acc + 64;                            // ... and of the fc2 accumulator
   const uint32_t idesc = idesc_bf16(128, 64);
   uint32_t phase = 0;
   int slot = 0;
@@ -178,58 +182,63 @@ mdr_chain_kernel(ChainParams p) {
     phase ^= 1;
     tc_fence_after();
   };
-
-  // ---- residual row ----
-  float x[E];
-  {
-    const float4* src = reinterpret_cast<const float4*>(p.x_in + grow * E);
+  auto ld32 = [&](uint32_t taddr, float* v) { tmem_ld32(taddr, v); tmem_ld_wait(); };
+  auto load_row32 = [&](const float* base, float* v) {
+    const float4* src = reinterpret_cast<const float4*>(base + grow * E + c0);
 #pragma unroll
-    for (int i = 0; i < E / 4; ++i) {
-      const float4 t = valid ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
-    }
-  }
-  float v[E];
-  if (p.att_in) {   // x = x3_prev + att_prev Wo^T + b
-    const float4* src = reinterpret_cast<const float4*>(p.att_in + grow * E);
-#pragma unroll
-    for (int i = 0; i < E / 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const float4 t = valid ? src[i] : make_float4(0.f, 0.f, 0.f, 0.f);
       v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
     }
-    write_a<8>(a0, row, 0, v);
-    run_unit(0, 0, false, U_Q);
-    ld_acc64(acc, v);
+  };
+  auto stats = [&](const float* xr, int which, float& mean, float& m2) {
+    float2* base = &xch_buf[which][tile][row][0];
+    float m = 0.f;
 #pragma unroll
-    for (int i = 0; i < E; ++i) x[i] += v[i] + prm[P_SO_B + i];
+    for (int i = 0; i < 32; ++i) m += xr[i];
+    m *= (1.0f / 32);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { const float d = xr[i] - m; q = fmaf(d, d, q); }
+    base[ch] = make_float2(m, q);
+    pair_sync(pair_id);
+    const float2 o = base[1 - ch];
+    const float dm = m - o.x;
+    mean = 0.5f * (m + o.x);
+    m2 = (q + o.y) + dm * dm * 16.0f;
+  };
+
+  // ---- residual row (this thread's 32 columns) ----
+  float x[32], v[32];
+  load_row32(p.x_in, x);
+  if (p.att_in) {   // x = x3_prev + att_prev Wo^T + b
+    load_row32(p.att_in, v);
+    write_a<4>(a0, row, ch * 4, v);
+    run_unit(0, 0, false, U_Q);
+    ld32(acc, v);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) x[i] += v[i] + prm[P_SO_B + c0 + i];
   }
   // ---- LayerNorm1 -> q ----
   {
-    float mean = 0.f;
+    float mean, m2;
+    stats(x, 0, mean, m2);
+    const float rstd = rsqrtf(m2 * (1.0f / E) + 1e-5f);
 #pragma unroll
-    for (int i = 0; i < E; ++i) mean += x[i];
-    mean *= (1.0f / E);
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < E; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
-    const float rstd = rsqrtf(var * (1.0f / E) + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < E; ++i) v[i] = (x[i] - mean) * rstd * prm[P_N1W + i] + prm[P_N1B + i];
-    write_a<8>(a0, row, 0, v);
+    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * prm[P_N1W + c0 + i] + prm[P_N1B + c0 + i];
+    write_a<4>(a0, row, ch * 4, v);
   }
   run_unit(0, 0, false, U_PROJ);
-  // ---- cross attention against the sample's J joints, one head at a time ----
-#pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
+  // ---- cross attention against the sample's J joints: this thread owns head `ch` of its row ----
+  {
     float q[DK];
-    tmem_ld32(acc + h * DK, q);
-    tmem_ld_wait();
+    ld32(acc, q);
     float s[MAXJ];
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
       if (j < J) {
-        const float4* kr = reinterpret_cast<const float4*>(skv + j * 128 + h * DK);
+        const float4* kr = reinterpret_cast<const float4*>(skv + j * 128 + c0);
         float a = 0.f;
 #pragma unroll
         for (int d4 = 0; d4 < DK / 4; ++d4) {
@@ -246,84 +255,73 @@ mdr_chain_kernel(ChainParams p) {
     for (int j = 0; j < MAXJ; ++j)
       if (j < J) { s[j] = expf(s[j] - mx); l += s[j]; }
     const float inv = 1.0f / l;
-    float o[DK];
 #pragma unroll
-    for (int d = 0; d < DK; ++d) o[d] = 0.f;
+    for (int d = 0; d < DK; ++d) v[d] = 0.f;
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) {
       if (j < J) {
         const float pj = s[j] * inv;
-        const float4* vr = reinterpret_cast<const float4*>(skv + j * 128 + E + h * DK);
+        const float4* vr = reinterpret_cast<const float4*>(skv + j * 128 + E + c0);
 #pragma unroll
         for (int d4 = 0; d4 < DK / 4; ++d4) {
           const float4 vv = vr[d4];
-          o[4 * d4] = fmaf(pj, vv.x, o[4 * d4]); o[4 * d4 + 1] = fmaf(pj, vv.y, o[4 * d4 + 1]);
-          o[4 * d4 + 2] = fmaf(pj, vv.z, o[4 * d4 + 2]); o[4 * d4 + 3] = fmaf(pj, vv.w, o[4 * d4 + 3]);
+          v[4 * d4] = fmaf(pj, vv.x, v[4 * d4]); v[4 * d4 + 1] = fmaf(pj, vv.y, v[4 * d4 + 1]);
+          v[4 * d4 + 2] = fmaf(pj, vv.z, v[4 * d4 + 2]); v[4 * d4 + 3] = fmaf(pj, vv.w, v[4 * d4 + 3]);
         }
       }
     }
-    write_a<4>(a0, row, h * 4, o);
+    write_a<4>(a0, row, ch * 4, v);
   }
   run_unit(0, 0, false, U_FC1);
-  ld_acc64(acc, v);
+  ld32(acc, v);
 #pragma unroll
-  for (int i = 0; i < E; ++i) x[i] += v[i] + prm[P_PROJ_B + i];
+  for (int i = 0; i < 32; ++i) x[i] += v[i] + prm[P_PROJ_B + c0 + i];
   // ---- LayerNorm2 -> MLP ----
   {
-    float mean = 0.f;
+    float mean, m2;
+    stats(x, 1, mean, m2);
+    const float rstd = rsqrtf(m2 * (1.0f / E) + 1e-5f);
 #pragma unroll
-    for (int i = 0; i < E; ++i) mean += x[i];
-    mean *= (1.0f / E);
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < E; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
-    const float rstd = rsqrtf(var * (1.0f / E) + 1e-5f);
-#pragma unroll
-    for (int i = 0; i < E; ++i) v[i] = (x[i] - mean) * rstd * prm[P_N2W + i] + prm[P_N2B + i];
-    write_a<8>(a0, row, 0, v);
+    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * prm[P_N2W + c0 + i] + prm[P_N2B + c0 + i];
+    write_a<4>(a0, row, ch * 4, v);
   }
 #pragma unroll 1
   for (int qd = 0; qd < 4; ++qd) {
     run_unit(0, 0, false, U_FC2 + qd);                     // fc1 quarter qd from LN2(x) (buffer 0 stays intact)
-    ld_acc64(acc, v);
+    ld32(acc, v);
 #pragma unroll
-    for (int i = 0; i < E; ++i) v[i] = gelu_erf(v[i] + prm[P_FC1_B + qd * 64 + i]);
-    write_a<8>(a1, row, 0, v);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i] + prm[P_FC1_B + qd * 64 + c0 + i]);
+    write_a<4>(a1, row, ch * 4, v);
     run_unit(1, 64, qd > 0, qd < 3 ? U_FC1 + qd + 1 : U_QKV);   // fc2 += GELU(.) W2[:, quarter]
   }
-  ld_acc64(acc2, v);
+  ld32(acc2, v);
 #pragma unroll
-  for (int i = 0; i < E; ++i) x[i] += v[i] + prm[P_FC2_B + i];
+  for (int i = 0; i < 32; ++i) x[i] += v[i] + prm[P_FC2_B + c0 + i];
   // ---- unbiased-std LayerNorm -> x3 ----
   {
-    float mean = 0.f;
+    float mean, m2;
+    stats(x, 2, mean, m2);
+    const float denom = sqrtf(m2 * (1.0f / (E - 1))) + 1e-6f;
 #pragma unroll
-    for (int i = 0; i < E; ++i) mean += x[i];
-    mean *= (1.0f / E);
-    float var = 0.f;
-#pragma unroll
-    for (int i = 0; i < E; ++i) { const float d = x[i] - mean; var = fmaf(d, d, var); }
-    const float denom = sqrtf(var * (1.0f / (E - 1))) + 1e-6f;
-#pragma unroll
-    for (int i = 0; i < E; ++i) x[i] = prm[P_CLN_A + i] * (x[i] - mean) / denom + prm[P_CLN_B + i];
-    write_a<8>(a0, row, 0, x);
+    for (int i = 0; i < 32; ++i) x[i] = prm[P_CLN_A + c0 + i] * (x[i] - mean) / denom + prm[P_CLN_B + c0 + i];
+    write_a<4>(a0, row, ch * 4, x);
     if (valid) {
-      float4* dst = reinterpret_cast<float4*>(p.x3_out + grow * E);
+      float4* dst = reinterpret_cast<float4*>(p.x3_out + grow * E + c0);
 #pragma unroll
-      for (int i = 0; i < E / 4; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+      for (int i = 0; i < 8; ++i) dst[i] = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
     }
   }
   // ---- q | k | v projections of the self-attention that follows ----
 #pragma unroll 1
   for (int t3 = 0; t3 < 3; ++t3) {
     run_unit(0, 0, false, t3 < 2 ? U_QKV + t3 + 1 : -1);
-    ld_acc64(acc, v);
+    ld32(acc, v);
     if (valid) {
-      float4* dst = reinterpret_cast<float4*>(p.qkv_out + grow * 3 * E + t3 * E);
+      float4* dst = reinterpret_cast<float4*>(p.qkv_out + grow * 3 * E + t3 * E + c0);
+      const float* bq = prm + P_QKV_B + t3 * E + c0;
 #pragma unroll
-      for (int i = 0; i < E / 4; ++i)
-        dst[i] = make_float4(v[4 * i] + prm[P_QKV_B + t3 * E + 4 * i], v[4 * i + 1] + prm[P_QKV_B + t3 * E + 4 * i + 1],
-                             v[4 * i + 2] + prm[P_QKV_B + t3 * E + 4 * i + 2], v[4 * i + 3] + prm[P_QKV_B + t3 * E + 4 * i + 3]);
+      for (int i = 0; i < 8; ++i)
+        dst[i] = make_float4(v[4 * i] + bq[4 * i], v[4 * i + 1] + bq[4 * i + 1], v[4 * i + 2] + bq[4 * i + 2], v[4 * i + 3] + bq[4 * i + 3]);
     }
   }
   tc_fence_before();
@@ -345,7 +343,7 @@ int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, co
   p.x_in = x_in; p.att_in = att_in; p.kv = kv; p.blob = static_cast<const uint8_t*>(blob);
   for (int i = 0; i < 11; ++i) p.prm[i] = prm[i];
   p.x3_out = x3_out; p.qkv_out = qkv_out; p.J = J; p.split = split ? 1 : 0;
-  mdr_chain_kernel<<<nb * 2, 256, SMEM_BYTES, stream>>>(p);
+  mdr_chain_kernel<<<nb * 2, NT, SMEM_BYTES, stream>>>(p);
   return check_launch("mdr_chain");
 }
 

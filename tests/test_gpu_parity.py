@@ -55,10 +55,11 @@ def test_gemm_f32(models, M, N, K):
     from gator_b200.packing import pack_umma_weight_pair
     hi, lo = pack_umma_weight_pair(W.to(DEV))
     Ad, Cbuf = A.to(DEV), torch.full((M, N), float('nan'), device=DEV)
+    bd, rd, Rd = bias.to(DEV), rows.to(DEV), R.to(DEV)      # keep the device buffers alive across the launch
     a = _lib.GemmArgs(M=M, N=N, K=K, lda=K, ldw=K, ldc=N, ldr=N, act=1, bias_period=5, precision=2, A=_lib.ptr(Ad), W=_lib.ptr(hi),
-                      W_lo=_lib.ptr(lo), bias=_lib.ptr(bias.to(DEV)), bias_rows=_lib.ptr(rows.to(DEV)), R=_lib.ptr(R.to(DEV)), C=_lib.ptr(Cbuf))
+                      W_lo=_lib.ptr(lo), bias=_lib.ptr(bd), bias_rows=_lib.ptr(rd), R=_lib.ptr(Rd), C=_lib.ptr(Cbuf))
     _lib.check(_lib.lib().gator_gemm(a, _lib.stream_ptr()), 'gator_gemm bf16x3')
-    assert (Cbuf.cpu().double() - ref).abs().max() < 2e-4
+    assert (Cbuf.cpu().double() - ref).abs().max() < 1e-4 + 1e-4 * ref.abs().max()
 
 
 @pytest.mark.parametrize('tag', ['h36m', 'coco'])
