@@ -220,6 +220,43 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = t.item()
 
+    # ---- batch-1 latency (BASELINE metric: p50 batch-1 latency), eager and under a CUDA graph ----
+    latency = None
+    if rank == 0:
+        x1 = x[:1].clone()
+        with torch.no_grad():
+            for _ in range(5):
+                model(x1)
+            torch.cuda.synchronize()
+
+            def p50(fn, iters=300):
+                ts = []
+                for _ in range(iters):
+                    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(); fn(); b_.record(); b_.synchronize()
+                    ts.append(a.elapsed_time(b_))
+                ts.sort()
+                return ts[len(ts) // 2]
+            eager = p50(lambda: model(x1))
+            graph_ms = None
+            try:
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    model(x1)
+                torch.cuda.current_stream().wait_stream(side)
+                with torch.cuda.graph(g):
+                    gm, gp = model(x1)
+                g.replay(); torch.cuda.synchronize()
+                ref_m, _ = model(x1)
+                assert torch.equal(gm, ref_m)
+                graph_ms = p50(g.replay)
+            except Exception as e:   # report, do not hide
+                graph_ms = f'capture failed: {type(e).__name__}: {e}'
+        latency = {'batch': 1, 'p50_ms_eager': eager, 'p50_ms_cuda_graph': graph_ms, 'iters': 300,
+                   'timing': 'CUDA events around each forward, inputs resident'}
+
     line = None
     if rank == 0:
         peaks = measured_peaks()
@@ -272,6 +309,7 @@ def run_b200(args):
                 'gpu_launches': int(launches),
                 'tflops_effective': FLOP_PER_MESH * value / 1e12,
                 'wall_s_timed_region': t_wall,
+                'latency_b1': latency,
                 'roofline': roofline, 'parity': parity,
                 'cpu_baseline': {'value': cpu_v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                                  'sample': f'{cpu_n} forwards of batch 64 (median {cpu_med * 1e3:.0f} ms), oracle port of the reference forward'}}
