@@ -185,12 +185,14 @@ const char* kBlockNames[GATB_NUM] = {
     "LN1_W", "LN1_B", "QKV_W", "QKV_B", "PROJ_W", "PROJ_B", "GCN_W01", "GCN_M", "GCN_ADIAG", "GCN_AOFF",
     "GCN_BIAS", "XF_W01", "XF_B01", "XF_WB", "XF_BB", "LN2_W", "LN2_B", "FC1_W", "FC1_B", "FC2_W", "FC2_B"};
 
-constexpr int kDefaultChunk = 1024;
+// default chunk: 296 GEMM M-tiles of 128 token rows = two full waves of the 148 SMs (a 1024-sample chunk
+// of J=19 gives 152 tiles: one wave plus a 4-CTA tail that costs as much as the wave)
+constexpr int kTilesPerChunk = 296;
 // per token row: x 128 | n 128 | big 512 | o 128 | h 256 | g 128
 constexpr size_t kRowFloats = 128 + 128 + 512 + 128 + 256 + 128;
 
-int resolve_chunk(int batch, int chunk) {
-  if (chunk <= 0) chunk = kDefaultChunk;
+int resolve_chunk(int batch, int chunk, int J) {
+  if (chunk <= 0) chunk = kTilesPerChunk * 128 / J;
   return chunk < batch ? chunk : batch;
 }
 
@@ -208,7 +210,7 @@ extern "C" const char* gator_gat_slot_name(int slot) {
 extern "C" size_t gator_gat_workspace_bytes(int32_t batch, int32_t num_joint, int32_t chunk) {
   using namespace gator;
   if (batch <= 0 || num_joint <= 0) return 0;
-  const int cb = resolve_chunk(batch, chunk);
+  const int cb = resolve_chunk(batch, chunk, num_joint);
   return align_up((size_t)cb * num_joint * kRowFloats * sizeof(float), 256);
 }
 
@@ -233,7 +235,7 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
   auto G = [&](int s) { return static_cast<const float*>(a->weights[s]); };
   auto GB = [&](int s) { PackedW w; w.hi = a->weights_bf16 ? a->weights_bf16[s] : nullptr; w.lo = a->weights_bf16_lo ? a->weights_bf16_lo[s] : nullptr; return w; };
   const int prec = a->precision;
-  const int cb = resolve_chunk(B, a->chunk);
+  const int cb = resolve_chunk(B, a->chunk, J);
   const size_t rows_max = (size_t)cb * J;
   float* ws = static_cast<float*>(a->workspace);
   float* x = ws;

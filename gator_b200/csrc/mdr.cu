@@ -334,7 +334,9 @@ struct Ws {
   size_t bytes;
 };
 
-Ws carve(float* base, int nb, int J) {
+constexpr int kSuperChunk = 8192;   // samples per upsample_conv GEMM launch (im2col rows kept for that many)
+
+Ws carve(float* base, int nb, int J, int nsuper) {
   Ws w;
   const size_t mv = (size_t)nb * V, mj = (size_t)nb * J;
   size_t off = 0;
@@ -348,7 +350,7 @@ Ws carve(float* base, int nb, int J) {
   w.kv = take(mj * 2 * E);
   w.hd = take(mv * HEADN);
   w.coarse = take((size_t)nb * V * 3);
-  w.a3 = take((size_t)nb * 3 * UPK);
+  w.a3 = take((size_t)nsuper * 3 * UPK);
   w.bytes = off * sizeof(float);
   return w;
 }
@@ -367,7 +369,7 @@ extern "C" const char* gator_mdr_slot_name(int slot) {
 extern "C" size_t gator_mdr_workspace_bytes(int32_t batch, int32_t num_joint, int32_t chunk) {
   using namespace gator;
   if (batch <= 0 || num_joint <= 0) return 0;
-  return align_up(carve(nullptr, resolve_chunk(batch, chunk), num_joint).bytes, 256);
+  return align_up(carve(nullptr, resolve_chunk(batch, chunk), num_joint, batch < kSuperChunk ? batch : kSuperChunk).bytes, 256);
 }
 
 namespace gator {
@@ -425,10 +427,13 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   auto P = [&](int bit) { return (a->precision != GATOR_PREC_FP32 && (mask & bit)) ? a->precision : (int)GATOR_PREC_FP32; };
   const int prec = P(2);
   const int cb = resolve_chunk(B, a->chunk);
-  Ws w = carve(static_cast<float*>(a->workspace), cb, J);
+  const int nsuper = B < kSuperChunk ? B : kSuperChunk;
+  Ws w = carve(static_cast<float*>(a->workspace), cb, J, nsuper);
 
-  for (int b0 = 0; b0 < B; b0 += cb) {
-    const int nb = (B - b0 < cb) ? B - b0 : cb;
+  for (int s0 = 0; s0 < B; s0 += nsuper) {
+  const int ns = (B - s0 < nsuper) ? B - s0 : nsuper;
+  for (int b0 = s0; b0 < s0 + ns; b0 += cb) {
+    const int nb = (s0 + ns - b0 < cb) ? s0 + ns - b0 : cb;
     const int Mv = nb * V, Mj = nb * J;
     mdr_embed_kernel<<<nb, 256, 0, stream>>>(a->pose2d + (size_t)b0 * J * 2, a->pose3d + (size_t)b0 * J * 3,
                                              G(MDR_JF_WPOSE), G(MDR_VF_CONST), G(MDR_VF_W3),
@@ -508,13 +513,15 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     e.bias = G(MDR_HEAD_B);
     GATOR_TRY(gemm(P(8), w.x, E, G(MDR_HEAD_W), E, GB(MDR_HEAD_W), w.hd, HEADN, Mv, HEADN, E, e, stream));
     mdr_head_kernel<<<nb, 256, 0, stream>>>(w.hd, G(MDR_BNORM_SCALE), G(MDR_BNORM_SHIFT), G(MDR_BCONV_W),
-                                            G(MDR_BCONV_B), a->alpha, a->coarse ? a->coarse + (size_t)b0 * V * 3 : nullptr, w.a3);
+                                            G(MDR_BCONV_B), a->alpha, a->coarse ? a->coarse + (size_t)b0 * V * 3 : nullptr,
+                                            w.a3 + (size_t)(b0 - s0) * 3 * UPK);
     GATOR_TRY(check_launch("mdr_head"));
-    // upsample_conv + template: (3 nb) x 1296 @ 1296 x 6890, scattered to (b, vertex, xyz)
-    e = Epilogue();
-    e.conv3 = 1;
-    e.bias_rows = G(MDR_UP_BIAST);
-    GATOR_TRY(gemm(P(16), w.a3, UPK, G(MDR_UP_W), UPK, GB(MDR_UP_W), a->mesh + (size_t)b0 * VF * 3, 0, nb * 3, VF, UPK, e, stream));
+  }
+  // upsample_conv + template for the whole super-chunk: (3 ns) x 1296 @ 1296 x 6890, scattered to (b, vertex, xyz)
+  Epilogue e;
+  e.conv3 = 1;
+  e.bias_rows = G(MDR_UP_BIAST);
+  GATOR_TRY(gemm(P(16), w.a3, UPK, G(MDR_UP_W), UPK, GB(MDR_UP_W), a->mesh + (size_t)s0 * VF * 3, 0, ns * 3, VF, UPK, e, stream));
   }
   return GATOR_OK;
 }

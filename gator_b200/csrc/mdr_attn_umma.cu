@@ -175,13 +175,24 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
 
     // ---- pass 1: row max over this thread's 216 columns ----
     float mx = -INFINITY;
-    for (int j = 0; j < p1_n; ++j) {
-      float s[8];
-      const int col0 = (p1_lo + j) * 8;
-      tmem_ld8(tmem + lane_addr + col0, s);
-      tmem_ld_wait();
+    {
+      // 13 or 14 chunks of 8 columns: loads issued in batches of up to 7 before one wait
+      float s[7][8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) mx = fmaxf(mx, (col0 + i) < V ? s[i] : -INFINITY);
+      for (int jb = 0; jb < 14; jb += 7) {
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+          if (jb + j < p1_n) tmem_ld8(tmem + lane_addr + (p1_lo + jb + j) * 8, s[j]);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+          if (jb + j < p1_n) {
+            const int col0 = (p1_lo + jb + j) * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, (col0 + i) < V ? s[j][i] : -INFINITY);
+          }
+        }
+      }
     }
     red_max[cq][row] = mx;
     __syncthreads();
@@ -191,20 +202,26 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     float sum = 0.f;
     for (int part = 0; part < PARTS; ++part) {
       uint8_t* prow = sP + (size_t)(row >> 3) * (PCH * 128) + (row & 7) * 16;
-      for (int j = 0; j < p2_n; ++j) {
-        float s[8];
-        const int col0 = part * PK + (p2_lo + j) * 8;
-        tmem_ld8(tmem + lane_addr + col0, s);
-        tmem_ld_wait();
+      float sc[5][8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          s[i] = (col0 + i) < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
-          sum += s[i];
+      for (int j = 0; j < 5; ++j)
+        if (j < p2_n) tmem_ld8(tmem + lane_addr + part * PK + (p2_lo + j) * 8, sc[j]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 5; ++j) {
+        if (j < p2_n) {
+          float* s = sc[j];
+          const int col0 = part * PK + (p2_lo + j) * 8;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            s[i] = (col0 + i) < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
+            sum += s[i];
+          }
+          const uint4 hi = pack8(s);
+          const int kc = p2_lo + j;
+          *reinterpret_cast<uint4*>(prow + kc * 128) = hi;
+          if (SPLIT) *reinterpret_cast<uint4*>(prow + LO + kc * 128) = pack8_residual(s, hi);
         }
-        const uint4 hi = pack8(s);
-        const int kc = p2_lo + j;
-        *reinterpret_cast<uint4*>(prow + kc * 128) = hi;
-        if (SPLIT) *reinterpret_cast<uint4*>(prow + LO + kc * 128) = pack8_residual(s, hi);
       }
       fence_proxy_async();
       tc_fence_before();
