@@ -150,57 +150,71 @@ smpl_pose_kernel(PoseParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Skinning.  CTA = 256 consecutive vertices x SG consecutive samples.  Per sample: the 24 transforms go
-// to shared memory, each thread blends its vertex's KW transforms, applies them to v_posed and parks
-// the 3 outputs in shared memory; the 768-float segment is then written with aligned float4 stores
-// (a sample row is 82 680 B = 8 mod 16, so odd samples start mid-float4: 2-float head/tail).
+// Skinning (smpl_layer.py:134-145).  HBM-bound: per mesh 82 680 B written (v_posed comes from L2, the
+// producer GEMM runs on the same 512-sample chunk).  CTA = 256 consecutive vertices x SG samples, 8 warps;
+// the SG x 24 joint transforms are staged once, then every warp runs on its own 32 vertices with no
+// block-level synchronisation: coalesced 8-byte loads of the 96-float v_posed segment -> warp-private
+// shared memory -> lane = vertex (ELL weights in registers, reused across the SG samples) -> warp-private
+// shared memory -> coalesced 8-byte stores (a sample row is 82 680 B = 8 mod 16, so 8 bytes is the widest
+// access that is aligned for every sample; each store instruction still covers 256 contiguous bytes).
+// The next sample's segment is prefetched into registers while the current one is processed.
 // ---------------------------------------------------------------------------------------------
 constexpr int SK_VT = 256;
-constexpr int SK_SG = 8;
+constexpr int SK_SG = 16;
 
 __global__ void __launch_bounds__(SK_VT)
 smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ amat, const float* __restrict__ offset,
                  const int* __restrict__ sidx, const float* __restrict__ sw, int KW, float* __restrict__ verts, int batch) {
-  __shared__ __align__(16) float sA[NJ * 12];
-  __shared__ __align__(16) float sin_[SK_VT * 3 + 4];
-  __shared__ __align__(16) float sout[SK_VT * 3 + 4];
-  __shared__ float soff[3];
-  const int tid = threadIdx.x;
-  const int v0 = blockIdx.x * SK_VT;
-  const int nv = min(SK_VT, NV - v0);
-  const int v = v0 + tid;
-  const bool active = tid < nv;
+  __shared__ __align__(16) float sA[SK_SG][NJ * 12];
+  __shared__ float soff[SK_SG][4];
+  __shared__ __align__(16) float stage[SK_VT / 32][96];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int v0w = blockIdx.x * SK_VT + warp * 32;          // first vertex of this warp
+  const int nvw = max(0, min(32, NV - v0w));               // vertices this warp owns (last tile is ragged)
+  const int v = v0w + lane;
+  const bool active = lane < nvw;
+  const int s_begin = blockIdx.y * SK_SG;
+  const int ns = min(SK_SG, batch - s_begin);
+  for (int i = tid; i < ns * NJ * 12; i += SK_VT) (&sA[0][0])[i] = amat[(size_t)s_begin * NJ * 12 + i];
+  for (int i = tid; i < ns * 3; i += SK_VT) soff[i / 3][i % 3] = offset[(size_t)s_begin * 3 + i];
   int jid[4];
   float jw[4];
-  if (KW <= 4) {
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      jid[k] = (active && k < KW) ? __ldg(sidx + (size_t)v * KW + k) : 0;
-      jw[k] = (active && k < KW) ? __ldg(sw + (size_t)v * KW + k) : 0.f;
-    }
+  for (int k = 0; k < 4; ++k) {
+    jid[k] = (active && k < KW && KW <= 4) ? __ldg(sidx + (size_t)v * KW + k) : 0;
+    jw[k] = (active && k < KW && KW <= 4) ? __ldg(sw + (size_t)v * KW + k) : 0.f;
   }
-  const int s_begin = blockIdx.y * SK_SG;
-  const int s_end = min(batch, s_begin + SK_SG);
-  const int seg = nv * 3;
-  for (int s = s_begin; s < s_end; ++s) {
-    __syncthreads();   // previous sample's sout/sA fully consumed
-    for (int i = tid; i < NJ * 12; i += SK_VT) sA[i] = amat[(size_t)s * NJ * 12 + i];
-    if (tid < 3) soff[tid] = offset[(size_t)s * 3 + tid];
-    {
-      // v_posed segment: 8-byte aligned always -> float2 loads
-      const float2* src = reinterpret_cast<const float2*>(vposed + (size_t)s * NV3 + (size_t)v0 * 3);
-      for (int i = tid; i < seg / 2; i += SK_VT) *reinterpret_cast<float2*>(&sin_[i * 2]) = src[i];
-      if ((seg & 1) && tid == 0) sin_[seg - 1] = vposed[(size_t)s * NV3 + (size_t)v0 * 3 + seg - 1];
+  __syncthreads();
+  if (nvw == 0) return;
+  const int seg2 = nvw * 3 / 2;                            // float2 per segment (nvw*3 is even: 96 or 42)
+  float* st = stage[warp];
+  auto seg_ptr = [&](const float* base, int s) { return base + (size_t)(s_begin + s) * NV3 + (size_t)v0w * 3; };
+  float2 pre0 = make_float2(0.f, 0.f), pre1 = pre0;
+  {
+    const float2* src = reinterpret_cast<const float2*>(seg_ptr(vposed, 0));
+    if (lane < seg2) pre0 = src[lane];
+    if (lane + 32 < seg2) pre1 = src[lane + 32];
+  }
+  for (int s = 0; s < ns; ++s) {
+    __syncwarp();                                          // previous iteration's readers of `st` are done
+    reinterpret_cast<float2*>(st)[lane] = pre0;
+    if (lane < 16) reinterpret_cast<float2*>(st)[lane + 32] = pre1;
+    if (s + 1 < ns) {
+      const float2* src = reinterpret_cast<const float2*>(seg_ptr(vposed, s + 1));
+      if (lane < seg2) pre0 = src[lane];
+      if (lane + 32 < seg2) pre1 = src[lane + 32];
     }
-    __syncthreads();
+    __syncwarp();
+    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
     if (active) {
+      const float px = st[lane * 3], py = st[lane * 3 + 1], pz = st[lane * 3 + 2];
       float T[12];
 #pragma unroll
       for (int e = 0; e < 12; ++e) T[e] = 0.f;
       if (KW <= 4) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float4* a4 = reinterpret_cast<const float4*>(sA + jid[k] * 12);
+          const float4* a4 = reinterpret_cast<const float4*>(&sA[s][jid[k] * 12]);
           const float4 r0 = a4[0], r1 = a4[1], r2 = a4[2];
           T[0] = fmaf(jw[k], r0.x, T[0]); T[1] = fmaf(jw[k], r0.y, T[1]); T[2] = fmaf(jw[k], r0.z, T[2]); T[3] = fmaf(jw[k], r0.w, T[3]);
           T[4] = fmaf(jw[k], r1.x, T[4]); T[5] = fmaf(jw[k], r1.y, T[5]); T[6] = fmaf(jw[k], r1.z, T[6]); T[7] = fmaf(jw[k], r1.w, T[7]);
@@ -211,27 +225,19 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
           const int jj = __ldg(sidx + (size_t)v * KW + k);
           const float ww = __ldg(sw + (size_t)v * KW + k);
 #pragma unroll
-          for (int e = 0; e < 12; ++e) T[e] = fmaf(ww, sA[jj * 12 + e], T[e]);
+          for (int e = 0; e < 12; ++e) T[e] = fmaf(ww, sA[s][jj * 12 + e], T[e]);
         }
       }
-      const float px = sin_[tid * 3], py = sin_[tid * 3 + 1], pz = sin_[tid * 3 + 2];
-      sout[tid * 3 + 0] = T[0] * px + T[1] * py + T[2] * pz + T[3] + soff[0];
-      sout[tid * 3 + 1] = T[4] * px + T[5] * py + T[6] * pz + T[7] + soff[1];
-      sout[tid * 3 + 2] = T[8] * px + T[9] * py + T[10] * pz + T[11] + soff[2];
+      o0 = T[0] * px + T[1] * py + T[2] * pz + T[3] + soff[s][0];
+      o1 = T[4] * px + T[5] * py + T[6] * pz + T[7] + soff[s][1];
+      o2 = T[8] * px + T[9] * py + T[10] * pz + T[11] + soff[s][2];
     }
-    __syncthreads();
-    // aligned float4 body with scalar head / tail
-    float* dst = verts + (size_t)s * NV3 + (size_t)v0 * 3;
-    const int head = (int)((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) >> 2;   // floats until 16B boundary
-    const int h = min(head, seg);
-    if (tid < h) dst[tid] = sout[tid];
-    const int body = (seg - h) >> 2;
-    for (int i = tid; i < body; i += SK_VT) {
-      const float* sp = sout + h + i * 4;
-      *reinterpret_cast<float4*>(dst + h + i * 4) = make_float4(sp[0], sp[1], sp[2], sp[3]);
-    }
-    const int tail0 = h + body * 4;
-    if (tid < seg - tail0) dst[tail0 + tid] = sout[tail0 + tid];
+    __syncwarp();                                          // everyone has read its inputs from `st`
+    if (active) { st[lane * 3] = o0; st[lane * 3 + 1] = o1; st[lane * 3 + 2] = o2; }
+    __syncwarp();
+    float2* dst = reinterpret_cast<float2*>(const_cast<float*>(seg_ptr(verts, s)));
+    if (lane < seg2) dst[lane] = reinterpret_cast<const float2*>(st)[lane];
+    if (lane + 32 < seg2) dst[lane + 32] = reinterpret_cast<const float2*>(st)[lane + 32];
   }
 }
 
