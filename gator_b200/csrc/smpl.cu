@@ -165,7 +165,7 @@ constexpr int SK_SG = 16;
 __global__ void __launch_bounds__(SK_VT)
 smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ amat, const float* __restrict__ offset,
                  const int* __restrict__ sidx, const float* __restrict__ sw, int KW, float* __restrict__ verts, int batch) {
-  __shared__ __align__(16) float sA[SK_SG][NJ * 12];
+  __shared__ float sA[SK_SG][12 * NJ];   // component-major [e][joint]: lanes reading different joints hit different banks
   __shared__ float soff[SK_SG][4];
   __shared__ __align__(16) float stage[SK_VT / 32][96];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -175,7 +175,10 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
   const bool active = lane < nvw;
   const int s_begin = blockIdx.y * SK_SG;
   const int ns = min(SK_SG, batch - s_begin);
-  for (int i = tid; i < ns * NJ * 12; i += SK_VT) (&sA[0][0])[i] = amat[(size_t)s_begin * NJ * 12 + i];
+  for (int i = tid; i < ns * NJ * 12; i += SK_VT) {
+    const int s = i / (NJ * 12), r = i - s * NJ * 12, j = r / 12, e = r - j * 12;
+    sA[s][e * NJ + j] = amat[(size_t)s_begin * NJ * 12 + i];
+  }
   for (int i = tid; i < ns * 3; i += SK_VT) soff[i / 3][i % 3] = offset[(size_t)s_begin * 3 + i];
   int jid[4];
   float jw[4];
@@ -214,18 +217,16 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
       if (KW <= 4) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float4* a4 = reinterpret_cast<const float4*>(&sA[s][jid[k] * 12]);
-          const float4 r0 = a4[0], r1 = a4[1], r2 = a4[2];
-          T[0] = fmaf(jw[k], r0.x, T[0]); T[1] = fmaf(jw[k], r0.y, T[1]); T[2] = fmaf(jw[k], r0.z, T[2]); T[3] = fmaf(jw[k], r0.w, T[3]);
-          T[4] = fmaf(jw[k], r1.x, T[4]); T[5] = fmaf(jw[k], r1.y, T[5]); T[6] = fmaf(jw[k], r1.z, T[6]); T[7] = fmaf(jw[k], r1.w, T[7]);
-          T[8] = fmaf(jw[k], r2.x, T[8]); T[9] = fmaf(jw[k], r2.y, T[9]); T[10] = fmaf(jw[k], r2.z, T[10]); T[11] = fmaf(jw[k], r2.w, T[11]);
+          const float* a = &sA[s][jid[k]];
+#pragma unroll
+          for (int e = 0; e < 12; ++e) T[e] = fmaf(jw[k], a[e * NJ], T[e]);
         }
       } else {
         for (int k = 0; k < KW; ++k) {
           const int jj = __ldg(sidx + (size_t)v * KW + k);
           const float ww = __ldg(sw + (size_t)v * KW + k);
 #pragma unroll
-          for (int e = 0; e < 12; ++e) T[e] = fmaf(ww, sA[s][jj * 12 + e], T[e]);
+          for (int e = 0; e < 12; ++e) T[e] = fmaf(ww, sA[s][e * NJ + jj], T[e]);
         }
       }
       o0 = T[0] * px + T[1] * py + T[2] * pz + T[3] + soff[s][0];
