@@ -35,16 +35,12 @@ constexpr int A_BUF = 2 * A_IMG;               // hi | lo
 constexpr int NUNITS = 14;
 enum { U_SO = 0, U_Q = 1, U_PROJ = 2, U_FC1 = 3, U_FC2 = 7, U_QKV = 11 };
 
-// shared memory map
-constexpr int OFF_A = 0;                              // [tile 2][buf 2][A_BUF]        = 131072
-constexpr int OFF_W = OFF_A + 4 * A_BUF;              // [slot 3][UNIT_BYTES]          =  49152
-constexpr int OFF_KV = OFF_W + 3 * UNIT_BYTES;        // [MAXJ][128] fp32              =  16384
-constexpr int OFF_PRM = OFF_KV + MAXJ * 128 * 4;      // parameters                    =   4352
-constexpr int PRM_FLOATS = 1088;
-constexpr int SMEM_BYTES = OFF_PRM + PRM_FLOATS * 4;  // 200 960
-// parameter offsets (floats)
-enum { P_SO_B = 0, P_N1W = 64, P_N1B = 128, P_PROJ_B = 192, P_N2W = 256, P_N2B = 320, P_FC1_B = 384, P_FC2_B = 640,
-       P_CLN_A = 704, P_CLN_B = 768, P_QKV_B = 832 };
+// shared memory map (TILES = M=128 tiles per CTA): [tile][buf 2][A_BUF] | W ring [2][UNIT_BYTES] | K|V [J][128] fp32
+// TILES = 1: 64 KB + 32 KB + J*512 B (= 105.5 KB for J = 19) -> two CTAs per SM overlap each other's MMA waits
+constexpr int W_SLOTS = 2;   // unit u+1 is prefetched into the slot of unit u-1, whose MMAs every thread has waited for
+constexpr int smem_bytes(int tiles, int J) { return tiles * 2 * A_BUF + W_SLOTS * UNIT_BYTES + J * 128 * 4; }
+// parameter arrays (index into ChainParams::prm)
+enum { P_SO_B = 0, P_N1W, P_N1B, P_PROJ_B, P_N2W, P_N2B, P_FC1_B, P_FC2_B, P_CLN_A, P_CLN_B, P_QKV_B };
 
 struct ChainParams {
   const float* x_in;      // (nb*431, 64): layer 0: embedded vertices; layers 1,2: x3 of the previous layer
@@ -84,32 +80,38 @@ __device__ __forceinline__ void write_a(uint8_t* abuf, int row, int kc0, const f
   }
 }
 
-constexpr int NT = 512;   // 16 warps: (tile 2) x (column half 2) x (lane quarter 4)
 
 __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 // LayerNorm statistics of a 64-wide row held as two 32-wide halves by two threads (different warps): each half does
 // its own two-pass mean / M2 and the halves are combined with the parallel-variance formula (see `stats` below).
-__global__ void __launch_bounds__(NT, 1)
+// TILES x 8 warps: (tile) x (column half 2) x (lane quarter 4)
+template <int TILES>
+__global__ void __launch_bounds__(256 * TILES, 2 / TILES)
 mdr_chain_kernel(ChainParams p) {
+  constexpr int NT = 256 * TILES;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_slot;
-  __shared__ float2 xch_buf[3][2][128][2];          // [LayerNorm #][tile][row][{mine, partner} by column half]
+  __shared__ float2 xch_buf[2][TILES][128][2];      // [LayerNorm # parity][tile][row][{mine, partner} by column half]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x >> 1, half = blockIdx.x & 1;
-  const int tile = warp >> 3;                      // 0/1: which M=128 tile of the CTA
+  constexpr int CPS = 4 / TILES;                   // CTAs per sample
+  const int b = blockIdx.x / CPS, part = blockIdx.x % CPS;
+  const int tile = warp >> 3;                      // which M=128 tile of the CTA
   const int ch = (warp >> 2) & 1;                  // which 32-column half of the 64-wide row this thread owns
   const int row = (warp & 3) * 32 + lane;          // row in tile = TMEM lane
-  const int vrow = half * 256 + tile * 128 + row;  // vertex index in the sample
+  const int vrow = (part * TILES + tile) * 128 + row;   // vertex index in the sample
   const bool valid = vrow < V;
   const size_t grow = (size_t)b * V + (valid ? vrow : 0);
   const int pair_id = 1 + tile * 4 + (warp & 3);   // named barrier shared by the two warps that own the same rows
-  uint8_t* a0 = smem + OFF_A + tile * 2 * A_BUF;   // this tile's buffer 0 (n / generic) ...
+  constexpr int OFF_W = TILES * 2 * A_BUF;
+  constexpr int OFF_KV = OFF_W + W_SLOTS * UNIT_BYTES;
+  uint8_t* a0 = smem + tile * 2 * A_BUF;           // this tile's buffer 0 (n / generic) ...
   uint8_t* a1 = a0 + A_BUF;                        // ... and buffer 1 (GELU(fc1) quarter)
   float* skv = reinterpret_cast<float*>(smem + OFF_KV);
-  float* prm = reinterpret_cast<float*>(smem + OFF_PRM);
   const int J = p.J;
+  // per-channel parameters come straight from global memory (L1-resident: ~4 KB per layer, shared by all CTAs)
+  auto prm = [&](int which, int i) { return __ldg(p.prm[which] + i); };
   const int c0 = ch * 32;                          // first column of this thread's half
 
   auto prefetch_w = [&](int unit, int slot) {
@@ -120,7 +122,7 @@ mdr_chain_kernel(ChainParams p) {
     cp_async_commit();
   };
 
-  if (warp == 0) tmem_alloc(&tmem_slot, 256);
+  if (warp == 0) tmem_alloc(&tmem_slot, 128 * TILES);
   if (tid == 32) {
     mbar_init(&bar, 1);
     mbar_init_fence();
@@ -128,15 +130,6 @@ mdr_chain_kernel(ChainParams p) {
   const int first_unit = p.att_in ? U_SO : U_Q;
   prefetch_w(first_unit, 0);
   for (int i = tid; i < J * 128; i += NT) skv[i] = p.kv[(size_t)b * J * 128 + i];
-  {
-    const int sizes[11] = {64, 64, 64, 64, 64, 64, 256, 64, 64, 64, 192};
-    int off = 0;
-#pragma unroll
-    for (int k = 0; k < 11; ++k) {
-      for (int i = tid; i < sizes[k]; i += NT) prm[off + i] = p.prm[k][i];
-      off += sizes[k];
-    }
-  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -158,8 +151,8 @@ mdr_chain_kernel(ChainParams p) {
       tc_fence_after();
       const uint32_t w0 = smem_u32(smem + OFF_W + slot * UNIT_BYTES);
 #pragma unroll
-      for (int t = 0; t < 2; ++t) {
-        const uint32_t abase = smem_u32(smem + OFF_A + (t * 2 + abuf_idx) * A_BUF);
+      for (int t = 0; t < TILES; ++t) {
+        const uint32_t abase = smem_u32(smem + (t * 2 + abuf_idx) * A_BUF);
         const uint32_t d = tmem + t * 128 + dcol;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -176,8 +169,8 @@ mdr_chain_kernel(ChainParams p) {
       }
       mma_commit(&bar);
     }
-    slot = (slot + 1) % 3;
-    if (next_unit >= 0) prefetch_w(next_unit, slot);   // slot was last read two units ago: its MMAs were waited for
+    slot = (slot + 1) % W_SLOTS;
+    if (next_unit >= 0) prefetch_w(next_unit, slot);   // that slot was read by the previous unit, whose MMAs were waited for
     mbar_wait(&bar, phase);
     phase ^= 1;
     tc_fence_after();
@@ -192,7 +185,7 @@ mdr_chain_kernel(ChainParams p) {
     }
   };
   auto stats = [&](const float* xr, int which, float& mean, float& m2) {
-    float2* base = &xch_buf[which][tile][row][0];
+    float2* base = &xch_buf[which & 1][tile][row][0];   // slot reuse is separated by full-CTA barriers
     float m = 0.f;
 #pragma unroll
     for (int i = 0; i < 32; ++i) m += xr[i];
@@ -217,7 +210,7 @@ mdr_chain_kernel(ChainParams p) {
     run_unit(0, 0, false, U_Q);
     ld32(acc, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] += v[i] + prm[P_SO_B + c0 + i];
+    for (int i = 0; i < 32; ++i) x[i] += v[i] + prm(P_SO_B, c0 + i);
   }
   // ---- LayerNorm1 -> q ----
   {
@@ -225,7 +218,7 @@ mdr_chain_kernel(ChainParams p) {
     stats(x, 0, mean, m2);
     const float rstd = rsqrtf(m2 * (1.0f / E) + 1e-5f);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * prm[P_N1W + c0 + i] + prm[P_N1B + c0 + i];
+    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * prm(P_N1W, c0 + i) + prm(P_N1B, c0 + i);
     write_a<4>(a0, row, ch * 4, v);
   }
   run_unit(0, 0, false, U_PROJ);
@@ -275,14 +268,14 @@ mdr_chain_kernel(ChainParams p) {
   run_unit(0, 0, false, U_FC1);
   ld32(acc, v);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) x[i] += v[i] + prm[P_PROJ_B + c0 + i];
+  for (int i = 0; i < 32; ++i) x[i] += v[i] + prm(P_PROJ_B, c0 + i);
   // ---- LayerNorm2 -> MLP ----
   {
     float mean, m2;
     stats(x, 1, mean, m2);
     const float rstd = rsqrtf(m2 * (1.0f / E) + 1e-5f);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * prm[P_N2W + c0 + i] + prm[P_N2B + c0 + i];
+    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * prm(P_N2W, c0 + i) + prm(P_N2B, c0 + i);
     write_a<4>(a0, row, ch * 4, v);
   }
 #pragma unroll 1
@@ -290,20 +283,20 @@ mdr_chain_kernel(ChainParams p) {
     run_unit(0, 0, false, U_FC2 + qd);                     // fc1 quarter qd from LN2(x) (buffer 0 stays intact)
     ld32(acc, v);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i] + prm[P_FC1_B + qd * 64 + c0 + i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i] + prm(P_FC1_B, qd * 64 + c0 + i));
     write_a<4>(a1, row, ch * 4, v);
     run_unit(1, 64, qd > 0, qd < 3 ? U_FC1 + qd + 1 : U_QKV);   // fc2 += GELU(.) W2[:, quarter]
   }
   ld32(acc2, v);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) x[i] += v[i] + prm[P_FC2_B + c0 + i];
+  for (int i = 0; i < 32; ++i) x[i] += v[i] + prm(P_FC2_B, c0 + i);
   // ---- unbiased-std LayerNorm -> x3 ----
   {
     float mean, m2;
     stats(x, 2, mean, m2);
     const float denom = sqrtf(m2 * (1.0f / (E - 1))) + 1e-6f;
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = prm[P_CLN_A + c0 + i] * (x[i] - mean) / denom + prm[P_CLN_B + c0 + i];
+    for (int i = 0; i < 32; ++i) x[i] = prm(P_CLN_A, c0 + i) * (x[i] - mean) / denom + prm(P_CLN_B, c0 + i);
     write_a<4>(a0, row, ch * 4, x);
     if (valid) {
       float4* dst = reinterpret_cast<float4*>(p.x3_out + grow * E + c0);
@@ -318,15 +311,15 @@ mdr_chain_kernel(ChainParams p) {
     ld32(acc, v);
     if (valid) {
       float4* dst = reinterpret_cast<float4*>(p.qkv_out + grow * 3 * E + t3 * E + c0);
-      const float* bq = prm + P_QKV_B + t3 * E + c0;
+      const float* bq = p.prm[P_QKV_B] + t3 * E + c0;
 #pragma unroll
       for (int i = 0; i < 8; ++i)
-        dst[i] = make_float4(v[4 * i] + bq[4 * i], v[4 * i + 1] + bq[4 * i + 1], v[4 * i + 2] + bq[4 * i + 2], v[4 * i + 3] + bq[4 * i + 3]);
+        dst[i] = make_float4(v[4 * i] + __ldg(bq + 4 * i), v[4 * i + 1] + __ldg(bq + 4 * i + 1), v[4 * i + 2] + __ldg(bq + 4 * i + 2), v[4 * i + 3] + __ldg(bq + 4 * i + 3));
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 128 * TILES);
 }
 
 }  // namespace
@@ -336,14 +329,17 @@ int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, co
                      float* x3_out, float* qkv_out, int nb, int J, bool split, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(mdr_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+    cudaFuncSetAttribute(mdr_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
+    cudaFuncSetAttribute(mdr_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2, MAXJ));
     attr_done = true;
   }
   ChainParams p;
   p.x_in = x_in; p.att_in = att_in; p.kv = kv; p.blob = static_cast<const uint8_t*>(blob);
   for (int i = 0; i < 11; ++i) p.prm[i] = prm[i];
   p.x3_out = x3_out; p.qkv_out = qkv_out; p.J = J; p.split = split ? 1 : 0;
-  mdr_chain_kernel<<<nb * 2, NT, SMEM_BYTES, stream>>>(p);
+  // one tile per CTA fits twice on an SM (2 x ~107 KB) as long as J <= 24; otherwise two tiles per CTA
+  if (smem_bytes(1, J) <= 110 * 1024) mdr_chain_kernel<1><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);
+  else mdr_chain_kernel<2><<<nb * 2, 512, smem_bytes(2, J), stream>>>(p);
   return check_launch("mdr_chain");
 }
 

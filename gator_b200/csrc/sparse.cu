@@ -41,62 +41,73 @@ csr_spmm_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx, 
   }
 }
 
-// xyz fast path (feat == 3): lane = output row, its <= 4 non-zeros live in registers and are reused for SG
-// samples; gathers go through L1/L2 (one sample's input is <= 83 KB); the 32 rows x 3 floats of a warp are
-// staged in warp-private shared memory and leave as 256-byte coalesced store instructions (8-byte accesses
-// when the segment is 8-byte aligned, else 4-byte).  No block-level synchronisation.
-constexpr int SP_SG = 8;
-
+// xyz fast path (feat == 3).  CTA = NS consecutive samples x all rows: the samples' inputs (cols x 3 floats each)
+// are staged in shared memory with coalesced loads, so the random column gathers hit shared memory banks instead
+// of touching up to 32 L1 lines per instruction; lane = output row, its <= 4 non-zeros are fetched once per
+// row and reused for the NS samples; a warp's 32 rows x 3 floats are staged in warp-private shared memory and
+// leave as 256-byte coalesced store instructions (8-byte accesses when the segment is 8-byte aligned).
 __global__ void __launch_bounds__(256)
 csr_spmm3_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ values,
-                 const float* __restrict__ x, float* __restrict__ y, int rows, int cols, float scale, int batch) {
+                 const float* __restrict__ x, float* __restrict__ y, int rows, int cols, float scale, int batch, int NS) {
+  extern __shared__ __align__(16) float sx[];          // [NS][cols*3]
   __shared__ __align__(16) float stage[8][96];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int r0 = blockIdx.x * 256 + warp * 32;
-  const int nr = max(0, min(32, rows - r0));
-  if (nr == 0) return;
-  const int r = r0 + lane;
-  const bool active = lane < nr;
-  int k0 = 0, k1 = 0;
-  if (active) { k0 = __ldg(rowptr + r); k1 = __ldg(rowptr + r + 1); }
-  const int nnz = k1 - k0;
-  int c[4] = {0, 0, 0, 0};
-  float w[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    if (k < nnz) { c[k] = __ldg(colidx + k0 + k) * 3; w[k] = __ldg(values + k0 + k); }
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b0 = blockIdx.x * NS;
+  const int ns = min(NS, batch - b0);
+  const int xs = cols * 3;
+  {
+    const float* src = x + (size_t)b0 * xs;
+    const int total = ns * xs;
+    if ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      for (int i = tid; i < total / 4; i += 256) reinterpret_cast<float4*>(sx)[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+      for (int i = (total / 4) * 4 + tid; i < total; i += 256) sx[i] = src[i];
+    } else {
+      for (int i = tid; i < total; i += 256) sx[i] = src[i];
+    }
+  }
+  __syncthreads();
   float* st = stage[warp];
-  const int seg = nr * 3;
-  const int b_end = min(batch, (int)(blockIdx.y + 1) * SP_SG);
-  for (int b = blockIdx.y * SP_SG; b < b_end; ++b) {
-    const float* xb = x + (size_t)b * cols * 3;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-    if (nnz <= 4) {
+  for (int r0 = warp * 32; r0 < rows; r0 += 256) {
+    const int nr = min(32, rows - r0);
+    const int r = r0 + lane;
+    const bool active = lane < nr;
+    int k0 = 0, k1 = 0;
+    if (active) { k0 = __ldg(rowptr + r); k1 = __ldg(rowptr + r + 1); }
+    const int nnz = k1 - k0;
+    int c[4] = {0, 0, 0, 0};
+    float w[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (k < nnz) {
-          a0 = fmaf(w[k], __ldg(xb + c[k]), a0);
-          a1 = fmaf(w[k], __ldg(xb + c[k] + 1), a1);
-          a2 = fmaf(w[k], __ldg(xb + c[k] + 2), a2);
+    for (int k = 0; k < 4; ++k)
+      if (k < nnz) { c[k] = __ldg(colidx + k0 + k) * 3; w[k] = __ldg(values + k0 + k); }
+    const int seg = nr * 3;
+    for (int s = 0; s < ns; ++s) {
+      const float* xb = sx + s * xs;
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      if (nnz <= 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < nnz) {
+            a0 = fmaf(w[k], xb[c[k]], a0); a1 = fmaf(w[k], xb[c[k] + 1], a1); a2 = fmaf(w[k], xb[c[k] + 2], a2);
+          }
+        }
+      } else {
+        for (int k = k0; k < k1; ++k) {
+          const float ww = __ldg(values + k);
+          const float* xp = xb + __ldg(colidx + k) * 3;
+          a0 = fmaf(ww, xp[0], a0); a1 = fmaf(ww, xp[1], a1); a2 = fmaf(ww, xp[2], a2);
         }
       }
-    } else {
-      for (int k = k0; k < k1; ++k) {
-        const float ww = __ldg(values + k);
-        const float* xp = xb + (size_t)__ldg(colidx + k) * 3;
-        a0 = fmaf(ww, __ldg(xp), a0); a1 = fmaf(ww, __ldg(xp + 1), a1); a2 = fmaf(ww, __ldg(xp + 2), a2);
+      __syncwarp();
+      if (active) { st[lane * 3] = a0 * scale; st[lane * 3 + 1] = a1 * scale; st[lane * 3 + 2] = a2 * scale; }
+      __syncwarp();
+      float* dst = y + ((size_t)(b0 + s) * rows + r0) * 3;
+      if (((reinterpret_cast<uintptr_t>(dst) & 7u) == 0) && (seg & 1) == 0) {
+        const int seg2 = seg >> 1;
+        if (lane < seg2) reinterpret_cast<float2*>(dst)[lane] = reinterpret_cast<const float2*>(st)[lane];
+        if (lane + 32 < seg2) reinterpret_cast<float2*>(dst)[lane + 32] = reinterpret_cast<const float2*>(st)[lane + 32];
+      } else {
+        for (int i = lane; i < seg; i += 32) dst[i] = st[i];
       }
-    }
-    __syncwarp();
-    if (active) { st[lane * 3] = a0 * scale; st[lane * 3 + 1] = a1 * scale; st[lane * 3 + 2] = a2 * scale; }
-    __syncwarp();
-    float* dst = y + ((size_t)b * rows + r0) * 3;
-    if (((reinterpret_cast<uintptr_t>(dst) & 7u) == 0) && (seg & 1) == 0) {
-      const int seg2 = seg >> 1;
-      if (lane < seg2) reinterpret_cast<float2*>(dst)[lane] = reinterpret_cast<const float2*>(st)[lane];
-      if (lane + 32 < seg2) reinterpret_cast<float2*>(dst)[lane + 32] = reinterpret_cast<const float2*>(st)[lane + 32];
-    } else {
-      for (int i = lane; i < seg; i += 32) dst[i] = st[i];
     }
   }
 }
@@ -111,11 +122,17 @@ extern "C" int gator_csr_spmm(const gator_csr_args* a, void* stream) {
   const long long total = (long long)a->batch * a->rows * a->feat;
   if (total == 0) return GATOR_OK;
   GATOR_REQUIRE(a->rowptr && a->colidx && a->values && a->x && a->y, "gator_csr_spmm: null buffer");
-  if (a->feat == 3 && a->rows >= 64) {
-    dim3 grid(ceil_div(a->rows, 256), ceil_div(a->batch, SP_SG));
-    GATOR_REQUIRE(grid.y <= 65535u, "gator_csr_spmm: batch too large for one launch");
-    csr_spmm3_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a->rowptr, a->colidx, a->values, a->x, a->y, a->rows, a->cols,
-                                                             a->scale, a->batch);
+  if (a->feat == 3 && a->rows >= 64 && (size_t)a->cols * 12 <= 96 * 1024) {
+    const int per_sample = a->cols * 12;
+    int NS = 96 * 1024 / per_sample;                 // <= 96 KB of staged inputs per CTA (2 CTAs / SM)
+    NS = NS > 8 ? 8 : NS;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(csr_spmm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      attr_done = true;
+    }
+    csr_spmm3_kernel<<<ceil_div(a->batch, NS), 256, (size_t)NS * per_sample, (cudaStream_t)stream>>>(
+        a->rowptr, a->colidx, a->values, a->x, a->y, a->rows, a->cols, a->scale, a->batch, NS);
     return check_launch("csr_spmm3");
   }
   const int vec = (reinterpret_cast<uintptr_t>(a->y) & 15u) == 0;
