@@ -188,8 +188,11 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
         for (int j = 0; j < 7; ++j) {
           if (jb + j < p1_n) {
             const int col0 = (p1_lo + jb + j) * 8;
+            float t[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) mx = fmaxf(mx, (col0 + i) < V ? s[j][i] : -INFINITY);
+            for (int i = 0; i < 8; ++i) t[i] = (col0 + i) < V ? s[j][i] : -INFINITY;
+            // tree max: no 8-long dependent chain
+            mx = fmaxf(mx, fmaxf(fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3])), fmaxf(fmaxf(t[4], t[5]), fmaxf(t[6], t[7]))));
           }
         }
       }
@@ -213,10 +216,8 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
           float* s = sc[j];
           const int col0 = part * PK + (p2_lo + j) * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            s[i] = (col0 + i) < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
-            sum += s[i];
-          }
+          for (int i = 0; i < 8; ++i) s[i] = (col0 + i) < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
+          sum += ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
           const uint4 hi = pack8(s);
           const int kc = p2_lo + j;
           *reinterpret_cast<uint4*>(prow + kc * 128) = hi;

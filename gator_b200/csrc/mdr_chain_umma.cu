@@ -86,7 +86,8 @@ __device__ __forceinline__ void pair_sync(int id) { asm volatile("bar.sync %0, 6
 // LayerNorm statistics of a 64-wide row held as two 32-wide halves by two threads (different warps): each half does
 // its own two-pass mean / M2 and the halves are combined with the parallel-variance formula (see `stats` below).
 // TILES x 8 warps: (tile) x (column half 2) x (lane quarter 4)
-template <int TILES>
+// JT = compile-time joint count (17 / 19: the cross-attention loops unroll exactly) or 0 = runtime J <= 32
+template <int TILES, int JT>
 __global__ void __launch_bounds__(256 * TILES, 2 / TILES)
 mdr_chain_kernel(ChainParams p) {
   constexpr int NT = 256 * TILES;
@@ -109,9 +110,17 @@ mdr_chain_kernel(ChainParams p) {
   uint8_t* a0 = smem + tile * 2 * A_BUF;           // this tile's buffer 0 (n / generic) ...
   uint8_t* a1 = a0 + A_BUF;                        // ... and buffer 1 (GELU(fc1) quarter)
   float* skv = reinterpret_cast<float*>(smem + OFF_KV);
-  const int J = p.J;
+  const int J = JT ? JT : p.J;
+  constexpr int JU = JT ? JT : MAXJ;               // unrolled trip count of the per-joint loops
   // per-channel parameters come straight from global memory (L1-resident: ~4 KB per layer, shared by all CTAs)
-  auto prm = [&](int which, int i) { return __ldg(p.prm[which] + i); };
+  auto prm32 = [&](int which, int off, float* dst) {     // 32 consecutive parameters as 8 x 16-byte loads
+    const float4* src = reinterpret_cast<const float4*>(p.prm[which] + off);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float4 t = __ldg(src + i);
+      dst[4 * i] = t.x; dst[4 * i + 1] = t.y; dst[4 * i + 2] = t.z; dst[4 * i + 3] = t.w;
+    }
+  };
   const int c0 = ch * 32;                          // first column of this thread's half
 
   auto prefetch_w = [&](int unit, int slot) {
@@ -186,13 +195,14 @@ mdr_chain_kernel(ChainParams p) {
   };
   auto stats = [&](const float* xr, int which, float& mean, float& m2) {
     float2* base = &xch_buf[which & 1][tile][row][0];   // slot reuse is separated by full-CTA barriers
-    float m = 0.f;
+    float m4[4] = {0.f, 0.f, 0.f, 0.f};     // 4 independent chains (a single serial chain costs 4 cycles per add)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) m += xr[i];
-    m *= (1.0f / 32);
-    float q = 0.f;
+    for (int i = 0; i < 32; ++i) m4[i & 3] += xr[i];
+    const float m = ((m4[0] + m4[1]) + (m4[2] + m4[3])) * (1.0f / 32);
+    float q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int i = 0; i < 32; ++i) { const float d = xr[i] - m; q = fmaf(d, d, q); }
+    for (int i = 0; i < 32; ++i) { const float d = xr[i] - m; q4[i & 3] = fmaf(d, d, q4[i & 3]); }
+    const float q = (q4[0] + q4[1]) + (q4[2] + q4[3]);
     base[ch] = make_float2(m, q);
     pair_sync(pair_id);
     const float2 o = base[1 - ch];
@@ -202,23 +212,26 @@ mdr_chain_kernel(ChainParams p) {
   };
 
   // ---- residual row (this thread's 32 columns) ----
-  float x[32], v[32];
+  float x[32], v[32], pw[32], pb[32];
   load_row32(p.x_in, x);
   if (p.att_in) {   // x = x3_prev + att_prev Wo^T + b
     load_row32(p.att_in, v);
     write_a<4>(a0, row, ch * 4, v);
     run_unit(0, 0, false, U_Q);
     ld32(acc, v);
+    prm32(P_SO_B, c0, pw);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] += v[i] + prm(P_SO_B, c0 + i);
+    for (int i = 0; i < 32; ++i) x[i] += v[i] + pw[i];
   }
   // ---- LayerNorm1 -> q ----
   {
     float mean, m2;
     stats(x, 0, mean, m2);
     const float rstd = rsqrtf(m2 * (1.0f / E) + 1e-5f);
+    prm32(P_N1W, c0, pw);
+    prm32(P_N1B, c0, pb);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * prm(P_N1W, c0 + i) + prm(P_N1B, c0 + i);
+    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * pw[i] + pb[i];
     write_a<4>(a0, row, ch * 4, v);
   }
   run_unit(0, 0, false, U_PROJ);
@@ -226,33 +239,33 @@ mdr_chain_kernel(ChainParams p) {
   {
     float q[DK];
     ld32(acc, q);
-    float s[MAXJ];
+    float s[JU];
     float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
-      if (j < J) {
+    for (int j = 0; j < JU; ++j) {
+      if (JT || j < J) {
         const float4* kr = reinterpret_cast<const float4*>(skv + j * 128 + c0);
-        float a = 0.f;
+        float a0_ = 0.f, a1_ = 0.f, a2_ = 0.f, a3_ = 0.f;       // 4 independent FMA chains
 #pragma unroll
         for (int d4 = 0; d4 < DK / 4; ++d4) {
           const float4 kk = kr[d4];
-          a = fmaf(q[4 * d4], kk.x, a); a = fmaf(q[4 * d4 + 1], kk.y, a);
-          a = fmaf(q[4 * d4 + 2], kk.z, a); a = fmaf(q[4 * d4 + 3], kk.w, a);
+          a0_ = fmaf(q[4 * d4], kk.x, a0_); a1_ = fmaf(q[4 * d4 + 1], kk.y, a1_);
+          a2_ = fmaf(q[4 * d4 + 2], kk.z, a2_); a3_ = fmaf(q[4 * d4 + 3], kk.w, a3_);
         }
-        s[j] = a * 0.17677669529663687f;
+        s[j] = ((a0_ + a1_) + (a2_ + a3_)) * 0.17677669529663687f;
         mx = fmaxf(mx, s[j]);
       }
     }
     float l = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j)
-      if (j < J) { s[j] = expf(s[j] - mx); l += s[j]; }
+    for (int j = 0; j < JU; ++j)
+      if (JT || j < J) { s[j] = expf(s[j] - mx); l += s[j]; }
     const float inv = 1.0f / l;
 #pragma unroll
     for (int d = 0; d < DK; ++d) v[d] = 0.f;
 #pragma unroll
-    for (int j = 0; j < MAXJ; ++j) {
-      if (j < J) {
+    for (int j = 0; j < JU; ++j) {
+      if (JT || j < J) {
         const float pj = s[j] * inv;
         const float4* vr = reinterpret_cast<const float4*>(skv + j * 128 + E + c0);
 #pragma unroll
@@ -267,36 +280,43 @@ mdr_chain_kernel(ChainParams p) {
   }
   run_unit(0, 0, false, U_FC1);
   ld32(acc, v);
+  prm32(P_PROJ_B, c0, pw);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) x[i] += v[i] + prm(P_PROJ_B, c0 + i);
+  for (int i = 0; i < 32; ++i) x[i] += v[i] + pw[i];
   // ---- LayerNorm2 -> MLP ----
   {
     float mean, m2;
     stats(x, 1, mean, m2);
     const float rstd = rsqrtf(m2 * (1.0f / E) + 1e-5f);
+    prm32(P_N2W, c0, pw);
+    prm32(P_N2B, c0, pb);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * prm(P_N2W, c0 + i) + prm(P_N2B, c0 + i);
+    for (int i = 0; i < 32; ++i) v[i] = (x[i] - mean) * rstd * pw[i] + pb[i];
     write_a<4>(a0, row, ch * 4, v);
   }
 #pragma unroll 1
   for (int qd = 0; qd < 4; ++qd) {
     run_unit(0, 0, false, U_FC2 + qd);                     // fc1 quarter qd from LN2(x) (buffer 0 stays intact)
     ld32(acc, v);
+    prm32(P_FC1_B, qd * 64 + c0, pw);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i] + prm(P_FC1_B, qd * 64 + c0 + i));
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i] + pw[i]);
     write_a<4>(a1, row, ch * 4, v);
     run_unit(1, 64, qd > 0, qd < 3 ? U_FC1 + qd + 1 : U_QKV);   // fc2 += GELU(.) W2[:, quarter]
   }
   ld32(acc2, v);
+  prm32(P_FC2_B, c0, pw);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) x[i] += v[i] + prm(P_FC2_B, c0 + i);
+  for (int i = 0; i < 32; ++i) x[i] += v[i] + pw[i];
   // ---- unbiased-std LayerNorm -> x3 ----
   {
     float mean, m2;
     stats(x, 2, mean, m2);
     const float denom = sqrtf(m2 * (1.0f / (E - 1))) + 1e-6f;
+    prm32(P_CLN_A, c0, pw);
+    prm32(P_CLN_B, c0, pb);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) x[i] = prm(P_CLN_A, c0 + i) * (x[i] - mean) / denom + prm(P_CLN_B, c0 + i);
+    for (int i = 0; i < 32; ++i) x[i] = pw[i] * (x[i] - mean) / denom + pb[i];
     write_a<4>(a0, row, ch * 4, x);
     if (valid) {
       float4* dst = reinterpret_cast<float4*>(p.x3_out + grow * E + c0);
@@ -329,8 +349,10 @@ int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, co
                      float* x3_out, float* qkv_out, int nb, int J, bool split, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(mdr_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
-    cudaFuncSetAttribute(mdr_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2, MAXJ));
+    cudaFuncSetAttribute(mdr_chain_kernel<1, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, 17));
+    cudaFuncSetAttribute(mdr_chain_kernel<1, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, 19));
+    cudaFuncSetAttribute(mdr_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
+    cudaFuncSetAttribute(mdr_chain_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2, MAXJ));
     attr_done = true;
   }
   ChainParams p;
@@ -338,8 +360,10 @@ int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, co
   for (int i = 0; i < 11; ++i) p.prm[i] = prm[i];
   p.x3_out = x3_out; p.qkv_out = qkv_out; p.J = J; p.split = split ? 1 : 0;
   // one tile per CTA fits twice on an SM (2 x ~107 KB) as long as J <= 24; otherwise two tiles per CTA
-  if (smem_bytes(1, J) <= 110 * 1024) mdr_chain_kernel<1><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);
-  else mdr_chain_kernel<2><<<nb * 2, 512, smem_bytes(2, J), stream>>>(p);
+  if (J == 17) mdr_chain_kernel<1, 17><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);
+  else if (J == 19) mdr_chain_kernel<1, 19><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);
+  else if (smem_bytes(1, J) <= 110 * 1024) mdr_chain_kernel<1, 0><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);
+  else mdr_chain_kernel<2, 0><<<nb * 2, 512, smem_bytes(2, J), stream>>>(p);
   return check_launch("mdr_chain");
 }
 
