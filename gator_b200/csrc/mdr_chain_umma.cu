@@ -300,7 +300,7 @@ mdr_chain_kernel(ChainParams p) {
     ld32(acc, v);
     prm32(P_FC1_B, qd * 64 + c0, pw);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i] + pw[i]);
+    for (int i = 0; i < 32; ++i) v[i] = gelu_erf_fast(v[i] + pw[i]);
     write_a<4>(a1, row, ch * 4, v);
     run_unit(1, 64, qd > 0, qd < 3 ? U_FC1 + qd + 1 : U_QKV);   // fc2 += GELU(.) W2[:, quarter]
   }

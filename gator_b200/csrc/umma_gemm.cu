@@ -38,6 +38,8 @@ struct UmmaGemmParams {
   const __nv_bfloat16* Wlo;    // lo part for the 3-term split, else null
   float* C;
   int lda, ldc, M, N, K, K_pad, BN;   // BN = columns per CTA (the packed tile width, halved in split mode if > 128)
+  int stages;                         // operand buffers: 2 = double-buffered K loop; 1 for short K loops, so that
+                                      // several CTAs fit on an SM and overlap each other's staging / epilogue
   Epilogue epi;
   int vec;
 };
@@ -52,8 +54,9 @@ umma_gemm_kernel(UmmaGemmParams p) {
   const int w_stage = BN * BKE * 2;
   const int a_stride = split ? 2 * A_STAGE : A_STAGE;      // [hi | lo] per stage
   const int w_stride = split ? 2 * w_stage : w_stage;
-  uint8_t* sA = smem;                          // [2][a_stride]
-  uint8_t* sW = smem + 2 * a_stride;           // [2][w_stride]
+  const int stages = p.stages;
+  uint8_t* sA = smem;                          // [stages][a_stride]
+  uint8_t* sW = smem + stages * a_stride;      // [stages][w_stride]
   float* stg = reinterpret_cast<float*>(smem); // epilogue staging aliases the operand buffers: [2][BM][STG_LD]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -76,8 +79,8 @@ umma_gemm_kernel(UmmaGemmParams p) {
   const int nk = p.K_pad / BKE;
   const int kgroups = p.K_pad / 8;             // 16-byte chunks per packed W row-group
   for (int kb = 0; kb < nk; ++kb) {
-    const int buf = kb & 1;
-    if (kb >= 2) mbar_wait(&mbar[buf], ((kb >> 1) - 1) & 1);
+    const int buf = kb % stages;
+    if (kb >= stages) mbar_wait(&mbar[buf], ((kb / stages) - 1) & 1);
     // ---- stage A: 128 rows x 64 k, fp32 -> bf16, chunk c = (rg, kc, r) stored linearly ----
     {
       uint4* dst = reinterpret_cast<uint4*>(sA + buf * a_stride);
@@ -134,7 +137,7 @@ umma_gemm_kernel(UmmaGemmParams p) {
       mma_commit(&mbar[buf]);
     }
   }
-  mbar_wait(&mbar[(nk - 1) & 1], ((nk - 1) >> 1) & 1);
+  mbar_wait(&mbar[(nk - 1) % stages], ((nk - 1) / stages) & 1);
   tc_fence_after();
   __syncthreads();   // every thread is past its last operand-buffer use: staging may alias them
 
@@ -224,7 +227,8 @@ int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, const void* Wpa
   p.epi = epi;
   p.vec = (!epi.conv3 && ldc % 4 == 0 && aligned16(C) && (!epi.R || (epi.ldr % 4 == 0 && aligned16(epi.R))) &&
            (!epi.bias || aligned16(epi.bias)) && (!epi.bias_rows || (aligned16(epi.bias_rows) && N % 4 == 0))) ? 1 : 0;
-  const int operand = (p.Wlo ? 2 : 1) * (2 * A_STAGE + 2 * p.BN * BKE * 2);
+  p.stages = (p.K_pad / BKE <= 2) ? 1 : 2;
+  const int operand = (p.Wlo ? 2 : 1) * p.stages * (A_STAGE + p.BN * BKE * 2);
   const int smem = operand > 2 * STG_BYTES ? operand : 2 * STG_BYTES;
   static int max_set = 0;
   if (smem > max_set) {
