@@ -260,30 +260,52 @@ def run_b200(args):
     line = None
     if rank == 0:
         peaks = measured_peaks()
-        # ---- dominant kernel alone: MDR self-attention core ----
+        # ---- dominant kernels alone (C-ABI entry points, CUDA events on the launching stream) ----
         nb = 148
         pcode = _lib.PRECISIONS[args.precision]
+        s = _lib.stream_ptr()
+
+        def time_launch(fn, reps=20):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
         qkv = torch.randn(nb * 431, 192, device=dev)
         out = torch.empty(nb * 431, 64, device=dev)
-        s = _lib.stream_ptr()
-        for _ in range(3):
-            L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, pcode, s)
-        torch.cuda.synchronize()
-        reps = 20
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, pcode, s)
-        e1.record()
-        torch.cuda.synchronize()
-        k_ms = e0.elapsed_time(e1) / reps
-        achieved = SA_FLOP_PER_SAMPLE * nb / (k_ms * 1e-3) / 1e12
-        kname = 'mdr_self_attn_kernel (fp32 FFMA)' if pcode == 0 else f'mdr_self_attn_umma_kernel<{"true" if pcode == 2 else "false"}> (tcgen05)'
-        roofline = {'kernel': kname, 'bound': 'tensor', 'achieved': achieved, 'peak': peaks['bf16_tflops'],
-                    'unit': 'TFLOP/s', 'frac': achieved / peaks['bf16_tflops'], 'traffic': None,
-                    'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)', 'launch_ms': k_ms,
-                    'note': 'algorithmic flops = 2 heads x (QK^T + PV) x 2*MAC x 148 samples per launch (47.6 MFLOP/sample-layer); '
-                            'the 3-term split issues 3x that many tensor-core MACs, which are not counted'}
+        sa_ms = time_launch(lambda: _lib.check(L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, pcode, s), 'self_attention'))
+        sa_tf = SA_FLOP_PER_SAMPLE * nb / (sa_ms * 1e-3) / 1e12
+        sa_name = 'mdr_self_attn_kernel (fp32 FFMA)' if pcode == 0 else f'mdr_self_attn_umma_kernel<{"true" if pcode == 2 else "false"}> (tcgen05)'
+        kernels = [{'kernel': sa_name, 'bound': 'tensor', 'achieved': sa_tf, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+                    'frac': sa_tf / peaks['bf16_tflops'], 'launch_ms': sa_ms,
+                    'flops_per_launch': SA_FLOP_PER_SAMPLE * nb}]
+        if pcode != 0:
+            model(x[:2])                                            # make sure the MDR weights are packed
+            (_, _, _, _), table, _ = model.pose2mesh._packed
+            xin = torch.randn(nb * 431, 64, device=dev)
+            att = torch.randn(nb * 431, 64, device=dev)
+            kvb = torch.randn(nb * J, 128, device=dev)
+            x3o = torch.empty(nb * 431, 64, device=dev)
+            qko = torch.empty(nb * 431, 192, device=dev)
+            ch_ms = time_launch(lambda: _lib.check(L.gator_mdr_layer_chain(table, 1, J, pcode, xin.data_ptr(), att.data_ptr(), kvb.data_ptr(),
+                                                                            x3o.data_ptr(), qko.data_ptr(), nb, s), 'layer_chain'))
+            ch_flop = nb * 431 * (14 * 64 * 64 * 2 + 2 * J * 32 * 2 * 2)
+            ch_tf = ch_flop / (ch_ms * 1e-3) / 1e12
+            kernels.insert(0, {'kernel': 'mdr_chain_kernel<1,J> (tcgen05 fused layer chain)', 'bound': 'tensor', 'achieved': ch_tf,
+                               'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': ch_tf / peaks['bf16_tflops'],
+                               'launch_ms': ch_ms, 'flops_per_launch': ch_flop})
+        roofline = dict(kernels[0])
+        roofline.update({'traffic': None, 'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)',
+                         'note': 'algorithmic flops (2*MAC of the layer\'s 14 64x64 products + cross-attention, or of QK^T + PV) per launch of '
+                                 '148 samples; the 3-term split issues 3x that many tensor-core MACs, which are not counted; both kernels are '
+                                 'bound by CUDA-core softmax/GELU/LayerNorm/operand-conversion work and MMA round-trip latency, not by the tensor pipe',
+                         'other_kernels': kernels[1:]})
         # parity of this very configuration against the CPU oracle (64 samples)
         from helpers import oracle_setup, orc, regressor
         sd, gc, mc, alpha = oracle_setup(TAG)

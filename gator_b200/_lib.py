@@ -67,7 +67,7 @@ class GemmArgs(C.Structure):
 
 _STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs]
 EXPORTS = ['gator_abi_version', 'gator_last_error', 'gator_abi_sizeof', 'gator_launch_count',
-           'gator_mdr_self_attention', 'gator_umma_weight_layout',
+           'gator_mdr_self_attention', 'gator_mdr_layer_chain', 'gator_umma_weight_layout',
            'gator_gat_slot_name', 'gator_gat_workspace_bytes', 'gator_gat_forward',
            'gator_mdr_slot_name', 'gator_mdr_workspace_bytes', 'gator_mdr_forward',
            'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_gemm']
@@ -109,6 +109,9 @@ def lib():
         L.gator_launch_count.argtypes = [C.c_int]
         L.gator_mdr_self_attention.restype = C.c_int
         L.gator_mdr_self_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.gator_mdr_layer_chain.restype = C.c_int
+        L.gator_mdr_layer_chain.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.gator_umma_weight_layout.restype = C.c_int
         L.gator_umma_weight_layout.argtypes = [C.c_int32, C.c_int32, c_int_p, c_int_p, c_int_p]
         if L.gator_abi_version() != 1:

@@ -396,6 +396,25 @@ extern "C" int gator_mdr_self_attention(const float* qkv, float* out, int32_t ba
   return launch_self_attn(qkv, out, batch, (cudaStream_t)stream);
 }
 
+extern "C" int gator_mdr_layer_chain(const void* const* weights, int32_t layer, int32_t num_joint, int32_t precision,
+                                     const float* x_in, const float* att_in, const float* kv, float* x3_out,
+                                     float* qkv_out, int32_t batch, void* stream) {
+  using namespace gator;
+  GATOR_REQUIRE(weights && x_in && kv && x3_out && qkv_out, "gator_mdr_layer_chain: null buffer");
+  GATOR_REQUIRE(layer >= 0 && layer < GATOR_MDR_LAYERS && num_joint >= 2 && num_joint <= MAXJ && batch >= 0,
+                "gator_mdr_layer_chain: bad argument");
+  GATOR_REQUIRE(precision == GATOR_PREC_BF16 || precision == GATOR_PREC_BF16X3, "gator_mdr_layer_chain: tensor-core precisions only");
+  GATOR_REQUIRE((layer == 0) == (att_in == nullptr), "gator_mdr_layer_chain: att_in must be given exactly for layers 1, 2");
+  if (batch == 0) return GATOR_OK;
+  const int base = MDR_NUM_GLOBAL + layer * MDRL_NUM, pbase = MDR_NUM_GLOBAL + (layer > 0 ? layer - 1 : layer) * MDRL_NUM;
+  auto W = [&](int s) { return static_cast<const float*>(weights[base + s]); };
+  GATOR_REQUIRE(weights[base + MDRL_CHAIN], "gator_mdr_layer_chain: CHAIN blob missing");
+  const float* prm[11] = {static_cast<const float*>(weights[pbase + MDRL_SO_B]), W(MDRL_N1_W), W(MDRL_N1_B), W(MDRL_PROJ_B),
+                          W(MDRL_N2_W), W(MDRL_N2_B), W(MDRL_FC1_B), W(MDRL_FC2_B), W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
+  return launch_mdr_chain(x_in, att_in, kv, weights[base + MDRL_CHAIN], prm, x3_out, qkv_out, batch, num_joint,
+                          precision == GATOR_PREC_BF16X3, (cudaStream_t)stream);
+}
+
 extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   using namespace gator;
   cudaStream_t stream = (cudaStream_t)stream_;

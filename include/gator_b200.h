@@ -190,6 +190,14 @@ int gator_mdr_forward(const gator_mdr_args* a, void* stream);
 /* The dominant kernel on its own, for roofline measurement: 2-head 431x431 self-attention core
  * (vanilla_transformer_encoder.py:36-46) over qkv (B*431, 192) -> out (B*431, 64). */
 int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_t precision, void* stream);
+/* The fused row-wise chain of MDR layer `layer` (0..2) on its own (csrc/mdr_chain_umma.cu; tensor-core precisions
+ * only): everything of MDR.py:140-153 between two self-attention cores.  `weights` is the gator_mdr_args table;
+ * x_in (B*431,64) = embedded vertices (layer 0) or the previous layer's x3; att_in (B*431,64) = previous
+ * self-attention output (NULL for layer 0); kv (B*J,128) = this layer's cross-attention K|V;
+ * outputs x3_out (B*431,64), qkv_out (B*431,192). */
+int gator_mdr_layer_chain(const void* const* weights, int32_t layer, int32_t num_joint, int32_t precision,
+                          const float* x_in, const float* att_in, const float* kv, float* x3_out, float* qkv_out,
+                          int32_t batch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SMPL linear blend skinning - replaces SMPL_Layer.forward
