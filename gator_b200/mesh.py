@@ -66,7 +66,7 @@ def adjmat_sparse(adjmat, nsize=1):
     adjmat = scipy.sparse.coo_matrix(adjmat.multiply(num_neighbors))
     i = torch.from_numpy(np.array([adjmat.row, adjmat.col])).long()
     v = torch.from_numpy(adjmat.data).float()
-    return torch.sparse_coo_tensor(i, v, adjmat.shape)
+    return torch.sparse_coo_tensor(i, v, adjmat.shape, check_invariants=False)
 
 
 class Mesh(object):
@@ -116,6 +116,6 @@ class Mesh(object):
         for i in range(n1, n2):
             d = scipy.sparse.coo_matrix(self._D_host[i])
             sp = torch.sparse_coo_tensor(torch.from_numpy(np.array([d.row, d.col])).long(),
-                                         torch.from_numpy(d.data.astype(np.float32)), d.shape)
+                                         torch.from_numpy(d.data.astype(np.float32)), d.shape, check_invariants=False)
             x = torch.matmul(sp, x)
         return x

@@ -117,7 +117,7 @@ def mesh_spmm(M, x: torch.Tensor) -> torch.Tensor:
     m = scipy.sparse.coo_matrix(M)
     idx = torch.from_numpy(np.array([m.row, m.col])).long()
     val = torch.from_numpy(m.data.astype(np.float32)).to(x.dtype)
-    sp = torch.sparse_coo_tensor(idx, val, m.shape)
+    sp = torch.sparse_coo_tensor(idx, val, m.shape, check_invariants=False)
     return torch.matmul(sp, x)
 
 
