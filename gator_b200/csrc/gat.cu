@@ -180,7 +180,7 @@ gat_hop_mix_kernel(const float* __restrict__ y, const float* __restrict__ mask1,
 
 const char* kGlobalNames[GAT_NUM_GLOBAL] = {
     "EMB_W1", "EMB_B1", "GN_W", "GN_B", "EMB_W2T", "EMB_B2", "POS_CONST", "ATTN_BIAS",
-    "HOP_MASK1", "HOP_MASK2", "NORM_W", "NORM_B", "LIFT_W", "LIFT_B"};
+    "HOP_MASK1", "HOP_MASK2", "NORM_W", "NORM_B", "LIFT_W", "LIFT_B", "CHAIN_BLOBS", "CHAIN_PRM"};
 const char* kBlockNames[GATB_NUM] = {
     "LN1_W", "LN1_B", "QKV_W", "QKV_B", "PROJ_W", "PROJ_B", "GCN_W01", "GCN_M", "GCN_ADIAG", "GCN_AOFF",
     "GCN_BIAS", "XF_W01", "XF_B01", "XF_WB", "XF_BB", "LN2_W", "LN2_B", "FC1_W", "FC1_B", "FC2_W", "FC2_B"};
@@ -226,7 +226,10 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
   GATOR_REQUIRE(B > 0 && a->weights && a->pose2d && a->pose3d && a->feat, "gator_gat_forward: null buffer");
   const int nslots = GAT_NUM_GLOBAL + a->depth * GATB_NUM;
   for (int i = 0; i < nslots; ++i)
-    GATOR_REQUIRE(a->weights[i], "gator_gat_forward: weight slot %d is null", i);
+    GATOR_REQUIRE(a->weights[i] || i == GAT_CHAIN_BLOBS || i == GAT_CHAIN_PRM, "gator_gat_forward: weight slot %d is null", i);
+  // tensor-core precisions run all GATBlocks in one fused kernel when its weight pieces were packed
+  const bool fused = a->precision != GATOR_PREC_FP32 && a->weights[GAT_CHAIN_BLOBS] && a->weights[GAT_CHAIN_PRM] &&
+                     gat_chain_supported(J) && a->reserved == 0;
   const size_t need = gator_gat_workspace_bytes(B, J, a->chunk);
   if (!a->workspace || a->workspace_bytes < need) {
     set_error("gator_gat_forward: workspace %zu < %zu bytes", a->workspace_bytes, need);
@@ -258,7 +261,11 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
     gat_embed_kernel<<<nb, 128, 0, stream>>>(a->pose2d + (size_t)b0 * J * 2, G(GAT_EMB_W1), G(GAT_EMB_B1), G(GAT_GN_W),
                                              G(GAT_GN_B), G(GAT_EMB_W2T), G(GAT_EMB_B2), G(GAT_POS_CONST), x, J);
     GATOR_TRY(check_launch("gat_embed"));
-    for (int l = 0; l < a->depth; ++l) {
+    if (fused)
+      GATOR_TRY(launch_gat_chain(x, M, J, a->depth, static_cast<const void* const*>(a->weights[GAT_CHAIN_BLOBS]),
+                                 static_cast<const float* const*>(a->weights[GAT_CHAIN_PRM]), G(GAT_ATTN_BIAS),
+                                 G(GAT_HOP_MASK1), G(GAT_HOP_MASK2), a->precision == GATOR_PREC_BF16X3, stream));
+    for (int l = 0; !fused && l < a->depth; ++l) {
       const int base = GAT_NUM_GLOBAL + l * GATB_NUM;
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
       auto WB = [&](int s) { return GB(base + s); };

@@ -175,6 +175,7 @@ class GAT(nn.Module):
         self._ws = None
         self.precision = _lib.PREC_FP32
         self.chunk = 0
+        self.fused = True       # tensor-core precisions: all GATBlocks in one kernel (csrc/gat_chain_umma.cu)
         self.register_load_state_dict_post_hook(_invalidate_hook)
         if pretrained:
             self._load_pretrained_model()
@@ -217,9 +218,9 @@ class GAT(nn.Module):
             'LIFT_W': f(self.lifter.weight), 'LIFT_B': f(self.lifter.bias),
         }
         gnames, bnames = _lib.slot_names('gat')
-        tensors = [t[n] for n in gnames]
-        packed = [pack_umma_weight_pair(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
+        t['CHAIN_BLOBS'] = t['CHAIN_PRM'] = None          # filled in after the per-block tensors exist
         eye = torch.eye(J, device=dev)
+        block_dicts = []
         for blk in self.blocks:
             adj = blk.adj.to(dev) + blk.gcn.adj2                                         # modules.py:247-249
             adj = (adj.T + adj) / 2
@@ -237,9 +238,49 @@ class GAT(nn.Module):
                 'FC1_W': f(blk.mlp.fc1.weight), 'FC1_B': f(blk.mlp.fc1.bias),
                 'FC2_W': f(blk.mlp.fc2.weight), 'FC2_B': f(blk.mlp.fc2.bias),
             }
+            block_dicts.append(b)
+        # fused-blocks kernel (csrc/gat_chain_umma.cu): 36 weight pieces + 14 parameter arrays per block
+        keep = []
+        blobs, prms = [], []
+        zeros16 = torch.zeros(16, 128, device=dev)
+        for b in block_dicts:
+            qkv, proj, gcn = b['QKV_W'], b['PROJ_W'], b['GCN_W01']
+            w01 = torch.zeros(192, 128, device=dev)
+            w01[:144] = b['XF_W01']
+            wb = torch.zeros(128, 192, device=dev)
+            wb[:, :144] = b['XF_WB']
+            pieces = [torch.cat([qkv[16 * h:16 * h + 16], qkv[128 + 16 * h:128 + 16 * h + 16],
+                                 qkv[256 + 16 * h:256 + 16 * h + 16], zeros16], 0) for h in range(8)]
+            pieces += [proj[:, 0:64], proj[:, 64:128]]
+            pieces += [gcn[0:128, 0:64], gcn[0:128, 64:128], gcn[128:256, 0:64], gcn[128:256, 64:128]]
+            for u in range(3):
+                pieces += [w01[64 * u:64 * u + 64], wb[:, 64 * u:64 * u + 64]]
+            for u in range(8):
+                pieces += [b['FC1_W'][64 * u:64 * u + 64], b['FC2_W'][:, 64 * u:64 * u + 64]]
+            parts = []
+            for w in pieces:
+                hi, lo = pack_umma_weight_pair(w.contiguous())
+                assert hi.numel() == 64 * 128
+                parts += [hi.reshape(-1), lo.reshape(-1)]
+            blob = torch.cat(parts).contiguous()
+            xfb = torch.zeros(192, device=dev)
+            xfb[:144] = b['XF_B01']
+            plist = [b['LN1_W'], b['LN1_B'], b['QKV_B'], b['PROJ_B'], b['GCN_M'], b['GCN_ADIAG'], b['GCN_AOFF'],
+                     b['GCN_BIAS'], xfb, b['XF_BB'], b['LN2_W'], b['LN2_B'], b['FC1_B'], b['FC2_B']]
+            keep += [blob, xfb]
+            blobs.append(blob.data_ptr())
+            prms += [x_.data_ptr() for x_ in plist]
+        if self.depth > 0:
+            t['CHAIN_BLOBS'] = torch.tensor(blobs, dtype=torch.int64, device=dev)
+            t['CHAIN_PRM'] = torch.tensor(prms, dtype=torch.int64, device=dev)
+        tensors = [t[n] for n in gnames]
+        packed = [pack_umma_weight_pair(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
+        for b in block_dicts:
             tensors += [b[n] for n in bnames]
             packed += [pack_umma_weight_pair(b[n]) if n in _BF16_BLOCK else None for n in bnames]
-        table = (ctypes.c_void_p * len(tensors))(*[t_.data_ptr() for t_ in tensors])
+        tensors += keep
+        table = (ctypes.c_void_p * (len(gnames) + len(bnames) * len(block_dicts)))(
+            *[(t_.data_ptr() if t_ is not None else None) for t_ in tensors[:len(gnames) + len(bnames) * len(block_dicts)]])
         table16 = (ctypes.c_void_p * len(packed))(*[(t_[0].data_ptr() if t_ is not None else None) for t_ in packed])
         table16lo = (ctypes.c_void_p * len(packed))(*[(t_[1].data_ptr() if t_ is not None else None) for t_ in packed])
         self._packed = ((tensors, packed, table16, table16lo), table, dev)
@@ -270,7 +311,7 @@ class GAT(nn.Module):
             return pose3d, feat
         ws = self._workspace(B, dev)
         a = _lib.GatArgs(num_joint=J, depth=self.depth, batch=B, chunk=self.chunk, precision=self.precision,
-                         reserved=0, weights=table, weights_bf16=table16, weights_bf16_lo=table16lo, pose2d=_lib.ptr(x), pose3d=_lib.ptr(pose3d),
+                         reserved=0 if self.fused else 1, weights=table, weights_bf16=table16, weights_bf16_lo=table16lo, pose2d=_lib.ptr(x), pose3d=_lib.ptr(pose3d),
                          feat=_lib.ptr(feat), workspace=_lib.ptr(ws), workspace_bytes=ws.numel())
         with torch.cuda.device(dev):
             _lib.check(_lib.lib().gator_gat_forward(a, _lib.stream_ptr()), 'gator_gat_forward')

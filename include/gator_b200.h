@@ -76,6 +76,12 @@ typedef enum {
   GAT_NORM_B,         /* (128)                                                    */
   GAT_LIFT_W,         /* (3J,128J) lifter.weight                                 */
   GAT_LIFT_B,         /* (3J)                                                     */
+  GAT_CHAIN_BLOBS,    /* fused-blocks kernel (csrc/gat_chain_umma.cu), may be NULL: DEVICE array [depth] of pointers to
+                         36 x 32 KB bf16 hi|lo tcgen05 weight pieces per block: qkv per head [q_h;k_h;v_h;0] (64x128) x8,
+                         proj K-halves (128x64) x2, gcn W0 / W1 K-halves x4, {x_feat.linears rows 64u.. (64x128),
+                         linearback[:, 64u..] (128x64)} x3, {fc1 rows 64u.. , fc2[:, 64u..]} x8 */
+  GAT_CHAIN_PRM,      /* DEVICE array [depth*14] of fp32 arrays: LN1_W, LN1_B, QKV_B, PROJ_B, GCN_M, GCN_ADIAG, GCN_AOFF,
+                         GCN_BIAS, XF_B01 (zero-padded to 192), XF_BB, LN2_W, LN2_B, FC1_B, FC2_B; may be NULL */
   GAT_NUM_GLOBAL
 } gator_gat_global_slot;
 

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_struct_mirrors_and_slot_names(lib):
     from gator_b200 import _lib
     g, b = _lib.slot_names('gat')
-    assert g[0] == 'EMB_W1' and g[-1] == 'LIFT_B' and len(g) == 14 and len(b) == 21
+    assert g[0] == "EMB_W1" and g[-1] == "CHAIN_PRM" and len(g) == 16 and len(b) == 21
     g, l = _lib.slot_names('mdr')
     assert g[-1] == "UP_BIAST" and len(g) == 14 and len(l) == 19
     assert lib.gator_gat_workspace_bytes(64, 17, 0) > 0
