@@ -426,7 +426,7 @@ gat_chain_kernel(GatChainParams p) {
 
 }  // namespace
 
-bool gat_chain_supported(int J) { return J >= 2 && J <= MAXJ && smem_bytes(J) + 5 * 1024 <= 227 * 1024; }
+bool gat_chain_supported(int J) { return J >= 2 && J <= 21; }   // attention-bias table [8][J][J] must fit beside the operands
 
 int launch_gat_chain(float* x, int rows, int J, int depth, const void* const* blobs_dev, const float* const* prm_dev,
                      const float* attn_bias, const float* mask1, const float* mask2, bool split, cudaStream_t stream) {
@@ -434,7 +434,8 @@ int launch_gat_chain(float* x, int rows, int J, int depth, const void* const* bl
   if (!attr_done) {
     cudaFuncSetAttribute(gat_chain_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(17));
     cudaFuncSetAttribute(gat_chain_kernel<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(19));
-    cudaFuncSetAttribute(gat_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(gat_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(21));
+    (void)cudaGetLastError();
     attr_done = true;
   }
   GATOR_REQUIRE(gat_chain_supported(J), "gat_chain: num_joint=%d does not fit the fused kernel", J);
