@@ -238,7 +238,11 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
   auto G = [&](int s) { return static_cast<const float*>(a->weights[s]); };
   auto GB = [&](int s) { PackedW w; w.hi = a->weights_bf16 ? a->weights_bf16[s] : nullptr; w.lo = a->weights_bf16_lo ? a->weights_bf16_lo[s] : nullptr; return w; };
   const int prec = a->precision;
-  const int cb = resolve_chunk(B, a->chunk, J);
+  int cb = resolve_chunk(B, a->chunk, J);
+  if (fused && a->chunk <= 0) {   // the fused kernel only needs x (128 floats / row): run the whole batch in one pass
+    const size_t cap = a->workspace_bytes / ((size_t)J * 128 * sizeof(float));
+    cb = (size_t)B < cap ? B : (int)cap;
+  }
   const size_t rows_max = (size_t)cb * J;
   float* ws = static_cast<float*>(a->workspace);
   float* x = ws;

@@ -23,6 +23,7 @@ __global__ void __launch_bounds__(256)
 mdr_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ pose3d, const float* __restrict__ wpose,
                  const float* __restrict__ vconst, const float* __restrict__ w3, const int* __restrict__ vj,
                  float* __restrict__ jf, float* __restrict__ x, int J) {
+  // jf == nullptr: vertices only; x == nullptr: joints only
   __shared__ float p5[MAXJ][5];
   __shared__ float sw3[E * 3];
   __shared__ float swp[E * 5];
@@ -36,13 +37,14 @@ mdr_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ pos
   for (int i = tid; i < E * 3; i += 256) sw3[i] = w3[i];
   for (int i = tid; i < E * 5; i += 256) swp[i] = wpose[i];
   __syncthreads();
-  for (int i = tid; i < J * E; i += 256) {
+  for (int i = tid; jf && i < J * E; i += 256) {
     const int j = i / E, n = i - j * E;
     float a = 0.f;
 #pragma unroll
     for (int q = 0; q < 5; ++q) a = fmaf(swp[n * 5 + q], p5[j][q], a);
     jf[((size_t)b * J + j) * E + n] = a;
   }
+  if (!x) return;
   float* xb = x + (size_t)b * V * E;
   for (int i = tid; i < V * (E / 4); i += 256) {
     const int v = i / (E / 4), n = (i - v * (E / 4)) * 4;
@@ -338,16 +340,17 @@ constexpr int kSuperChunk = 8192;   // samples per upsample_conv GEMM launch (im
 
 Ws carve(float* base, int nb, int J, int nsuper) {
   Ws w;
-  const size_t mv = (size_t)nb * V, mj = (size_t)nb * J;
+  const size_t mv = (size_t)nb * V;
   size_t off = 0;
   auto take = [&](size_t n) { float* p = base ? base + off : nullptr; off += (n + 63) / 64 * 64; return p; };
   w.x = take(mv * E);
   w.y = take(mv * E);
   w.q = take(mv * E);
   w.hid = take(mv * 256);
-  w.jf = take(mj * E);
-  w.yj = take(mj * E);
-  w.kv = take(mj * 2 * E);
+  const size_t msj = (size_t)nsuper * J;   // joint rows of a super-chunk: K|V of all 3 layers are computed once for it
+  w.jf = take(msj * E);
+  w.yj = take(msj * E);
+  w.kv = take(msj * 2 * E * GATOR_MDR_LAYERS);
   w.hd = take(mv * HEADN);
   w.coarse = take((size_t)nb * V * 3);
   w.a3 = take((size_t)nsuper * 3 * UPK);
@@ -451,19 +454,37 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
 
   for (int s0 = 0; s0 < B; s0 += nsuper) {
   const int ns = (B - s0 < nsuper) ? B - s0 : nsuper;
-  for (int b0 = s0; b0 < s0 + ns; b0 += cb) {
-    const int nb = (s0 + ns - b0 < cb) ? s0 + ns - b0 : cb;
-    const int Mv = nb * V, Mj = nb * J;
-    mdr_embed_kernel<<<nb, 256, 0, stream>>>(a->pose2d + (size_t)b0 * J * 2, a->pose3d + (size_t)b0 * J * 3,
+  {
+    // joint tokens of the whole super-chunk: embedding, then LayerNorm1 + [Wk;Wv] of every layer (they depend
+    // only on the joint features, MDR.py:130,140-153) - 8 launches instead of 4 per 148-sample chunk
+    const int Msj = ns * J;
+    mdr_embed_kernel<<<ns, 256, 0, stream>>>(a->pose2d + (size_t)s0 * J * 2, a->pose3d + (size_t)s0 * J * 3,
                                              G(MDR_JF_WPOSE), G(MDR_VF_CONST), G(MDR_VF_W3),
-                                             static_cast<const int*>(a->weights[MDR_VJ]), w.jf, w.x, J);
-    GATOR_TRY(check_launch("mdr_embed"));
+                                             static_cast<const int*>(a->weights[MDR_VJ]), w.jf, nullptr, J);
+    GATOR_TRY(check_launch("mdr_embed_joints"));
     Epilogue e;
     e.bias_rows = G(MDR_JF_BIASROWS);
     e.bias_period = J;
     e.R = w.jf;
     e.ldr = E;
-    GATOR_TRY(gemm(P(32), a->feat + (size_t)b0 * J * 128, 128, G(MDR_JF_WFEAT), 128, GB(MDR_JF_WFEAT), w.jf, E, Mj, E, 128, e, stream));
+    GATOR_TRY(gemm(P(32), a->feat + (size_t)s0 * J * 128, 128, G(MDR_JF_WFEAT), 128, GB(MDR_JF_WFEAT), w.jf, E, Msj, E, 128, e, stream));
+    for (int l = 0; l < GATOR_MDR_LAYERS; ++l) {
+      const int base = MDR_NUM_GLOBAL + l * MDRL_NUM;
+      GATOR_TRY(layernorm_rows(w.jf, w.yj, static_cast<const float*>(a->weights[base + MDRL_N1_W]),
+                               static_cast<const float*>(a->weights[base + MDRL_N1_B]), Msj, E, 0, 0, stream));
+      GATOR_TRY(gemm(prec, w.yj, E, static_cast<const float*>(a->weights[base + MDRL_WKV]), E, GB(base + MDRL_WKV),
+                     w.kv + (size_t)l * Msj * 2 * E, 2 * E, Msj, 2 * E, E, Epilogue(), stream));
+    }
+  }
+  for (int b0 = s0; b0 < s0 + ns; b0 += cb) {
+    const int nb = (s0 + ns - b0 < cb) ? s0 + ns - b0 : cb;
+    const int Mv = nb * V;
+    mdr_embed_kernel<<<nb, 256, 0, stream>>>(a->pose2d + (size_t)b0 * J * 2, a->pose3d + (size_t)b0 * J * 3,
+                                             G(MDR_JF_WPOSE), G(MDR_VF_CONST), G(MDR_VF_W3),
+                                             static_cast<const int*>(a->weights[MDR_VJ]), nullptr, w.x, J);
+    GATOR_TRY(check_launch("mdr_embed"));
+    Epilogue e;
+    auto KV = [&](int l) { return w.kv + ((size_t)l * ns + (b0 - s0)) * J * 2 * E; };   // this chunk's K|V rows of layer l
 
     // bit 64 of the ablation mask disables the fused layer kernel
     const bool fused = a->precision != GATOR_PREC_FP32 && have_chain && a->reserved == 0;
@@ -472,12 +493,10 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
       auto WB = [&](int s) { return GB(base + s); };
       const int pbase = MDR_NUM_GLOBAL + (l > 0 ? l - 1 : l) * MDRL_NUM;     // previous layer's linears.3 bias
-      GATOR_TRY(layernorm_rows(w.jf, w.yj, W(MDRL_N1_W), W(MDRL_N1_B), Mj, E, 0, 0, stream));
-      GATOR_TRY(gemm(prec, w.yj, E, W(MDRL_WKV), E, WB(MDRL_WKV), w.kv, 2 * E, Mj, 2 * E, E, Epilogue(), stream));
       const float* prm[11] = {static_cast<const float*>(a->weights[pbase + MDRL_SO_B]), W(MDRL_N1_W), W(MDRL_N1_B),
                               W(MDRL_PROJ_B), W(MDRL_N2_W), W(MDRL_N2_B), W(MDRL_FC1_B), W(MDRL_FC2_B),
                               W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
-      GATOR_TRY(launch_mdr_chain(l == 0 ? w.x : w.q, l == 0 ? nullptr : w.y, w.kv, a->weights[base + MDRL_CHAIN], prm,
+      GATOR_TRY(launch_mdr_chain(l == 0 ? w.x : w.q, l == 0 ? nullptr : w.y, KV(l), a->weights[base + MDRL_CHAIN], prm,
                                  w.q, w.hid, nb, J, a->precision == GATOR_PREC_BF16X3, stream));
       GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, a->precision == GATOR_PREC_BF16X3, stream));
       if (l == GATOR_MDR_LAYERS - 1) {   // last layer: x = x3 + linears.3(att) + b, then the head
@@ -494,10 +513,8 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
       auto WB = [&](int s) { return GB(base + s); };
       // CrossAttentionBlock
       GATOR_TRY(layernorm_rows(w.x, w.y, W(MDRL_N1_W), W(MDRL_N1_B), Mv, E, 0, 0, stream));
-      GATOR_TRY(layernorm_rows(w.jf, w.yj, W(MDRL_N1_W), W(MDRL_N1_B), Mj, E, 0, 0, stream));
       GATOR_TRY(gemm(prec, w.y, E, W(MDRL_WQ), E, WB(MDRL_WQ), w.q, E, Mv, E, E, Epilogue(), stream));
-      GATOR_TRY(gemm(prec, w.yj, E, W(MDRL_WKV), E, WB(MDRL_WKV), w.kv, 2 * E, Mj, 2 * E, E, Epilogue(), stream));
-      mdr_cross_attn_kernel<<<nb, 256, 0, stream>>>(w.q, w.kv, w.y, J);
+      mdr_cross_attn_kernel<<<nb, 256, 0, stream>>>(w.q, KV(l), w.y, J);
       GATOR_TRY(check_launch("mdr_cross_attn"));
       e = Epilogue();
       e.bias = W(MDRL_PROJ_B);
