@@ -69,8 +69,9 @@ inline int gemm(int precision, const float* A, int lda, const float* W, int ldw,
 int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream);
 
 // Fused row-wise chain of one MDR layer (csrc/mdr_chain_umma.cu): x3_prev/att_prev -> x3, qkv
+// hd_out != null selects the final pass (x3 + linears[3](att) -> MDR head projection -> hd (rows, 28))
 int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
-                     float* x3_out, float* qkv_out, int nb, int J, bool split, cudaStream_t stream);
+                     float* x3_out, float* qkv_out, float* hd_out, int nb, int J, bool split, cudaStream_t stream);
 
 // All GATBlocks of the lifter in one kernel (csrc/gat_chain_umma.cu).  blobs_dev / prm_dev are DEVICE arrays of
 // pointers: [depth] weight-piece blobs and [depth * 14] fp32 parameter arrays.

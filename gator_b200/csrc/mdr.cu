@@ -319,7 +319,7 @@ mdr_head_kernel(const float* __restrict__ hd, const float* __restrict__ nscale, 
 
 const char* kGlobalNames[MDR_NUM_GLOBAL] = {
     "JF_WFEAT", "JF_WPOSE", "JF_BIASROWS", "VF_CONST", "VF_W3", "VJ", "HEAD_W", "HEAD_B",
-    "BNORM_SCALE", "BNORM_SHIFT", "BCONV_W", "BCONV_B", "UP_W", "UP_BIAST"};
+    "BNORM_SCALE", "BNORM_SHIFT", "BCONV_W", "BCONV_B", "UP_W", "UP_BIAST", "CHAIN_FINAL"};
 const char* kLayerNames[MDRL_NUM] = {
     "N1_W", "N1_B", "WQ", "WKV", "PROJ_W", "PROJ_B", "N2_W", "N2_B", "FC1_W", "FC1_B", "FC2_W", "FC2_B",
     "CLN_A", "CLN_B", "SQKV_W", "SQKV_B", "SO_W", "SO_B", "CHAIN"};
@@ -414,7 +414,7 @@ extern "C" int gator_mdr_layer_chain(const void* const* weights, int32_t layer, 
   GATOR_REQUIRE(weights[base + MDRL_CHAIN], "gator_mdr_layer_chain: CHAIN blob missing");
   const float* prm[11] = {static_cast<const float*>(weights[pbase + MDRL_SO_B]), W(MDRL_N1_W), W(MDRL_N1_B), W(MDRL_PROJ_B),
                           W(MDRL_N2_W), W(MDRL_N2_B), W(MDRL_FC1_B), W(MDRL_FC2_B), W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
-  return launch_mdr_chain(x_in, att_in, kv, weights[base + MDRL_CHAIN], prm, x3_out, qkv_out, batch, num_joint,
+  return launch_mdr_chain(x_in, att_in, kv, weights[base + MDRL_CHAIN], prm, x3_out, qkv_out, nullptr, batch, num_joint,
                           precision == GATOR_PREC_BF16X3, (cudaStream_t)stream);
 }
 
@@ -430,7 +430,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   const int nslots = MDR_NUM_GLOBAL + GATOR_MDR_LAYERS * MDRL_NUM;
   bool have_chain = true;
   for (int i = 0; i < nslots; ++i) {
-    if (i >= MDR_NUM_GLOBAL && (i - MDR_NUM_GLOBAL) % MDRL_NUM == MDRL_CHAIN) {
+    if (i == MDR_CHAIN_FINAL || (i >= MDR_NUM_GLOBAL && (i - MDR_NUM_GLOBAL) % MDRL_NUM == MDRL_CHAIN)) {
       have_chain = have_chain && a->weights[i] != nullptr;
       continue;
     }
@@ -497,14 +497,13 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
                               W(MDRL_PROJ_B), W(MDRL_N2_W), W(MDRL_N2_B), W(MDRL_FC1_B), W(MDRL_FC2_B),
                               W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
       GATOR_TRY(launch_mdr_chain(l == 0 ? w.x : w.q, l == 0 ? nullptr : w.y, KV(l), a->weights[base + MDRL_CHAIN], prm,
-                                 w.q, w.hid, nb, J, a->precision == GATOR_PREC_BF16X3, stream));
+                                 w.q, w.hid, nullptr, nb, J, a->precision == GATOR_PREC_BF16X3, stream));
       GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, a->precision == GATOR_PREC_BF16X3, stream));
-      if (l == GATOR_MDR_LAYERS - 1) {   // last layer: x = x3 + linears.3(att) + b, then the head
-        Epilogue e2;
-        e2.bias = W(MDRL_SO_B);
-        e2.R = w.q;
-        e2.ldr = E;
-        GATOR_TRY(gemm(prec, w.y, E, W(MDRL_SO_W), E, WB(MDRL_SO_W), w.x, E, Mv, E, E, e2, stream));
+      if (l == GATOR_MDR_LAYERS - 1) {   // last layer: x = x3 + linears.3(att) + b and the head projection, fused
+        const float* prm2[11] = {W(MDRL_SO_B), G(MDR_HEAD_B), W(MDRL_N1_B), W(MDRL_PROJ_B), W(MDRL_N2_W), W(MDRL_N2_B),
+                                 W(MDRL_FC1_B), W(MDRL_FC2_B), W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
+        GATOR_TRY(launch_mdr_chain(w.q, w.y, KV(l), a->weights[MDR_CHAIN_FINAL], prm2, nullptr, nullptr, w.hd, nb, J,
+                                   a->precision == GATOR_PREC_BF16X3, stream));
       }
     }
     for (int l = 0; !fused && l < GATOR_MDR_LAYERS; ++l) {
@@ -545,9 +544,11 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
       GATOR_TRY(gemm(prec, w.y, E, W(MDRL_SO_W), E, WB(MDRL_SO_W), w.x, E, Mv, E, E, e, stream));
     }
     // head
-    e = Epilogue();
-    e.bias = G(MDR_HEAD_B);
-    GATOR_TRY(gemm(P(8), w.x, E, G(MDR_HEAD_W), E, GB(MDR_HEAD_W), w.hd, HEADN, Mv, HEADN, E, e, stream));
+    if (!fused) {
+      e = Epilogue();
+      e.bias = G(MDR_HEAD_B);
+      GATOR_TRY(gemm(P(8), w.x, E, G(MDR_HEAD_W), E, GB(MDR_HEAD_W), w.hd, HEADN, Mv, HEADN, E, e, stream));
+    }
     mdr_head_kernel<<<nb, 256, 0, stream>>>(w.hd, G(MDR_BNORM_SCALE), G(MDR_BNORM_SHIFT), G(MDR_BCONV_W),
                                             G(MDR_BCONV_B), a->alpha, a->coarse ? a->coarse + (size_t)b0 * V * 3 : nullptr,
                                             w.a3 + (size_t)(b0 - s0) * 3 * UPK);

@@ -50,6 +50,8 @@ struct ChainParams {
   const float* prm[11];   // so_b, n1w, n1b, proj_b, n2w, n2b, fc1_b, fc2_b, cln_a, cln_b, qkv_b
   float* x3_out;          // (nb*431, 64)
   float* qkv_out;         // (nb*431, 192)
+  float* hd_out;          // non-null: FINAL pass - only x = x_in + att_in Wo^T + b, then hd = x W_head^T + b_head (nb*431, 28);
+                          // blob = [linears[3] of the last layer, head (28 rows zero-padded to 64)], prm[0] = so_b, prm[1] = head_b
   int J;
   int split;              // 1: 3-term bf16 split products
 };
@@ -136,7 +138,7 @@ mdr_chain_kernel(ChainParams p) {
     mbar_init(&bar, 1);
     mbar_init_fence();
   }
-  const int first_unit = p.att_in ? U_SO : U_Q;
+  const int first_unit = p.att_in ? U_SO : U_Q;   // (the FINAL pass needs att_in: unit 0 = linears[3], unit 1 = head)
   prefetch_w(first_unit, 0);
   for (int i = tid; i < J * 128; i += NT) skv[i] = p.kv[(size_t)b * J * 128 + i];
   tc_fence_before();
@@ -223,6 +225,22 @@ mdr_chain_kernel(ChainParams p) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) x[i] += v[i] + pw[i];
   }
+  if (p.hd_out) {
+    // final pass after the last self-attention: x = x3 + linears[3](att) + b is complete; apply the MDR head
+    // projection [motion_linear | bias_linear | scale_linear] (MDR.py:156-162) and stop
+    write_a<4>(a0, row, ch * 4, x);
+    run_unit(0, 0, false, -1);
+    if (ch == 0) {
+      ld32(acc, v);
+      if (valid) {
+        float* dst = p.hd_out + grow * 28;
+#pragma unroll
+        for (int i = 0; i < 28; i += 4)
+          *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] + __ldg(p.prm[P_N1W] + i), v[i + 1] + __ldg(p.prm[P_N1W] + i + 1),
+                                                            v[i + 2] + __ldg(p.prm[P_N1W] + i + 2), v[i + 3] + __ldg(p.prm[P_N1W] + i + 3));
+      }
+    }
+  } else {
   // ---- LayerNorm1 -> q ----
   {
     float mean, m2;
@@ -337,6 +355,7 @@ mdr_chain_kernel(ChainParams p) {
         dst[i] = make_float4(v[4 * i] + __ldg(bq + 4 * i), v[4 * i + 1] + __ldg(bq + 4 * i + 1), v[4 * i + 2] + __ldg(bq + 4 * i + 2), v[4 * i + 3] + __ldg(bq + 4 * i + 3));
     }
   }
+  }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 128 * TILES);
@@ -346,7 +365,7 @@ mdr_chain_kernel(ChainParams p) {
 
 // x_in / att_in / kv / outputs as in ChainParams; prm = 11 device pointers (so_b of the PREVIOUS layer first).
 int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
-                     float* x3_out, float* qkv_out, int nb, int J, bool split, cudaStream_t stream) {
+                     float* x3_out, float* qkv_out, float* hd_out, int nb, int J, bool split, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(mdr_chain_kernel<1, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, 17));
@@ -358,7 +377,7 @@ int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, co
   ChainParams p;
   p.x_in = x_in; p.att_in = att_in; p.kv = kv; p.blob = static_cast<const uint8_t*>(blob);
   for (int i = 0; i < 11; ++i) p.prm[i] = prm[i];
-  p.x3_out = x3_out; p.qkv_out = qkv_out; p.J = J; p.split = split ? 1 : 0;
+  p.x3_out = x3_out; p.qkv_out = qkv_out; p.hd_out = hd_out; p.J = J; p.split = split ? 1 : 0;
   // one tile per CTA fits twice on an SM (2 x ~107 KB) as long as J <= 24; otherwise two tiles per CTA
   if (J == 17) mdr_chain_kernel<1, 17><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);
   else if (J == 19) mdr_chain_kernel<1, 19><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);

@@ -178,9 +178,9 @@ class MDR(nn.Module):
             'UP_W': f(up_w),
             'UP_BIAST': f(self.upsample_conv.bias[:, None] + self.init_vertices_6890),
         }
+        t['CHAIN_FINAL'] = None
         gnames, lnames = _lib.slot_names('mdr')
-        tensors = [t[n] for n in gnames]
-        packed = [pack_umma_weight_pair(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
+        layer_dicts = []
         prev_so = None
         for sfx in ('', '_1', '_2'):
             enc, sa, cln = getattr(self, 'encoder' + sfx), getattr(self, 'selfatt' + sfx), getattr(self, 'norm' + sfx)
@@ -207,6 +207,17 @@ class MDR(nn.Module):
                 blob += [hi.reshape(-1), lo.reshape(-1)]
             l['CHAIN'] = torch.cat(blob).contiguous()
             prev_so = l['SO_W']
+            layer_dicts.append(l)
+        head64 = torch.zeros(E, E, device=dev)
+        head64[:28] = t['HEAD_W']
+        fin = []
+        for u in (prev_so, head64):
+            hi, lo = pack_umma_weight_pair(u.contiguous())
+            fin += [hi.reshape(-1), lo.reshape(-1)]
+        t['CHAIN_FINAL'] = torch.cat(fin).contiguous()
+        tensors = [t[n] for n in gnames]
+        packed = [pack_umma_weight_pair(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
+        for l in layer_dicts:
             tensors += [l[n] for n in lnames]
             packed += [pack_umma_weight_pair(l[n]) if n in _BF16_LAYER else None for n in lnames]
         table = (ctypes.c_void_p * len(tensors))(*[t_.data_ptr() for t_ in tensors])
@@ -215,8 +226,16 @@ class MDR(nn.Module):
         self._packed = ((tensors, packed, table16, table16lo), table, dev)
         return self
 
+    def _chunk(self):
+        """Samples per pass through the workspace.  fp32 (kernel per op): 148, small enough for the token matrices
+        to stay L2-resident between kernels; tensor-core path (fused layer kernel): 1184 = 8 x 148, fewer launches
+        (measured on B200: 25.3 ms/step at 148 -> 23.6 ms at 1184 for B = 4096)."""
+        if self.chunk > 0:
+            return self.chunk
+        return 148 if self.precision == _lib.PREC_FP32 else 1184
+
     def _workspace(self, batch, dev):
-        need = _lib.lib().gator_mdr_workspace_bytes(batch, self.num_joint, self.chunk)
+        need = _lib.lib().gator_mdr_workspace_bytes(batch, self.num_joint, self._chunk())
         if self._ws is None or self._ws.numel() < need or self._ws.device != dev:
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         return self._ws
@@ -240,7 +259,7 @@ class MDR(nn.Module):
         coarse = torch.empty((B, V_COARSE, 3), dtype=torch.float32, device=dev) if want_coarse else None
         if B > 0:
             ws = self._workspace(B, dev)
-            a = _lib.MdrArgs(num_joint=J, batch=B, chunk=self.chunk, alpha=int(self.alpha), precision=self.precision,
+            a = _lib.MdrArgs(num_joint=J, batch=B, chunk=self._chunk(), alpha=int(self.alpha), precision=self.precision,
                              reserved=self.bf16_mask, weights=table, weights_bf16=table16, weights_bf16_lo=table16lo, pose2d=_lib.ptr(p2), pose3d=_lib.ptr(p3), feat=_lib.ptr(ft),
                              mesh=_lib.ptr(mesh), coarse=_lib.ptr(coarse), workspace=_lib.ptr(ws),
                              workspace_bytes=ws.numel())

@@ -146,6 +146,8 @@ typedef enum {
   MDR_BCONV_B,        /* (20)                                                                 */
   MDR_UP_W,           /* (6890,1296) upsample_conv.weight flattened (431*3=1293), K zero-padded */
   MDR_UP_BIAST,       /* (6890,3)   upsample_conv.bias[:,None] + init_vertices_6890            */
+  MDR_CHAIN_FINAL,    /* bf16 blob for the final pass of the fused layer kernel: 2 units x [hi 8 KB | lo 8 KB]: the last
+                         layer's selfatt.linears.3 and HEAD_W zero-padded to 64 rows; may be NULL          */
   MDR_NUM_GLOBAL
 } gator_mdr_global_slot;
 
