@@ -198,14 +198,12 @@ def run_b200(args):
     value = B * world / (step_ms * 1e-3)
 
     # ---- end to end: pinned host input -> H2D -> forward -> mesh + pose3d D2H ----
-    mesh_host = torch.empty((B, 6890, 3), dtype=torch.float32).pin_memory()
-    p3_host = torch.empty((B, J, 3), dtype=torch.float32).pin_memory()
+    from gator_b200.pipeline import HostPipeline
+    pipe = HostPipeline(model, B, slices=8)          # public host-to-host API: sliced forward, D2H overlapped
+    mesh_host, p3_host = pipe.mesh_host, pipe.pose3d_host
     with torch.no_grad():
         def e2e_step():
-            xd = x_host.to(dev, non_blocking=True)
-            m, p = model(xd)
-            mesh_host.copy_(m, non_blocking=True)
-            p3_host.copy_(p, non_blocking=True)
+            pipe.forward(x_host)
         e2e_step()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

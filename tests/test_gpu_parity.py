@@ -282,3 +282,16 @@ def test_joint_regression_post_step(models):
     j = reg(mesh)
     assert np.abs(j.cpu().numpy() - g['h36m/joints']).max() <= 1e-6
     assert torch.allclose(reg(mesh, scale=1000.0), j * 1000.0, rtol=1e-6)
+
+
+def test_host_pipeline_matches_plain_forward(models):
+    """gator_b200.pipeline.HostPipeline (sliced forward with overlapped device-to-host copies) returns exactly
+    what one forward + .cpu() returns."""
+    from gator_b200.pipeline import HostPipeline
+    m = models['h36m']
+    x = torch.from_numpy(synthetic.poses2d(37, 17, seed=9)).pin_memory()
+    mesh, p3 = m(x.to(DEV))
+    pipe = HostPipeline(m, 37, slices=4)
+    hm, hp = pipe.forward(x)
+    torch.cuda.synchronize()
+    assert torch.equal(hm, mesh.cpu()) and torch.equal(hp, p3.cpu())
