@@ -66,8 +66,7 @@ inline int gemm(int precision, const float* A, int lda, const float* W, int ldw,
 }
 
 // tcgen05 version of the MDR self-attention core: qkv (nb*431, 192) -> out (nb*431, 64)
-// mode 0: bf16; 1: 3-term bf16 split in both GEMMs; 2: 3-term split for Q K^T, TF32 P and V for P V
-int launch_self_attn_umma(const float* qkv, float* out, int nb, int mode, cudaStream_t stream);
+int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream);
 
 // Fused row-wise chain of one MDR layer (csrc/mdr_chain_umma.cu): x3_prev/att_prev -> x3, qkv
 // hd_out != null selects the final pass (x3 + linears[3](att) -> MDR head projection -> hd (rows, 28))

@@ -393,10 +393,9 @@ int launch_self_attn(const float* qkv, float* out, int nb, cudaStream_t stream) 
 extern "C" int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_t precision, void* stream) {
   using namespace gator;
   GATOR_REQUIRE(qkv && out && batch >= 0, "gator_mdr_self_attention: bad argument");
-  GATOR_REQUIRE(precision >= GATOR_PREC_FP32 && precision <= 3, "gator_mdr_self_attention: bad precision %d", precision);
+  GATOR_REQUIRE(precision >= GATOR_PREC_FP32 && precision <= GATOR_PREC_BF16X3, "gator_mdr_self_attention: bad precision %d", precision);
   if (batch == 0) return GATOR_OK;
-  if (precision == 3) return launch_self_attn_umma(qkv, out, batch, 2, (cudaStream_t)stream);   // experimental: TF32 P V
-  if (precision != GATOR_PREC_FP32) return launch_self_attn_umma(qkv, out, batch, precision == GATOR_PREC_BF16X3 ? 1 : 0, (cudaStream_t)stream);
+  if (precision != GATOR_PREC_FP32) return launch_self_attn_umma(qkv, out, batch, precision == GATOR_PREC_BF16X3, (cudaStream_t)stream);
   return launch_self_attn(qkv, out, batch, (cudaStream_t)stream);
 }
 
@@ -449,7 +448,6 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   const int mask = a->reserved ? a->reserved : ~0;
   auto P = [&](int bit) { return (a->precision != GATOR_PREC_FP32 && (mask & bit)) ? a->precision : (int)GATOR_PREC_FP32; };
   const int prec = P(2);
-  const int attn_mode = 1;   // bf16x3: 3-term split in both attention GEMMs (mode 2 = TF32 P V, see mdr_attn_umma.cu)
   const int cb = resolve_chunk(B, a->chunk);
   const int nsuper = B < kSuperChunk ? B : kSuperChunk;
   Ws w = carve(static_cast<float*>(a->workspace), cb, J, nsuper);
@@ -500,7 +498,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
                               W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
       GATOR_TRY(launch_mdr_chain(l == 0 ? w.x : w.q, l == 0 ? nullptr : w.y, KV(l), a->weights[base + MDRL_CHAIN], prm,
                                  w.q, w.hid, nullptr, nb, J, a->precision == GATOR_PREC_BF16X3, stream));
-      GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, a->precision == GATOR_PREC_BF16X3 ? attn_mode : 0, stream));
+      GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, a->precision == GATOR_PREC_BF16X3, stream));
       if (l == GATOR_MDR_LAYERS - 1) {   // last layer: x = x3 + linears.3(att) + b and the head projection, fused
         const float* prm2[11] = {W(MDRL_SO_B), G(MDR_HEAD_B), W(MDRL_N1_B), W(MDRL_PROJ_B), W(MDRL_N2_W), W(MDRL_N2_B),
                                  W(MDRL_FC1_B), W(MDRL_FC2_B), W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
@@ -537,7 +535,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
       e = Epilogue();
       e.bias = W(MDRL_SQKV_B);
       GATOR_TRY(gemm(prec, w.q, E, W(MDRL_SQKV_W), E, WB(MDRL_SQKV_W), w.hid, 3 * E, Mv, 3 * E, E, e, stream));
-      if (P(4) != GATOR_PREC_FP32) GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, P(4) == GATOR_PREC_BF16X3 ? 1 : 0, stream));
+      if (P(4) != GATOR_PREC_FP32) GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, P(4) == GATOR_PREC_BF16X3, stream));
       else GATOR_TRY(launch_self_attn(w.hid, w.y, nb, stream));
       e = Epilogue();
       e.bias = W(MDRL_SO_B);

@@ -33,27 +33,7 @@ constexpr int SK_BYTES = VP * DK * 2;        // 27 648  K   [kg 54][kc 4][8][8]
 constexpr int SVT_BYTES = DK * VP * 2;       // 27 648  V^T [dg 4][kc 54][8][8]
 constexpr int SQ_BYTES = QT * DK * 2;        //  8 192  Q   [rg 16][kc 4][8][8]
 constexpr int SP_BYTES = QT * PK * 2;        // 36 864  P   [rg 16][kc 18][8][8]
-// MODE 0: bf16 operands.  MODE 1: bf16 hi/lo images of Q, K, V^T, P (3-term products everywhere).
-// MODE 2: 3-term bf16 products for S = Q K^T, but P and V^T as TF32 (fp32 bits, rounded with cvt.rna) for O = P V:
-//         same shared-memory footprint, no hi/lo conversion of the 431 x 431 probabilities.
-constexpr int smem_bytes(int mode) { return (mode ? 2 : 1) * (SK_BYTES + SVT_BYTES + SQ_BYTES + SP_BYTES); }
-__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ float to_tf32(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
+constexpr int smem_bytes(bool split) { return (split ? 2 : 1) * (SK_BYTES + SVT_BYTES + SQ_BYTES + SP_BYTES); }
 
 __device__ __forceinline__ float ex2(float x) {
   float y;
@@ -81,7 +61,7 @@ __device__ __forceinline__ uint4 pack8_residual(const float* v, const uint4& hi)
 
 constexpr int NT = 512;   // 16 warps: (lane quarter 4) x (column quarter 4): 4 threads share a score row
 
-template <int MODE>
+template <bool SPLIT>
 __global__ void __launch_bounds__(NT, 1)
 mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -89,14 +69,12 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   __shared__ uint32_t tmem_slot;
   __shared__ float red_max[4][QT];
   __shared__ float red_sum[4][QT];
-  constexpr bool SPLIT = MODE != 0;          // Q / K carry bf16 residual images
-  constexpr bool PV32 = MODE == 2;           // P and V^T are TF32 images instead of bf16 hi (+ lo)
-  // [K hi | K lo] [Q hi | Q lo] [V^T hi | V^T lo  or  V^T tf32] [P hi | P lo  or  P tf32]   (lo images only if SPLIT)
-  constexpr int KLO = SK_BYTES, QLO = SQ_BYTES, VLO = SVT_BYTES, PLO = SP_BYTES;   // hi -> lo image offsets
+  // hi images first, lo images (SPLIT only) after them
   uint8_t* sK = smem;
-  uint8_t* sQ = sK + (SPLIT ? 2 : 1) * SK_BYTES;
-  uint8_t* sVT = sQ + (SPLIT ? 2 : 1) * SQ_BYTES;
-  uint8_t* sP = sVT + (SPLIT ? 2 : 1) * SVT_BYTES;
+  uint8_t* sVT = sK + SK_BYTES;
+  uint8_t* sQ = sVT + SVT_BYTES;
+  uint8_t* sP = sQ + SQ_BYTES;
+  constexpr int LO = SK_BYTES + SVT_BYTES + SQ_BYTES + SP_BYTES;   // offset of the residual images
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int b = blockIdx.x >> 1, h = blockIdx.x & 1;
@@ -120,7 +98,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     }
     const uint4 hi = cvt8(a, bb);
     reinterpret_cast<uint4*>(sK)[c] = hi;
-    if (SPLIT) reinterpret_cast<uint4*>(sK + KLO)[c] = cvt8_residual(a, bb, hi);
+    if (SPLIT) reinterpret_cast<uint4*>(sK + LO)[c] = cvt8_residual(a, bb, hi);
   }
   // ---- stage V^T: warp takes a group of 8 keys, lane = d; chunk (dg, kc, r): d = dg*8 + r ----
   for (int kc = warp; kc < KCH; kc += NT / 32) {
@@ -131,16 +109,10 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
       v[i] = key < V ? base[(size_t)key * 3 * E + 2 * E + h * DK + lane] : 0.f;
     }
     const int dg = lane >> 3, r = lane & 7;
-    if (PV32) {   // tf32 image [dg 4][kc 108][8][4 x fp32]: this lane's 8 keys = two 16-byte chunks
-      uint8_t* dst = sVT + (size_t)dg * (2 * KCH * 128) + (2 * kc) * 128 + r * 16;
-      *reinterpret_cast<float4*>(dst) = make_float4(to_tf32(v[0]), to_tf32(v[1]), to_tf32(v[2]), to_tf32(v[3]));
-      *reinterpret_cast<float4*>(dst + 128) = make_float4(to_tf32(v[4]), to_tf32(v[5]), to_tf32(v[6]), to_tf32(v[7]));
-    } else {
-      const size_t off = (size_t)dg * (KCH * 128) + kc * 128 + r * 16;
-      const uint4 hi = pack8(v);
-      *reinterpret_cast<uint4*>(sVT + off) = hi;
-      if (SPLIT) *reinterpret_cast<uint4*>(sVT + VLO + off) = pack8_residual(v, hi);
-    }
+    const size_t off = (size_t)dg * (KCH * 128) + kc * 128 + r * 16;
+    const uint4 hi = pack8(v);
+    *reinterpret_cast<uint4*>(sVT + off) = hi;
+    if (SPLIT) *reinterpret_cast<uint4*>(sVT + LO + off) = pack8_residual(v, hi);
   }
   tc_fence_before();
   __syncthreads();
@@ -168,7 +140,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
       }
       const uint4 hi = cvt8(a, bb);
       reinterpret_cast<uint4*>(sQ)[c] = hi;
-      if (SPLIT) reinterpret_cast<uint4*>(sQ + QLO)[c] = cvt8_residual(a, bb, hi);
+      if (SPLIT) reinterpret_cast<uint4*>(sQ + LO)[c] = cvt8_residual(a, bb, hi);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -183,8 +155,8 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
         const uint64_t ad = smem_desc(q0 + ks * 256, 128, 512);
         const uint64_t b0d = smem_desc(k0 + ks * 256, 128, 512), b1d = smem_desc(k0 + kofs + ks * 256, 128, 512);
         if (SPLIT) {
-          const uint64_t adl = smem_desc(q0 + QLO + ks * 256, 128, 512);
-          const uint64_t b0l = smem_desc(k0 + KLO + ks * 256, 128, 512), b1l = smem_desc(k0 + KLO + kofs + ks * 256, 128, 512);
+          const uint64_t adl = smem_desc(q0 + LO + ks * 256, 128, 512);
+          const uint64_t b0l = smem_desc(k0 + LO + ks * 256, 128, 512), b1l = smem_desc(k0 + LO + kofs + ks * 256, 128, 512);
           mma_bf16(tmem, adl, b0d, i0, ks);
           mma_bf16(tmem, ad, b0l, i0, 1);
           mma_bf16(tmem, ad, b0d, i0, 1);
@@ -232,7 +204,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     // ---- pass 2, one third of the keys at a time: P = exp2(s*c - max*c) -> smem, O += P V ----
     float sum = 0.f;
     for (int part = 0; part < PARTS; ++part) {
-      uint8_t* prow = sP + (size_t)(row >> 3) * ((PV32 ? 2 : 1) * PCH * 128) + (row & 7) * 16;
+      uint8_t* prow = sP + (size_t)(row >> 3) * (PCH * 128) + (row & 7) * 16;
       float sc[5][8];
 #pragma unroll
       for (int j = 0; j < 5; ++j)
@@ -244,20 +216,12 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
           float* s = sc[j];
           const int col0 = part * PK + (p2_lo + j) * 8;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            s[i] = (col0 + i) < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
-            if (PV32) s[i] = to_tf32(s[i]);      // the row sum uses exactly the values the tensor core will see
-          }
+          for (int i = 0; i < 8; ++i) s[i] = (col0 + i) < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
           sum += ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+          const uint4 hi = pack8(s);
           const int kc = p2_lo + j;
-          if (PV32) {
-            *reinterpret_cast<float4*>(prow + (2 * kc) * 128) = make_float4(s[0], s[1], s[2], s[3]);
-            *reinterpret_cast<float4*>(prow + (2 * kc + 1) * 128) = make_float4(s[4], s[5], s[6], s[7]);
-          } else {
-            const uint4 hi = pack8(s);
-            *reinterpret_cast<uint4*>(prow + kc * 128) = hi;
-            if (SPLIT) *reinterpret_cast<uint4*>(prow + PLO + kc * 128) = pack8_residual(s, hi);
-          }
+          *reinterpret_cast<uint4*>(prow + kc * 128) = hi;
+          if (SPLIT) *reinterpret_cast<uint4*>(prow + LO + kc * 128) = pack8_residual(s, hi);
         }
       }
       fence_proxy_async();
@@ -265,27 +229,18 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        if (PV32) {   // TF32: 4 elements per 16-byte chunk, K = 8 per MMA = 256 B, 18 k-steps per key third
-          const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sVT) + part * (2 * PCH * 128);
-          const uint32_t io = idesc_tf32(QT, DK);
+        const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sVT) + part * (PCH * 128);
+        const uint32_t io = idesc_bf16(QT, DK);
 #pragma unroll 1
-          for (int ks = 0; ks < PK / 8; ++ks)
-            mma_tf32(tmem_o, smem_desc(p0 + ks * 256, 128, 2 * PCH * 128), smem_desc(v0 + ks * 256, 128, 2 * KCH * 128), io,
-                     (part | ks) != 0);
-        } else {
-          const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sVT) + part * (PCH * 128);
-          const uint32_t io = idesc_bf16(QT, DK);
-#pragma unroll 1
-          for (int ks = 0; ks < PK / 16; ++ks) {
-            const uint32_t acc = (part | ks) != 0;
-            const uint64_t pd = smem_desc(p0 + ks * 256, 128, PCH * 128), vd = smem_desc(v0 + ks * 256, 128, KCH * 128);
-            if (SPLIT) {
-              mma_bf16(tmem_o, smem_desc(p0 + PLO + ks * 256, 128, PCH * 128), vd, io, acc);
-              mma_bf16(tmem_o, pd, smem_desc(v0 + VLO + ks * 256, 128, KCH * 128), io, 1);
-              mma_bf16(tmem_o, pd, vd, io, 1);
-            } else {
-              mma_bf16(tmem_o, pd, vd, io, acc);
-            }
+        for (int ks = 0; ks < PK / 16; ++ks) {
+          const uint32_t acc = (part | ks) != 0;
+          const uint64_t pd = smem_desc(p0 + ks * 256, 128, PCH * 128), vd = smem_desc(v0 + ks * 256, 128, KCH * 128);
+          if (SPLIT) {
+            mma_bf16(tmem_o, smem_desc(p0 + LO + ks * 256, 128, PCH * 128), vd, io, acc);
+            mma_bf16(tmem_o, pd, smem_desc(v0 + LO + ks * 256, 128, KCH * 128), io, 1);
+            mma_bf16(tmem_o, pd, vd, io, 1);
+          } else {
+            mma_bf16(tmem_o, pd, vd, io, acc);
           }
         }
         mma_commit(&bar_o);
@@ -317,17 +272,15 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
 
 }  // namespace
 
-int launch_self_attn_umma(const float* qkv, float* out, int nb, int mode, cudaStream_t stream) {
+int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(mdr_self_attn_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(0));
-    cudaFuncSetAttribute(mdr_self_attn_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1));
-    cudaFuncSetAttribute(mdr_self_attn_umma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2));
+    cudaFuncSetAttribute(mdr_self_attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(false));
+    cudaFuncSetAttribute(mdr_self_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true));
     attr_done = true;
   }
-  if (mode == 2) mdr_self_attn_umma_kernel<2><<<nb * 2, NT, smem_bytes(2), stream>>>(qkv, out);
-  else if (mode == 1) mdr_self_attn_umma_kernel<1><<<nb * 2, NT, smem_bytes(1), stream>>>(qkv, out);
-  else mdr_self_attn_umma_kernel<0><<<nb * 2, NT, smem_bytes(0), stream>>>(qkv, out);
+  if (split) mdr_self_attn_umma_kernel<true><<<nb * 2, NT, smem_bytes(true), stream>>>(qkv, out);
+  else mdr_self_attn_umma_kernel<false><<<nb * 2, NT, smem_bytes(false), stream>>>(qkv, out);
   return check_launch("mdr_self_attn_umma");
 }
 
