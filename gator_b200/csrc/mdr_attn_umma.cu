@@ -5,7 +5,8 @@
 //   S = Q K^T      -> TMEM columns [0,432)   (MMAs of N = 224 / 208, K = 32)
 //   row max        -> 512 threads, thread = (row, column quarter); the whole key range of a row sits in TMEM,
 //                     so it is a plain two-pass softmax - no online rescaling
-//   for each third of the keys (144): P = exp2(.) as bf16 -> shared memory (A operand), O += P V
+//   for each of 6 key parts (80 / 64 keys): P = exp2(.) as bf16 -> one of two smem buffers (A operand), O += P V;
+//                     the exp pass of the next part runs while the tensor core consumes the previous one
 //   O (TMEM columns [432,464)) scaled by 1/rowsum on the way out.
 // SPLIT mode (GATOR_PREC_BF16X3) carries bf16 residuals of Q, K, V and P as well and issues the 3-term
 // product for both GEMMs, which brings the kernel to ~1e-5 absolute error (fp32-parity on tensor cores);
@@ -25,14 +26,14 @@ constexpr int E = 64;
 constexpr int QT = 128;             // query rows per tile
 constexpr int KCH = VP / 8;         // 54 key chunks
 constexpr int N0 = 224, N1 = 208;   // S = two MMAs (N <= 256, multiple of 16)
-constexpr int PARTS = 3;
-constexpr int PK = VP / PARTS;      // 144 keys per P part
-constexpr int PCH = PK / 8;         // 18 chunks
+constexpr int PARTS = 6;            // key parts of 80 / 64 keys alternately (5 / 4 k-steps of 16); P is double-buffered so the
+constexpr int PCH = 10;             // exp pass of part p+1 overlaps the P V MMAs of part p.  PCH = chunks per P buffer row group
 
 constexpr int SK_BYTES = VP * DK * 2;        // 27 648  K   [kg 54][kc 4][8][8]
 constexpr int SVT_BYTES = DK * VP * 2;       // 27 648  V^T [dg 4][kc 54][8][8]
 constexpr int SQ_BYTES = QT * DK * 2;        //  8 192  Q   [rg 16][kc 4][8][8]
-constexpr int SP_BYTES = QT * PK * 2;        // 36 864  P   [rg 16][kc 18][8][8]
+constexpr int PBUF = QT * PCH * 8 * 2;        // 20 480  one P buffer [rg 16][kc 10][8][8]
+constexpr int SP_BYTES = 2 * PBUF;           // 40 960  two P buffers
 constexpr int smem_bytes(bool split) { return (split ? 2 : 1) * (SK_BYTES + SVT_BYTES + SQ_BYTES + SP_BYTES); }
 
 __device__ __forceinline__ float ex2(float x) {
@@ -65,7 +66,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(NT, 1)
 mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar_s, bar_o;
+  __shared__ uint64_t bar_s, bar_p[2];
   __shared__ uint32_t tmem_slot;
   __shared__ float red_max[4][QT];
   __shared__ float red_sum[4][QT];
@@ -83,7 +84,8 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 32) {
     mbar_init(&bar_s, 1);
-    mbar_init(&bar_o, 1);
+    mbar_init(&bar_p[0], 1);
+    mbar_init(&bar_p[1], 1);
     mbar_init_fence();
   }
   // ---- stage K: chunk c = (kg, kc, r) -> key = kg*8 + r, d = kc*8 ----
@@ -122,10 +124,9 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   const int cq = warp >> 2;                         // which column quarter of the row this thread owns
   const int p1_lo = cq < 2 ? cq * 14 : 28 + (cq - 2) * 13, p1_n = cq < 2 ? 14 : 13;   // row-max pass: 54 chunks of 8
-  const int p2_lo = cq < 2 ? cq * 5 : 10 + (cq - 2) * 4, p2_n = cq < 2 ? 5 : 4;        // exp pass: 18 chunks per part
   const int row = (warp & 3) * 32 + lane;           // row within the tile = TMEM lane
   const float c_log2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32)
-  uint32_t phase_o = 0;
+  uint32_t phase_p[2] = {0, 0};
 
   for (int qt = 0; qt < 4; ++qt) {
     // ---- stage Q tile ----
@@ -201,25 +202,35 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     __syncthreads();
     mx = fmaxf(fmaxf(red_max[0][row], red_max[1][row]), fmaxf(red_max[2][row], red_max[3][row])) * c_log2;
 
-    // ---- pass 2, one third of the keys at a time: P = exp2(s*c - max*c) -> smem, O += P V ----
+    // ---- pass 2 over 6 key parts: P = exp2(s*c - max*c) -> smem buffer (part & 1), O += P V asynchronously ----
     float sum = 0.f;
+#pragma unroll 1
     for (int part = 0; part < PARTS; ++part) {
-      uint8_t* prow = sP + (size_t)(row >> 3) * (PCH * 128) + (row & 7) * 16;
-      float sc[5][8];
+      const int pb = part & 1;
+      const int koff = (part >> 1) * 144 + pb * 80;          // 0, 80, 144, 224, 288, 368
+      const int nch = pb ? 8 : 10;                           // chunks of 8 keys in this part
+      const int c_lo = pb ? cq * 2 : (cq < 2 ? cq * 3 : 6 + (cq - 2) * 2);
+      const int c_n = pb ? 2 : (cq < 2 ? 3 : 2);
+      if (part >= 2) {                                       // the MMAs that read this buffer two parts ago are done
+        mbar_wait(&bar_p[pb], phase_p[pb]);
+        phase_p[pb] ^= 1;
+      }
+      uint8_t* prow = sP + pb * PBUF + (size_t)(row >> 3) * (PCH * 128) + (row & 7) * 16;
+      float sc[3][8];
 #pragma unroll
-      for (int j = 0; j < 5; ++j)
-        if (j < p2_n) tmem_ld8(tmem + lane_addr + part * PK + (p2_lo + j) * 8, sc[j]);
+      for (int j = 0; j < 3; ++j)
+        if (j < c_n) tmem_ld8(tmem + lane_addr + koff + (c_lo + j) * 8, sc[j]);
       tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 5; ++j) {
-        if (j < p2_n) {
+      for (int j = 0; j < 3; ++j) {
+        if (j < c_n) {
           float* s = sc[j];
-          const int col0 = part * PK + (p2_lo + j) * 8;
+          const int col0 = koff + (c_lo + j) * 8;
 #pragma unroll
           for (int i = 0; i < 8; ++i) s[i] = (col0 + i) < V ? ex2(fmaf(s[i], c_log2, -mx)) : 0.f;
           sum += ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
           const uint4 hi = pack8(s);
-          const int kc = p2_lo + j;
+          const int kc = c_lo + j;
           *reinterpret_cast<uint4*>(prow + kc * 128) = hi;
           if (SPLIT) *reinterpret_cast<uint4*>(prow + LO + kc * 128) = pack8_residual(s, hi);
         }
@@ -229,10 +240,11 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
       __syncthreads();
       if (tid == 0) {
         tc_fence_after();
-        const uint32_t p0 = smem_u32(sP), v0 = smem_u32(sVT) + part * (PCH * 128);
+        const uint32_t p0 = smem_u32(sP) + pb * PBUF, v0 = smem_u32(sVT) + (koff / 8) * 128;
         const uint32_t io = idesc_bf16(QT, DK);
+        const int ksteps = nch / 2;
 #pragma unroll 1
-        for (int ks = 0; ks < PK / 16; ++ks) {
+        for (int ks = 0; ks < ksteps; ++ks) {
           const uint32_t acc = (part | ks) != 0;
           const uint64_t pd = smem_desc(p0 + ks * 256, 128, PCH * 128), vd = smem_desc(v0 + ks * 256, 128, KCH * 128);
           if (SPLIT) {
@@ -243,12 +255,15 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
             mma_bf16(tmem_o, pd, vd, io, acc);
           }
         }
-        mma_commit(&bar_o);
+        mma_commit(&bar_p[pb]);
       }
-      mbar_wait(&bar_o, phase_o);     // P buffer free again / O complete
-      phase_o ^= 1;
-      tc_fence_after();
     }
+    // both P buffers' last MMAs (parts 4, 5) complete => O is final
+    mbar_wait(&bar_p[0], phase_p[0]);
+    phase_p[0] ^= 1;
+    mbar_wait(&bar_p[1], phase_p[1]);
+    phase_p[1] ^= 1;
+    tc_fence_after();
     red_sum[cq][row] = sum;
     __syncthreads();
     // ---- O tile out: thread = (row, 8-column quarter) ----
