@@ -13,6 +13,8 @@ constexpr int NJ = GATOR_SMPL_JOINTS;   // 24
 constexpr int KB = GATOR_SMPL_K;        // 220
 constexpr int NV = GATOR_V_FULL;        // 6890
 constexpr int NV3 = NV * 3;             // 20670
+constexpr int VP_LD = 20672;            // row stride of the v_posed workspace: a multiple of 4 floats, so the GEMM epilogue
+                                        // stores 16-byte vectors (20670 would force 4-byte stores)
 
 __global__ void smpl_flags_kernel(const float* __restrict__ betas, int nb, const float* __restrict__ trans, int nt,
                                   int* __restrict__ flags) {
@@ -191,10 +193,10 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
   if (nvw == 0) return;
   const int seg2 = nvw * 3 / 2;                            // float2 per segment (nvw*3 is even: 96 or 42)
   float* st = stage[warp];
-  auto seg_ptr = [&](const float* base, int s) { return base + (size_t)(s_begin + s) * NV3 + (size_t)v0w * 3; };
+  auto seg_ptr = [&](const float* base, int s, int ld) { return base + (size_t)(s_begin + s) * ld + (size_t)v0w * 3; };
   float2 pre0 = make_float2(0.f, 0.f), pre1 = pre0;
   {
-    const float2* src = reinterpret_cast<const float2*>(seg_ptr(vposed, 0));
+    const float2* src = reinterpret_cast<const float2*>(seg_ptr(vposed, 0, VP_LD));
     if (lane < seg2) pre0 = src[lane];
     if (lane + 32 < seg2) pre1 = src[lane + 32];
   }
@@ -203,7 +205,7 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
     reinterpret_cast<float2*>(st)[lane] = pre0;
     if (lane < 16) reinterpret_cast<float2*>(st)[lane + 32] = pre1;
     if (s + 1 < ns) {
-      const float2* src = reinterpret_cast<const float2*>(seg_ptr(vposed, s + 1));
+      const float2* src = reinterpret_cast<const float2*>(seg_ptr(vposed, s + 1, VP_LD));
       if (lane < seg2) pre0 = src[lane];
       if (lane + 32 < seg2) pre1 = src[lane + 32];
     }
@@ -236,13 +238,13 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
     __syncwarp();                                          // everyone has read its inputs from `st`
     if (active) { st[lane * 3] = o0; st[lane * 3 + 1] = o1; st[lane * 3 + 2] = o2; }
     __syncwarp();
-    float2* dst = reinterpret_cast<float2*>(const_cast<float*>(seg_ptr(verts, s)));
+    float2* dst = reinterpret_cast<float2*>(const_cast<float*>(seg_ptr(verts, s, NV3)));
     if (lane < seg2) dst[lane] = reinterpret_cast<const float2*>(st)[lane];
     if (lane + 32 < seg2) dst[lane + 32] = reinterpret_cast<const float2*>(st)[lane + 32];
   }
 }
 
-constexpr int kChunk = 512;
+constexpr int kChunk = 1024;
 
 struct Ws {
   float *aop, *amat, *offset, *vposed;
@@ -258,7 +260,7 @@ Ws carve(char* base, int nb) {
   w.aop = reinterpret_cast<float*>(take((size_t)nb * KB * 4));
   w.amat = reinterpret_cast<float*>(take((size_t)nb * NJ * 12 * 4));
   w.offset = reinterpret_cast<float*>(take((size_t)nb * 3 * 4));
-  w.vposed = reinterpret_cast<float*>(take((size_t)nb * NV3 * 4));
+  w.vposed = reinterpret_cast<float*>(take((size_t)nb * VP_LD * 4));
   w.bytes = off;
   return w;
 }
@@ -320,7 +322,7 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     GATOR_TRY(check_launch("smpl_pose"));
     Epilogue e;
     e.bias = a->v_template;
-    GATOR_TRY(gemm(a->precision, w.aop, KB, a->blend_w, KB, PackedW{a->blend_w_bf16, a->blend_w_bf16_lo}, w.vposed, NV3, nb, NV3, KB, e, stream));
+    GATOR_TRY(gemm(a->precision, w.aop, KB, a->blend_w, KB, PackedW{a->blend_w_bf16, a->blend_w_bf16_lo}, w.vposed, VP_LD, nb, NV3, KB, e, stream));
     dim3 grid(ceil_div(NV, SK_VT), ceil_div(nb, SK_SG));
     smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w,
                                                  a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb);

@@ -215,12 +215,12 @@ def test_smpl_layer_matches_reference_golden():
 
 def test_smpl_layer_zero_norm_switches_and_chunks():
     """smpl_layer.py:87,148: all-zero betas fall back to th_betas; all-zero trans enables centring.
-    B=600 crosses the 512-sample workspace chunk."""
+    B=1100 crosses the 1024-sample workspace chunk."""
     buf = {k: torch.from_numpy(v) for k, v in synthetic.smpl_buffers().items()}
     buf['th_betas'] = torch.full((1, 10), 0.3)
     from gator_b200.smpl_layer import SMPL_Layer
     layer = SMPL_Layer.from_buffers(buf, synthetic.SMPL_PARENTS, center_idx=3).eval().to(DEV)
-    pose, betas, trans = [torch.from_numpy(a) for a in synthetic.smpl_inputs(600)]
+    pose, betas, trans = [torch.from_numpy(a) for a in synthetic.smpl_inputs(1100)]
     for bt, tr in ((betas, trans), (torch.zeros_like(betas), trans), (betas, torch.zeros_like(trans)), (betas, None)):
         rv, rj, _ = orc.smpl_forward(buf, synthetic.SMPL_PARENTS, pose, bt, tr, center_idx=3)
         args = [pose.to(DEV), bt.to(DEV)] + ([tr.to(DEV)] if tr is not None else [])
