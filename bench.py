@@ -299,7 +299,9 @@ def run_b200(args):
                                'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': ch_tf / peaks['bf16_tflops'],
                                'launch_ms': ch_ms, 'flops_per_launch': ch_flop})
         roofline = dict(kernels[0])
-        roofline.update({'traffic': None, 'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)',
+        # dram__bytes_read.sum + dram__bytes_write.sum of one 592-CTA launch from the committed `ncu --set full` capture
+        # (profiles/r01_ncu_full_mdr_chain_kernel.csv; ncu flushes caches, so this is an upper bound of a warm launch)
+        roofline.update({'traffic': 52.9e6 if pcode != 0 else None, 'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)',
                          'note': 'algorithmic flops (2*MAC of the layer\'s 14 64x64 products + cross-attention, or of QK^T + PV) per launch of '
                                  '148 samples; the 3-term split issues 3x that many tensor-core MACs, which are not counted; both kernels are '
                                  'bound by CUDA-core softmax/GELU/LayerNorm/operand-conversion work and MMA round-trip latency, not by the tensor pipe',
