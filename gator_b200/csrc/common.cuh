@@ -27,6 +27,16 @@ int check_launch(const char* what);   // cudaGetLastError -> status
     if (_st != GATOR_OK) return _st;                   \
   } while (0)
 
+// cudaFuncSetAttribute is per device: returns true the first time it is called for the current device with this
+// flag word (one static uint64_t per call site; devices 0..63), so each kernel's attributes are set once per GPU.
+static inline bool first_use_on_device(unsigned long long* seen) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const unsigned long long bit = 1ull << (dev & 63);
+  const unsigned long long old = __atomic_fetch_or(seen, bit, __ATOMIC_RELAXED);
+  return (old & bit) == 0;
+}
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

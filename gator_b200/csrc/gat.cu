@@ -252,11 +252,10 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
   float* h = o + rows_max * 128;
   float* g = h + rows_max * 256;
 
-  static bool attr_done = false;
+  static unsigned long long attr_seen = 0;
   const int attn_smem = J * (3 * C + 1) * (int)sizeof(float);
-  if (!attr_done) {
+  if (first_use_on_device(&attr_seen)) {
     cudaFuncSetAttribute(gat_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXJ * (3 * C + 1) * (int)sizeof(float));
-    attr_done = true;
   }
 
   for (int b0 = 0; b0 < B; b0 += cb) {

@@ -379,10 +379,9 @@ namespace gator {
 namespace {
 int launch_self_attn(const float* qkv, float* out, int nb, cudaStream_t stream) {
   constexpr int sa_smem = 2 * SA_VPAD * DK * (int)sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_seen = 0;
+  if (first_use_on_device(&attr_seen)) {
     cudaFuncSetAttribute(mdr_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sa_smem);
-    attr_done = true;
   }
   mdr_self_attn_kernel<<<nb * 2, SA_THREADS, sa_smem, stream>>>(qkv, out);
   return check_launch("mdr_self_attn");

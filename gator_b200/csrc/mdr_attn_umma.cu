@@ -288,11 +288,10 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
 }  // namespace
 
 int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_seen = 0;
+  if (first_use_on_device(&attr_seen)) {
     cudaFuncSetAttribute(mdr_self_attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(false));
     cudaFuncSetAttribute(mdr_self_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true));
-    attr_done = true;
   }
   if (split) mdr_self_attn_umma_kernel<true><<<nb * 2, NT, smem_bytes(true), stream>>>(qkv, out);
   else mdr_self_attn_umma_kernel<false><<<nb * 2, NT, smem_bytes(false), stream>>>(qkv, out);

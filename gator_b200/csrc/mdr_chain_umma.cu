@@ -366,13 +366,12 @@ mdr_chain_kernel(ChainParams p) {
 // x_in / att_in / kv / outputs as in ChainParams; prm = 11 device pointers (so_b of the PREVIOUS layer first).
 int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
                      float* x3_out, float* qkv_out, float* hd_out, int nb, int J, bool split, cudaStream_t stream) {
-  static bool attr_done = false;
-  if (!attr_done) {
+  static unsigned long long attr_seen = 0;
+  if (first_use_on_device(&attr_seen)) {
     cudaFuncSetAttribute(mdr_chain_kernel<1, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, 17));
     cudaFuncSetAttribute(mdr_chain_kernel<1, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, 19));
     cudaFuncSetAttribute(mdr_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
     cudaFuncSetAttribute(mdr_chain_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2, MAXJ));
-    attr_done = true;
   }
   ChainParams p;
   p.x_in = x_in; p.att_in = att_in; p.kv = kv; p.blob = static_cast<const uint8_t*>(blob);

@@ -126,10 +126,9 @@ extern "C" int gator_csr_spmm(const gator_csr_args* a, void* stream) {
     const int per_sample = a->cols * 12;
     int NS = 96 * 1024 / per_sample;                 // <= 96 KB of staged inputs per CTA (2 CTAs / SM)
     NS = NS > 8 ? 8 : NS;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static unsigned long long attr_seen = 0;
+    if (first_use_on_device(&attr_seen)) {
       cudaFuncSetAttribute(csr_spmm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      attr_done = true;
     }
     csr_spmm3_kernel<<<ceil_div(a->batch, NS), 256, (size_t)NS * per_sample, (cudaStream_t)stream>>>(
         a->rowptr, a->colidx, a->values, a->x, a->y, a->rows, a->cols, a->scale, a->batch, NS);

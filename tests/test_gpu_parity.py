@@ -295,3 +295,40 @@ def test_host_pipeline_matches_plain_forward(models):
     hm, hp = pipe.forward(x)
     torch.cuda.synchronize()
     assert torch.equal(hm, mesh.cpu()) and torch.equal(hp, p3.cpu())
+
+
+def test_config5_shard_size_tensor_path(models):
+    """BASELINE config 5 per-GPU shard (65536 / 8 = 8192 samples) on the tensor-core path: crosses the GAT pass,
+    MDR chunk (1184) and super-chunk boundaries; every sample equals its own batch-1 forward bit for bit."""
+    m = models['coco'].set_precision('bf16x3')
+    try:
+        base = golden('fixtures')['demo_pose19']
+        x = torch.from_numpy(synthetic.coco_poses2d(base, 8192 + 37, seed=4)).to(DEV)
+        mesh, p3 = m(x)
+        assert torch.isfinite(mesh).all() and torch.isfinite(p3).all()
+        for i in (0, 5, 6, 1183, 1184, 8191, 8192, 8228):
+            mi, pi = m(x[i:i + 1])
+            assert torch.equal(mi[0], mesh[i]) and torch.equal(pi[0], p3[i]), i
+    finally:
+        m.set_precision('fp32')
+
+
+def test_cuda_graph_capture(models):
+    """No call synchronises the host: a whole forward is capturable and replays to the same result."""
+    m = models['h36m'].set_precision('bf16x3')
+    try:
+        x = torch.from_numpy(synthetic.poses2d(3, 17, seed=2)).to(DEV)
+        ref, _ = m(x)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            m(x)
+        torch.cuda.current_stream().wait_stream(side)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out, _ = m(x)
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, ref)
+    finally:
+        m.set_precision('fp32')
