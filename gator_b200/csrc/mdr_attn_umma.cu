@@ -5,7 +5,7 @@
 //   S = Q K^T      -> TMEM columns [0,432)   (MMAs of N = 224 / 208, K = 32)
 //   row max        -> 512 threads, thread = (row, column quarter); the whole key range of a row sits in TMEM,
 //                     so it is a plain two-pass softmax - no online rescaling
-//   for each of 6 key parts (80 / 64 keys): P = exp2(.) as bf16 -> one of two smem buffers (A operand), O += P V;
+//   for each of 5 key parts (4 x 96 + 48 keys): P = exp2(.) as bf16 -> one of two smem buffers (A operand), O += P V;
 //                     the exp pass of the next part runs while the tensor core consumes the previous one
 //   O (TMEM columns [432,464)) scaled by 1/rowsum on the way out.
 // SPLIT mode (GATOR_PREC_BF16X3) carries bf16 residuals of Q, K, V and P as well and issues the 3-term
@@ -26,8 +26,8 @@ constexpr int E = 64;
 constexpr int QT = 128;             // query rows per tile
 constexpr int KCH = VP / 8;         // 54 key chunks
 constexpr int N0 = 224, N1 = 208;   // S = two MMAs (N <= 256, multiple of 16)
-constexpr int PARTS = 6;            // key parts of 80 / 64 keys alternately (5 / 4 k-steps of 16); P is double-buffered so the
-constexpr int PCH = 10;             // exp pass of part p+1 overlaps the P V MMAs of part p.  PCH = chunks per P buffer row group
+constexpr int PARTS = 5;            // key parts of 96, 96, 96, 96, 48 keys (12 / 6 chunks of 8: 3 or 3|1 per thread - balanced);
+constexpr int PCH = 12;             // P is double-buffered so the exp pass of part p+1 overlaps the P V MMAs of part p
 
 constexpr int SK_BYTES = VP * DK * 2;        // 27 648  K   [kg 54][kc 4][8][8]
 constexpr int SVT_BYTES = DK * VP * 2;       // 27 648  V^T [dg 4][kc 54][8][8]
@@ -89,32 +89,56 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     mbar_init_fence();
   }
   // ---- stage K: chunk c = (kg, kc, r) -> key = kg*8 + r, d = kc*8 ----
-  for (int c = tid; c < VP * 4; c += NT) {
-    const int r = c & 7, kc = (c >> 3) & 3, kg = c >> 5;
-    const int key = kg * 8 + r;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
-    if (key < V) {
-      const float* src = base + (size_t)key * 3 * E + E + h * DK + kc * 8;
-      a = *reinterpret_cast<const float4*>(src);
-      bb = *reinterpret_cast<const float4*>(src + 4);
+  {
+    // all global loads of this thread are issued before the first conversion (4 chunks x 2 x 16 B in flight)
+    constexpr int NCH = (VP * 4 + NT - 1) / NT;
+    float4 ka[NCH], kb2[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = tid + i * NT;
+      const int r = c & 7, kc = (c >> 3) & 3, kg = c >> 5;
+      const int key = kg * 8 + r;
+      ka[i] = kb2[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < VP * 4 && key < V) {
+        const float* src = base + (size_t)key * 3 * E + E + h * DK + kc * 8;
+        ka[i] = *reinterpret_cast<const float4*>(src);
+        kb2[i] = *reinterpret_cast<const float4*>(src + 4);
+      }
     }
-    const uint4 hi = cvt8(a, bb);
-    reinterpret_cast<uint4*>(sK)[c] = hi;
-    if (SPLIT) reinterpret_cast<uint4*>(sK + LO)[c] = cvt8_residual(a, bb, hi);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = tid + i * NT;
+      if (c < VP * 4) {
+        const uint4 hi = cvt8(ka[i], kb2[i]);
+        reinterpret_cast<uint4*>(sK)[c] = hi;
+        if (SPLIT) reinterpret_cast<uint4*>(sK + LO)[c] = cvt8_residual(ka[i], kb2[i], hi);
+      }
+    }
   }
   // ---- stage V^T: warp takes a group of 8 keys, lane = d; chunk (dg, kc, r): d = dg*8 + r ----
-  for (int kc = warp; kc < KCH; kc += NT / 32) {
-    float v[8];
+  {
+    constexpr int NG = (KCH + NT / 32 - 1) / (NT / 32);   // key groups per warp (4)
+    float vv[NG][8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int key = kc * 8 + i;
-      v[i] = key < V ? base[(size_t)key * 3 * E + 2 * E + h * DK + lane] : 0.f;
+    for (int g = 0; g < NG; ++g) {
+      const int kc = warp + g * (NT / 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = kc * 8 + i;
+        vv[g][i] = (kc < KCH && key < V) ? base[(size_t)key * 3 * E + 2 * E + h * DK + lane] : 0.f;
+      }
     }
     const int dg = lane >> 3, r = lane & 7;
-    const size_t off = (size_t)dg * (KCH * 128) + kc * 128 + r * 16;
-    const uint4 hi = pack8(v);
-    *reinterpret_cast<uint4*>(sVT + off) = hi;
-    if (SPLIT) *reinterpret_cast<uint4*>(sVT + LO + off) = pack8_residual(v, hi);
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const int kc = warp + g * (NT / 32);
+      if (kc < KCH) {
+        const size_t off = (size_t)dg * (KCH * 128) + kc * 128 + r * 16;
+        const uint4 hi = pack8(vv[g]);
+        *reinterpret_cast<uint4*>(sVT + off) = hi;
+        if (SPLIT) *reinterpret_cast<uint4*>(sVT + LO + off) = pack8_residual(vv[g], hi);
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -127,21 +151,27 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   const int row = (warp & 3) * 32 + lane;           // row within the tile = TMEM lane
   const float c_log2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32)
   uint32_t phase_p[2] = {0, 0};
+  // Q tile staging: QT*4 = 512 chunks = one per thread; the next tile's chunk is prefetched into registers
+  float4 qa, qb;
+  auto load_q = [&](int qt) {
+    const int r = tid & 7, kc = (tid >> 3) & 3, rg = tid >> 5;
+    const int q = qt * QT + rg * 8 + r;
+    qa = qb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < V) {
+      const float* src = base + (size_t)q * 3 * E + h * DK + kc * 8;
+      qa = *reinterpret_cast<const float4*>(src);
+      qb = *reinterpret_cast<const float4*>(src + 4);
+    }
+  };
+  load_q(0);
 
   for (int qt = 0; qt < 4; ++qt) {
     // ---- stage Q tile ----
-    for (int c = tid; c < QT * 4; c += NT) {
-      const int r = c & 7, kc = (c >> 3) & 3, rg = c >> 5;
-      const int q = qt * QT + rg * 8 + r;
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), bb = a;
-      if (q < V) {
-        const float* src = base + (size_t)q * 3 * E + h * DK + kc * 8;
-        a = *reinterpret_cast<const float4*>(src);
-        bb = *reinterpret_cast<const float4*>(src + 4);
-      }
-      const uint4 hi = cvt8(a, bb);
-      reinterpret_cast<uint4*>(sQ)[c] = hi;
-      if (SPLIT) reinterpret_cast<uint4*>(sQ + LO)[c] = cvt8_residual(a, bb, hi);
+    {
+      const uint4 hi = cvt8(qa, qb);
+      reinterpret_cast<uint4*>(sQ)[tid] = hi;
+      if (SPLIT) reinterpret_cast<uint4*>(sQ + LO)[tid] = cvt8_residual(qa, qb, hi);
+      if (qt + 1 < 4) load_q(qt + 1);
     }
     fence_proxy_async();
     tc_fence_before();
@@ -207,10 +237,10 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
 #pragma unroll 1
     for (int part = 0; part < PARTS; ++part) {
       const int pb = part & 1;
-      const int koff = (part >> 1) * 144 + pb * 80;          // 0, 80, 144, 224, 288, 368
-      const int nch = pb ? 8 : 10;                           // chunks of 8 keys in this part
-      const int c_lo = pb ? cq * 2 : (cq < 2 ? cq * 3 : 6 + (cq - 2) * 2);
-      const int c_n = pb ? 2 : (cq < 2 ? 3 : 2);
+      const int koff = part * 96;                            // 0, 96, 192, 288, 384
+      const int nch = part < 4 ? 12 : 6;                     // chunks of 8 keys in this part
+      const int c_lo = part < 4 ? cq * 3 : (cq < 2 ? cq * 2 : 4 + (cq - 2));
+      const int c_n = part < 4 ? 3 : (cq < 2 ? 2 : 1);
       if (part >= 2) {                                       // the MMAs that read this buffer two parts ago are done
         mbar_wait(&bar_p[pb], phase_p[pb]);
         phase_p[pb] ^= 1;
@@ -258,7 +288,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
         mma_commit(&bar_p[pb]);
       }
     }
-    // both P buffers' last MMAs (parts 4, 5) complete => O is final
+    // both P buffers' last MMAs (parts 3, 4) complete => O is final
     mbar_wait(&bar_p[0], phase_p[0]);
     phase_p[0] ^= 1;
     mbar_wait(&bar_p[1], phase_p[1]);
