@@ -165,44 +165,53 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   };
   load_q(0);
 
-  for (int qt = 0; qt < 4; ++qt) {
-    // ---- stage Q tile ----
-    {
-      const uint4 hi = cvt8(qa, qb);
-      reinterpret_cast<uint4*>(sQ)[tid] = hi;
-      if (SPLIT) reinterpret_cast<uint4*>(sQ + LO)[tid] = cvt8_residual(qa, qb, hi);
-      if (qt + 1 < 4) load_q(qt + 1);
-    }
+  auto stage_q = [&]() {          // registers (prefetched) -> sQ images
+    const uint4 hi = cvt8(qa, qb);
+    reinterpret_cast<uint4*>(sQ)[tid] = hi;
+    if (SPLIT) reinterpret_cast<uint4*>(sQ + LO)[tid] = cvt8_residual(qa, qb, hi);
     fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK);
-      const uint32_t i0 = idesc_bf16(QT, N0), i1 = idesc_bf16(QT, N1);
-      const uint32_t kofs = (N0 / 8) * 512;
+  };
+  auto issue_s = [&]() {          // one thread: S = Q K^T into TMEM columns [0, 432), commit -> bar_s
+    const uint32_t q0 = smem_u32(sQ), k0 = smem_u32(sK);
+    const uint32_t i0 = idesc_bf16(QT, N0), i1 = idesc_bf16(QT, N1);
+    const uint32_t kofs = (N0 / 8) * 512;
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        const uint64_t ad = smem_desc(q0 + ks * 256, 128, 512);
-        const uint64_t b0d = smem_desc(k0 + ks * 256, 128, 512), b1d = smem_desc(k0 + kofs + ks * 256, 128, 512);
-        if (SPLIT) {
-          const uint64_t adl = smem_desc(q0 + LO + ks * 256, 128, 512);
-          const uint64_t b0l = smem_desc(k0 + LO + ks * 256, 128, 512), b1l = smem_desc(k0 + LO + kofs + ks * 256, 128, 512);
-          mma_bf16(tmem, adl, b0d, i0, ks);
-          mma_bf16(tmem, ad, b0l, i0, 1);
-          mma_bf16(tmem, ad, b0d, i0, 1);
-          mma_bf16(tmem + N0, adl, b1d, i1, ks);
-          mma_bf16(tmem + N0, ad, b1l, i1, 1);
-          mma_bf16(tmem + N0, ad, b1d, i1, 1);
-        } else {
-          mma_bf16(tmem, ad, b0d, i0, ks);
-          mma_bf16(tmem + N0, ad, b1d, i1, ks);
-        }
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint64_t ad = smem_desc(q0 + ks * 256, 128, 512);
+      const uint64_t b0d = smem_desc(k0 + ks * 256, 128, 512), b1d = smem_desc(k0 + kofs + ks * 256, 128, 512);
+      if (SPLIT) {
+        const uint64_t adl = smem_desc(q0 + LO + ks * 256, 128, 512);
+        const uint64_t b0l = smem_desc(k0 + LO + ks * 256, 128, 512), b1l = smem_desc(k0 + LO + kofs + ks * 256, 128, 512);
+        mma_bf16(tmem, adl, b0d, i0, ks);
+        mma_bf16(tmem, ad, b0l, i0, 1);
+        mma_bf16(tmem, ad, b0d, i0, 1);
+        mma_bf16(tmem + N0, adl, b1d, i1, ks);
+        mma_bf16(tmem + N0, ad, b1l, i1, 1);
+        mma_bf16(tmem + N0, ad, b1d, i1, 1);
+      } else {
+        mma_bf16(tmem, ad, b0d, i0, ks);
+        mma_bf16(tmem + N0, ad, b1d, i1, ks);
       }
-      mma_commit(&bar_s);
     }
+    mma_commit(&bar_s);
+  };
+  // prologue: S of tile 0
+  stage_q();
+  load_q(1);
+  tc_fence_before();
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    issue_s();
+  }
+
+  for (int qt = 0; qt < 4; ++qt) {
     mbar_wait(&bar_s, qt & 1);
     tc_fence_after();
+    if (qt + 1 < 4) {             // S(qt) is complete, so sQ is free: stage the next tile now; its S MMA is issued at the
+      stage_q();                  // end of this tile's exp pass and overlaps the last P V MMAs and the O write-out
+      if (qt + 2 < 4) load_q(qt + 2);
+    }
 
     // ---- pass 1: row max over this thread's 216 columns ----
     float mx = -INFINITY;
@@ -286,6 +295,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
           }
         }
         mma_commit(&bar_p[pb]);
+        if (part == PARTS - 1 && qt + 1 < 4) issue_s();    // every thread has finished reading S(qt) (barrier above)
       }
     }
     // both P buffers' last MMAs (parts 3, 4) complete => O is final
