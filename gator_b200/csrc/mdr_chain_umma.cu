@@ -140,7 +140,12 @@ mdr_chain_kernel(ChainParams p) {
   }
   const int first_unit = p.att_in ? U_SO : U_Q;   // (the FINAL pass needs att_in: unit 0 = linears[3], unit 1 = head)
   prefetch_w(first_unit, 0);
-  for (int i = tid; i < J * 128; i += NT) skv[i] = p.kv[(size_t)b * J * 128 + i];
+  {   // K|V of the sample: asynchronous 16-byte copies, completed by the cp.async wait of the first unit
+    const float* src = p.kv + (size_t)b * J * 128;
+    const uint32_t dst = smem_u32(skv);
+    for (int i = tid; i < J * 32; i += NT) cp_async16(dst + i * 16, src + i * 4);
+    cp_async_commit();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
