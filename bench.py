@@ -199,7 +199,7 @@ def run_b200(args):
 
     # ---- end to end: pinned host input -> H2D -> forward -> mesh + pose3d D2H ----
     from gator_b200.pipeline import HostPipeline
-    pipe = HostPipeline(model, B, slices=8)          # public host-to-host API: sliced forward, D2H overlapped
+    pipe = HostPipeline(model, B)                    # public host-to-host API: sliced decoder, D2H overlapped
     mesh_host, p3_host = pipe.mesh_host, pipe.pose3d_host
     with torch.no_grad():
         def e2e_step():

@@ -10,12 +10,13 @@ import torch
 class HostPipeline:
     """forward(pose2d_host (B,J,2) pinned) -> (mesh_host (B,6890,3), pose3d_host (B,J,3)) pinned, both fp32."""
 
-    def __init__(self, model, batch: int, slices: int = 4):
+    def __init__(self, model, batch: int, slice_samples: int = 0):
+        """slice_samples = 0: one MDR workspace chunk per slice (1184 samples on the tensor-core path)."""
         p = next(model.parameters())
         self.model, self.dev = model, p.device
         self.J = model.num_joint
         self.batch = batch
-        self.slices = max(1, min(slices, batch))
+        self.slice_samples = slice_samples
         self.copy_stream = torch.cuda.Stream(device=self.dev)
         self.mesh_host = torch.empty((batch, 6890, 3), dtype=torch.float32).pin_memory()
         self.pose3d_host = torch.empty((batch, self.J, 3), dtype=torch.float32).pin_memory()
@@ -27,20 +28,29 @@ class HostPipeline:
         if B != self.batch:
             raise ValueError(f'pipeline was built for batch {self.batch}, got {B}')
         main = torch.cuda.current_stream(self.dev)
-        step = (B + self.slices - 1) // self.slices
+        m = self.model
+        step = self.slice_samples or m.pose2mesh._chunk()
         self._keep.clear()
+        # the lifter runs once over the whole batch (its outputs are small: 12 J + 512 J bytes per sample) ...
+        xd = pose2d_host.to(self.dev, non_blocking=True)
+        p3, feat = m.pose_lifter(xd.reshape(B, self.J * 2))
+        p3 = p3.reshape(B, self.J, 3)
+        done = torch.cuda.Event()
+        done.record(main)
+        self.copy_stream.wait_event(done)
+        with torch.cuda.stream(self.copy_stream):
+            self.pose3d_host.copy_(p3, non_blocking=True)
+        p3.record_stream(self.copy_stream)
+        # ... the decoder slice by slice, each slice's 83 KB/mesh copy overlapping the next slice's kernels
         for lo in range(0, B, step):
             hi = min(B, lo + step)
-            xd = pose2d_host[lo:hi].to(self.dev, non_blocking=True)
-            mesh, p3 = self.model(xd)
+            mesh = m.pose2mesh.forward_parts(xd[lo:hi], p3[lo:hi], feat[lo:hi])
             done = torch.cuda.Event()
             done.record(main)
             self.copy_stream.wait_event(done)
             with torch.cuda.stream(self.copy_stream):
                 self.mesh_host[lo:hi].copy_(mesh, non_blocking=True)
-                self.pose3d_host[lo:hi].copy_(p3, non_blocking=True)
             mesh.record_stream(self.copy_stream)
-            p3.record_stream(self.copy_stream)
-            self._keep.append((mesh, p3))
+            self._keep.append(mesh)
         main.wait_stream(self.copy_stream)
         return self.mesh_host, self.pose3d_host

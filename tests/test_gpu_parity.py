@@ -291,7 +291,7 @@ def test_host_pipeline_matches_plain_forward(models):
     m = models['h36m']
     x = torch.from_numpy(synthetic.poses2d(37, 17, seed=9)).pin_memory()
     mesh, p3 = m(x.to(DEV))
-    pipe = HostPipeline(m, 37, slices=4)
+    pipe = HostPipeline(m, 37, slice_samples=10)
     hm, hp = pipe.forward(x)
     torch.cuda.synchronize()
     assert torch.equal(hm, mesh.cpu()) and torch.equal(hp, p3.cpu())
