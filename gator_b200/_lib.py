@@ -65,12 +65,31 @@ class GemmArgs(C.Structure):
                 ('R', C.c_void_p), ('C', C.c_void_p)]
 
 
-_STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs]
+class EvalArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('verts', C.c_int32), ('joints', C.c_int32), ('n_eval', C.c_int32),
+                ('root', C.c_int32), ('scale', C.c_float),
+                ('jreg_rowptr', C.c_void_p), ('jreg_colidx', C.c_void_p), ('jreg_values', C.c_void_p),
+                ('eval_joints', C.c_void_p), ('pred_mesh', C.c_void_p), ('gt_mesh', C.c_void_p),
+                ('gt_joints', C.c_void_p), ('pred_joints_in', C.c_void_p), ('pred_joints', C.c_void_p),
+                ('joint_err', C.c_void_p), ('surface_err', C.c_void_p), ('pa_joint_err', C.c_void_p),
+                ('batch_mean', C.c_void_p)]
+
+
+class Pose2dArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('joints_in', C.c_int32), ('in_stride', C.c_int32), ('n_mid', C.c_int32),
+                ('mid_a', C.c_int32 * 2), ('mid_b', C.c_int32 * 2),
+                ('out_w', C.c_float), ('out_h', C.c_float), ('aspect', C.c_float), ('bbox_scale', C.c_float),
+                ('joints', C.c_void_p), ('pose2d', C.c_void_p), ('joint_img', C.c_void_p), ('bbox', C.c_void_p),
+                ('valid', C.c_void_p)]
+
+
+_STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs, EvalArgs, Pose2dArgs]
 EXPORTS = ['gator_abi_version', 'gator_last_error', 'gator_abi_sizeof', 'gator_launch_count',
            'gator_mdr_self_attention', 'gator_mdr_layer_chain', 'gator_umma_weight_layout',
            'gator_gat_slot_name', 'gator_gat_workspace_bytes', 'gator_gat_forward',
            'gator_mdr_slot_name', 'gator_mdr_workspace_bytes', 'gator_mdr_forward',
-           'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_gemm']
+           'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_gemm',
+           'gator_eval_epilogue', 'gator_pose2d_preprocess']
 
 _lock = threading.Lock()
 _lib = None
@@ -102,7 +121,8 @@ def lib():
         L.gator_smpl_workspace_bytes.restype = C.c_size_t
         L.gator_smpl_workspace_bytes.argtypes = [C.c_int32]
         for name, st in (('gator_gat_forward', GatArgs), ('gator_mdr_forward', MdrArgs),
-                         ('gator_smpl_forward', SmplArgs), ('gator_csr_spmm', CsrArgs), ('gator_gemm', GemmArgs)):
+                         ('gator_smpl_forward', SmplArgs), ('gator_csr_spmm', CsrArgs), ('gator_gemm', GemmArgs),
+                         ('gator_eval_epilogue', EvalArgs), ('gator_pose2d_preprocess', Pose2dArgs)):
             getattr(L, name).restype = C.c_int
             getattr(L, name).argtypes = [C.POINTER(st), C.c_void_p]
         L.gator_launch_count.restype = C.c_longlong

@@ -40,6 +40,8 @@ extern "C" size_t gator_abi_sizeof(int which) {
     case 2: return sizeof(gator_smpl_args);
     case 3: return sizeof(gator_csr_args);
     case 4: return sizeof(gator_gemm_args);
+    case 5: return sizeof(gator_eval_args);
+    case 6: return sizeof(gator_pose2d_args);
     default: return 0;
   }
 }

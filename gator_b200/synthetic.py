@@ -272,3 +272,41 @@ def smpl_inputs(batch: int, seed: int = 3):
     betas = r.standard_normal((batch, 10)).astype(np.float32)
     trans = r.standard_normal((batch, 3)).astype(np.float32)
     return pose, betas, trans
+
+
+def eval_inputs(batch: int, regressor: np.ndarray, seed: int = 7):
+    """Inputs of the evaluation epilogue (lib/core/base.py:216-223): predicted / ground-truth meshes in metres
+    and `reg_pose3d` in mm.  gt = template deformed per sample; pred = gt + a per-sample similarity perturbation
+    + N(0, 15 mm) noise, so MPJPE, MPVPE and PA-MPJPE are all different and non-trivial."""
+    r = _rng('eval_inputs', seed)
+    tmpl = mean_vertices()
+    gt = tmpl[None] * (1.0 + 0.1 * r.standard_normal((batch, 1, 3))) + 0.3 * r.standard_normal((batch, 1, 3))
+    ang = 0.15 * r.standard_normal((batch, 3))
+    pred = np.empty_like(gt)
+    for b in range(batch):
+        ax, ay, az = ang[b]
+        Rx = np.array([[1, 0, 0], [0, np.cos(ax), -np.sin(ax)], [0, np.sin(ax), np.cos(ax)]])
+        Ry = np.array([[np.cos(ay), 0, np.sin(ay)], [0, 1, 0], [-np.sin(ay), 0, np.cos(ay)]])
+        Rz = np.array([[np.cos(az), -np.sin(az), 0], [np.sin(az), np.cos(az), 0], [0, 0, 1]])
+        pred[b] = (1.0 + 0.05 * r.standard_normal()) * gt[b] @ (Rz @ Ry @ Rx).T + 0.05 * r.standard_normal(3)
+    pred += 0.015 * r.standard_normal(pred.shape)
+    gt = gt.astype(np.float32)
+    pred = pred.astype(np.float32)
+    gt_pose = (regressor.astype(np.float32) @ (gt * np.float32(1000.0))) + r.standard_normal((batch, len(regressor), 3)).astype(np.float32)
+    return pred, gt, gt_pose.astype(np.float32)
+
+
+def pixel_poses(base17: np.ndarray, batch: int, seed: int = 9) -> np.ndarray:
+    """(batch, 17, 3) float64 detector-style inputs (x, y, confidence) derived from the shipped
+    demo/coco_joint_input.npy: sample 0 is the file itself, then per-sample anisotropic scalings / shifts so that
+    tall boxes (w < ar*h), wide boxes (w > ar*h) and small boxes all occur, plus pixel jitter."""
+    r = _rng('pixel_poses', seed)
+    out = np.repeat(np.asarray(base17, np.float64).reshape(1, 17, -1)[:, :, :3], batch, 0).copy()
+    c = out[0, :, :2].mean(0)
+    for b in range(1, batch):
+        sx, sy = (3.0, 0.4) if b % 3 == 1 else ((0.5, 1.5) if b % 3 == 2 else (0.08, 0.08))
+        sx, sy = sx * (1 + 0.2 * r.random()), sy * (1 + 0.2 * r.random())
+        out[b, :, 0] = (out[b, :, 0] - c[0]) * sx + c[0] + 200 * r.standard_normal()
+        out[b, :, 1] = (out[b, :, 1] - c[1]) * sy + c[1] + 200 * r.standard_normal()
+        out[b, :, :2] += 2.0 * r.standard_normal((17, 2))
+    return out

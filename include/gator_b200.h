@@ -49,7 +49,7 @@ typedef enum {
 int gator_abi_version(void);
 const char* gator_last_error(void);
 /* sizeof() of the ABI structs as compiled, so the ctypes mirror can be verified at load time:
- * which = 0 gat, 1 mdr, 2 smpl, 3 csr, 4 gemm */
+ * which = 0 gat, 1 mdr, 2 smpl, 3 csr, 4 gemm, 5 eval, 6 pose2d */
 size_t gator_abi_sizeof(int which);
 /* number of kernels this library has launched (process-wide); reset != 0 zeroes it after reading.
  * bench.py reports it as `gpu_launches`. */
@@ -267,6 +267,67 @@ typedef struct {
 } gator_csr_args;
 
 int gator_csr_spmm(const gator_csr_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused evaluation epilogue - replaces, per batch, lib/core/base.py:219-223
+ *     pred_mesh, gt_mesh = pred_mesh * 1000, gt_mesh * 1000
+ *     pred_pose = J_regressor[None] @ pred_mesh
+ *     j_err, s_err = val_dataset.compute_both_err(pred_mesh, gt_mesh, pred_pose, gt_pose3d)
+ * with compute_both_err of data/Human36M/dataset.py:466-478 (= data/PW3D/dataset.py:273-286): root-align
+ * meshes and joints on joint `root`, mean L2 over the vertices / over the evaluation joints; and the
+ * per-sample MPJPE / PA-MPJPE of evaluate_joint (dataset.py:480-504, rigid_align lib/coord_utils.py:127-149).
+ * One read of the two meshes, no device->host copy of a mesh.  All per-sample outputs are optional.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch;               /* B                                                       */
+  int32_t verts;               /* 6890                                                    */
+  int32_t joints;              /* rows of the regressor (<= 32)                           */
+  int32_t n_eval;              /* evaluation joints (<= 32)                               */
+  int32_t root;                /* joint both sides are aligned on (0 in both datasets)    */
+  float scale;                 /* 1000.0f: metres -> millimetres applied to both meshes   */
+  const int32_t* jreg_rowptr;  /* CSR J_regressor (joints x verts); unused if pred_joints_in */
+  const int32_t* jreg_colidx;
+  const float* jreg_values;
+  const int32_t* eval_joints;  /* (n_eval) indices into the joint set                     */
+  const float* pred_mesh;      /* (B, verts, 3) before `scale`                            */
+  const float* gt_mesh;        /* (B, verts, 3) before `scale`, or NULL (no surface error) */
+  const float* gt_joints;      /* (B, joints, 3) ALREADY in output units (reg_pose3d, mm) */
+  const float* pred_joints_in; /* (B, joints, 3) in output units: skip the regression, or NULL */
+  float* pred_joints;          /* out (B, joints, 3) = J_regressor @ (pred_mesh*scale), or NULL */
+  float* joint_err;            /* out (B) mean over the eval joints, or NULL              */
+  float* surface_err;          /* out (B) mean over the vertices, or NULL                 */
+  float* pa_joint_err;         /* out (B) joint error after similarity Procrustes, or NULL */
+  float* batch_mean;           /* out (3) batch means of the three arrays above (0 where absent), or NULL */
+} gator_eval_args;
+
+int gator_eval_epilogue(const gator_eval_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 2D-pose pre-processing - replaces the per-sample numpy/cv2 chain in front of every forward:
+ * add_pelvis / add_neck (demo/run.py:103-121), get_bbox + process_bbox (lib/coord_utils.py:21-66),
+ * j2d_processing with rot = 0, flip = 0 (lib/aug_utils.py:51-64,140-184), "-> 0~1" and the per-axis
+ * standardisation (demo/run.py:130-133, data/Human36M/dataset.py:383-389).
+ * A sample whose box process_bbox would reject (returns None) gets NaN outputs and valid[b] = 0.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch;               /* B                                                       */
+  int32_t joints_in;           /* joints per sample in `joints`                           */
+  int32_t in_stride;           /* floats per input joint (2, or 3 with a confidence column) */
+  int32_t n_mid;               /* joints to synthesise as midpoints and append (0..2)     */
+  int32_t mid_a[2];            /* COCO demo: (L_Hip, R_Hip) -> Pelvis, (L_Shoulder, R_Shoulder) -> Neck */
+  int32_t mid_b[2];
+  float out_w;                 /* cfg.MODEL.input_shape[1] (288)                          */
+  float out_h;                 /* cfg.MODEL.input_shape[0] (384)                          */
+  float aspect;                /* process_bbox aspect_ratio = out_w / out_h               */
+  float bbox_scale;            /* process_bbox scale (1.0)                                */
+  const float* joints;         /* (B, joints_in, in_stride) pixel coordinates, x and y first */
+  float* pose2d;               /* out (B, joints_in + n_mid, 2) standardised - the forward's input */
+  float* joint_img;            /* out (B, joints_in + n_mid, 2) crop pixel coordinates, or NULL */
+  float* bbox;                 /* out (B, 4) processed box x, y, w, h, or NULL            */
+  int32_t* valid;              /* out (B), or NULL                                        */
+} gator_pose2d_args;
+
+int gator_pose2d_preprocess(const gator_pose2d_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Building block exported for tests and micro-benchmarks:

@@ -440,3 +440,134 @@ def mpjpe_pa(pred_mesh_m: np.ndarray, gt_mesh_m: np.ndarray, regressor_h36m: np.
         mp.append(np.sqrt(((jp - jg) ** 2).sum(1)).mean())
         pa.append(np.sqrt(((rigid_align(jp, jg) - jg) ** 2).sum(1)).mean())
     return float(np.mean(mp)), float(np.mean(pa))
+
+
+# ----------------------------------------------------------------------------------------------
+# evaluation epilogue - the checker of csrc/eval.cu
+# ----------------------------------------------------------------------------------------------
+def eval_pred_pose(J_regressor: torch.Tensor, pred_mesh_m: torch.Tensor, scale: float = 1000.0) -> torch.Tensor:
+    """lib/core/base.py:219-221: ``pred_mesh * 1000`` then the dense ``J_regressor[None] @ pred_mesh``."""
+    return torch.matmul(J_regressor[None, :, :], pred_mesh_m * scale)
+
+
+def compute_both_err(pred_mesh, target_mesh, pred_joint, target_joint, eval_joints=H36M_EVAL_JOINTS):
+    """data/Human36M/dataset.py:466-478 (= data/PW3D/dataset.py:273-286); all arguments in mm, torch fp32.
+    Returns (joint_mean_error, mesh_mean_error) as numpy float32 scalars, like the reference."""
+    pred_mesh, target_mesh = pred_mesh - pred_joint[:, :1, :], target_mesh - target_joint[:, :1, :]
+    pred_joint, target_joint = pred_joint - pred_joint[:, :1, :], target_joint - target_joint[:, :1, :]
+    pm, tm = pred_mesh.numpy(), target_mesh.numpy()
+    pj, tj = pred_joint.numpy()[:, list(eval_joints), :], target_joint.numpy()[:, list(eval_joints), :]
+    mesh_err = np.sqrt(((pm - tm) ** 2).sum(axis=2)).mean()
+    joint_err = np.sqrt(((pj - tj) ** 2).sum(axis=2)).mean()
+    return joint_err, mesh_err
+
+
+def per_sample_errors(pred_mesh, target_mesh, pred_joint, target_joint, eval_joints=H36M_EVAL_JOINTS):
+    """Per-sample MPJPE / MPVPE / PA-MPJPE in the form evaluate_joint computes them
+    (data/Human36M/dataset.py:480-504): root-align on joint 0, select the eval joints, mean L2, then the same
+    after ``rigid_align``.  numpy arrays in mm; returns three (B,) float64 arrays."""
+    ev = list(eval_joints)
+    mpjpe, mpvpe, pa = [], [], []
+    for n in range(len(pred_joint)):
+        out, gt = pred_joint[n] - pred_joint[n][:1], target_joint[n] - target_joint[n][:1]
+        out, gt = out[ev, :], gt[ev, :]
+        mpjpe.append(np.sqrt(np.sum((out - gt) ** 2, 1)).mean())
+        pa.append(np.sqrt(np.sum((rigid_align(out, gt) - gt) ** 2, 1)).mean())
+        if target_mesh is not None:
+            pm, tm = pred_mesh[n] - pred_joint[n][:1], target_mesh[n] - target_joint[n][:1]
+            mpvpe.append(np.sqrt(np.sum((pm - tm) ** 2, 1)).mean())
+    return np.asarray(mpjpe, np.float64), np.asarray(mpvpe, np.float64), np.asarray(pa, np.float64)
+
+
+# ----------------------------------------------------------------------------------------------
+# 2D-pose pre-processing (SURVEY.md section 8 row f3) - the checker of csrc/preprocess.cu
+# ----------------------------------------------------------------------------------------------
+def add_mid_joint(joint_coord: np.ndarray, a: int, b: int) -> np.ndarray:
+    """demo/run.py:103-121 (add_pelvis / add_neck): midpoint of two joints appended; a third column
+    (confidence) is multiplied instead of averaged."""
+    mid = (joint_coord[a, :] + joint_coord[b, :]) * 0.5
+    if joint_coord.shape[1] > 2:
+        mid[2] = joint_coord[a, 2] * joint_coord[b, 2]
+    return np.concatenate((joint_coord, mid.reshape(1, -1)))
+
+
+def get_bbox(joint_img: np.ndarray) -> np.ndarray:
+    """lib/coord_utils.py:21-39: tight box (x, y, w, h) as float32."""
+    x_img, y_img = joint_img[:, 0], joint_img[:, 1]
+    xmin, ymin, xmax, ymax = min(x_img), min(y_img), max(x_img), max(y_img)
+    x_center = (xmin + xmax) / 2.
+    width = xmax - xmin
+    xmin, xmax = x_center - 0.5 * width, x_center + 0.5 * width
+    y_center = (ymin + ymax) / 2.
+    height = ymax - ymin
+    ymin, ymax = y_center - 0.5 * height, y_center + 0.5 * height
+    return np.array([xmin, ymin, xmax - xmin, ymax - ymin]).astype(np.float32)
+
+
+def process_bbox(bbox: np.ndarray, aspect_ratio: float, scale: float = 1.0):
+    """lib/coord_utils.py:42-66: sanitise, then grow to the aspect ratio about the centre (float32 arithmetic
+    because `bbox` is float32 and Python scalars are weak)."""
+    x, y, w, h = bbox
+    x1, y1, x2, y2 = x, y, x + (w - 1), y + (h - 1)
+    if w * h > 0 and x2 >= x1 and y2 >= y1:
+        bbox = np.array([x1, y1, x2 - x1, y2 - y1])
+    else:
+        return None
+    w, h = bbox[2], bbox[3]
+    c_x, c_y = bbox[0] + w / 2., bbox[1] + h / 2.
+    if w > aspect_ratio * h:
+        h = w / aspect_ratio
+    elif w < aspect_ratio * h:
+        w = h * aspect_ratio
+    bbox[2], bbox[3] = w * scale, h * scale
+    bbox[0], bbox[1] = c_x - bbox[2] / 2., c_y - bbox[3] / 2.
+    return bbox
+
+
+def crop_affine(bbox: np.ndarray, res) -> np.ndarray:
+    """j2d_processing's transform for rot = 0 (lib/aug_utils.py:51-57, get_center_scale coord_utils.py:7-18,
+    get_affine_transform aug_utils.py:140-172): three float32 point pairs, solved in float64 like
+    cv2.getAffineTransform."""
+    x, y, w, h = bbox
+    center = np.zeros(2, np.float32)
+    center[0], center[1] = x + w * 0.5, y + h * 0.5
+    scale = np.array([w * 1.0, h * 1.0], np.float32)
+    src_w, dst_w, dst_h = scale[0], res[0], res[1]
+    src_dir = [0.0, np.float64(src_w * -0.5)]
+    dst_dir = np.array([0, dst_w * -0.5], np.float32)
+    src, dst = np.zeros((3, 2), np.float32), np.zeros((3, 2), np.float32)
+    src[0, :] = center
+    src[1, :] = center + src_dir
+    dst[0, :] = [dst_w * 0.5, dst_h * 0.5]
+    dst[1, :] = np.array([dst_w * 0.5, dst_h * 0.5]) + dst_dir
+
+    def third(a, b):
+        direct = a - b
+        return b + np.array([-direct[1], direct[0]], np.float32)
+    src[2, :], dst[2, :] = third(src[0], src[1]), third(dst[0], dst[1])
+    A = np.concatenate([src.astype(np.float64), np.ones((3, 1))], 1)          # (3,3) @ trans.T = dst
+    return np.linalg.solve(A, dst.astype(np.float64)).T                       # (2,3)
+
+
+def preprocess_pose2d(joint_input: np.ndarray, input_shape=(384, 288), mid_pairs=(), bbox_scale: float = 1.0):
+    """demo/run.py:124-133 (= data/Human36M/dataset.py:383-389 after the crop): bbox -> aspect-ratio box ->
+    affine into the (input_shape[1], input_shape[0]) crop -> /[W, H] -> per-axis standardisation.
+    joint_input (J, >=2) pixel coordinates.  Returns (pose2d (J',2) f32, joint_img (J',2) f32, bbox (4,) f32)."""
+    j = np.asarray(joint_input)
+    for a, b in mid_pairs:
+        j = add_mid_joint(j, a, b)
+    j = j[:, :2]
+    W, H = input_shape[1], input_shape[0]
+    bbox = process_bbox(get_bbox(j).copy(), aspect_ratio=W / H, scale=bbox_scale)
+    if bbox is None:
+        return None
+    trans = crop_affine(bbox, (W, H))
+    kp = j.copy()
+    for i in range(kp.shape[0]):
+        kp[i, :2] = np.dot(trans, np.array([kp[i, 0], kp[i, 1], 1.]).T)[:2]
+    kp = kp.astype('float32')
+    joint_img = kp[:, :2].copy()
+    ji = joint_img.copy()
+    ji /= np.array([[W, H]])
+    mean, std = np.mean(ji, axis=0), np.std(ji, axis=0)
+    return ((ji.copy() - mean) / std).astype(np.float32), joint_img, bbox

@@ -167,3 +167,19 @@ def ref_mesh(root: str):
     with chdir(root):
         from models.backbones import mesh as m
         return m.Mesh(device=torch.device('cpu'))
+
+
+def dataset_class(name: str = 'Human36M'):
+    """The reference dataset class (data/<name>/dataset.py) without constructing it: its evaluation methods
+    (`compute_both_err`, `evaluate_joint`) only read `self.human36_eval_joint` / `self.datalist`, so they can be
+    called unbound on a stand-in object.  Import-time dependencies that are absent here and unused by those
+    methods are stubbed: transforms3d, pycocotools, vis (needs mpl_toolkits)."""
+    install_shims()
+    for mod in ('transforms3d', 'pycocotools', 'pycocotools.coco', 'vis', 'mpl_toolkits', 'mpl_toolkits.mplot3d'):
+        if mod not in sys.modules:
+            m = types.ModuleType(mod)
+            m.COCO = object
+            m.vis_2d_pose = m.vis_3d_pose = m.Axes3D = None
+            sys.modules[mod] = m
+    import importlib
+    return getattr(importlib.import_module(f'{name}.dataset'), name)
