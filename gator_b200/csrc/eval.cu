@@ -9,16 +9,18 @@
 // a Procrustes alignment (dataset.py:480-504, lib/coord_utils.py:127-149).
 //
 // One CTA per sample does all of it with a single read of the two meshes: sparse J-regression (the shipped
-// regressors have ~6 non-zeros per row), metres -> mm, root alignment, per-sample MPJPE / MPVPE and - on request -
-// PA-MPJPE (3x3 one-sided Jacobi SVD in fp64 by one thread).  HBM-bound: 2 x 82 680 B read per sample, a few
-// hundred bytes written.  eval_mean_kernel then reduces the per-sample values in a fixed order.
+// regressors have ~6 non-zeros per row), metres -> mm, root alignment, per-sample MPJPE / MPVPE.  HBM-bound:
+// 2 x 82 680 B read per sample, a few hundred bytes written.  On request eval_pa_kernel adds PA-MPJPE (3x3
+// one-sided Jacobi SVD in fp64, one thread per sample), and eval_mean_kernel reduces the per-sample values in a
+// fixed order.
 #include "common.cuh"
 
 namespace gator {
 namespace {
 
 constexpr int kMaxJoints = 32;
-constexpr int kTile = 1024;          // vertices staged per pass: 2 x 12 KB of shared memory
+constexpr int kWarpTile = 64;        // vertices per warp tile: 768 B of each mesh
+constexpr int kStages = 3;           // cp.async ring depth per warp (8 warps x 3 x 1536 B = 36 KB per CTA)
 
 __device__ __forceinline__ float block_sum(float v, float* red) {
   v = warp_sum(v);
@@ -117,16 +119,65 @@ __device__ double procrustes_error(const float (*A)[3], const float (*Bp)[3], in
   return err / n;
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
+__global__ void __launch_bounds__(256, 6)
 eval_sample_kernel(gator_eval_args a) {
   __shared__ float pj[kMaxJoints][3], gj[kMaxJoints][3];
-  __shared__ float ea[kMaxJoints][3], eb[kMaxJoints][3];
   __shared__ float red[8];
-  __shared__ __align__(16) float sp[kTile * 3], sg[kTile * 3];
+  // per-warp cp.async ring: [warp][stage][pred | gt][kWarpTile * 3] - no block-wide barrier in the streaming loop
+  __shared__ __align__(16) float ring[8][kStages][2][kWarpTile * 3 + 4];
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int V = a.verts, J = a.joints;
   const float* pm = a.pred_mesh + (size_t)b * V * 3;
   const float scale = a.scale;
+  const bool surface = a.gt_mesh && a.surface_err;
+  const float* gm = surface ? a.gt_mesh + (size_t)b * V * 3 : nullptr;
+  const int n_tiles = (V + kWarpTile - 1) / kWarpTile;
+  const bool aligned = surface && ((((uintptr_t)pm | (uintptr_t)gm) & 7u) == 0) && (V & 1) == 0;
+
+  // Shared-memory image of a tile keeps the global 16-byte phase (a sample starts 0 or 8 bytes past a 16-byte
+  // boundary: 82 680 = 8 mod 16), so whole 16-byte chunks can be copied and only the two ends are 8-byte copies.
+  const int op = aligned ? (int)(((uintptr_t)pm >> 2) & 3u) : 0;          // floats past the 16-byte boundary (0 or 2)
+  const int og = aligned ? (int)(((uintptr_t)gm >> 2) & 3u) : 0;
+  auto copy_tile = [&](float* dst, const float* src, int o, int nf) {
+    // chunk c covers tile floats [4c - o, 4c - o + 4) clipped to [0, nf)
+    for (int c = lane; c * 4 < o + nf; c += 32) {
+      const int lo = max(4 * c - o, 0), hi = min(4 * c - o + 4, nf);
+      if (hi - lo == 4) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((uint32_t)__cvta_generic_to_shared(dst + o + lo)), "l"(src + lo) : "memory");
+      } else {
+        cp_async8(dst + o + lo, src + lo);                                  // o, nf even => exactly 2 floats
+      }
+    }
+  };
+  // tile `k` of this warp (global tile warp + 8k) into ring stage k % kStages; always commits one group
+  auto issue = [&](int k) {
+    const int tile = warp + 8 * k;
+    if (surface && tile < n_tiles) {
+      const int v0 = tile * kWarpTile;
+      const int nf = min(kWarpTile, V - v0) * 3;
+      const float* ps = pm + (size_t)v0 * 3;
+      const float* gs = gm + (size_t)v0 * 3;
+      float* dp = ring[warp][k % kStages][0];
+      float* dg = ring[warp][k % kStages][1];
+      if (aligned) {
+        copy_tile(dp, ps, op, nf);
+        copy_tile(dg, gs, og, nf);
+      } else {
+        for (int i = lane; i < nf; i += 32) { cp_async4(dp + i, ps + i); cp_async4(dg + i, gs + i); }
+      }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  };
+  // the first tiles stream in while the joints are regressed
+#pragma unroll
+  for (int k = 0; k < kStages - 1; ++k) issue(k);
 
   // 1. joints: sparse regression of the predicted mesh (base.py:219-221) or the caller's own joints
   if (a.pred_joints_in) {
@@ -152,37 +203,33 @@ eval_sample_kernel(gator_eval_args a) {
   const float rp0 = pj[a.root][0], rp1 = pj[a.root][1], rp2 = pj[a.root][2];
   const float rg0 = gj[a.root][0], rg1 = gj[a.root][1], rg2 = gj[a.root][2];
 
-  // 2. surface error: both meshes streamed once through shared memory (8-byte aligned for every sample)
-  if (a.gt_mesh && a.surface_err) {
-    const float* gm = a.gt_mesh + (size_t)b * V * 3;
+  // 2. surface error: both meshes streamed exactly once
+  if (surface) {
     float acc = 0.f;
-    for (int v0 = 0; v0 < V; v0 += kTile) {
-      const int nv = min(kTile, V - v0);
-      const int nf = nv * 3;
-      const float* ps = pm + (size_t)v0 * 3;
-      const float* gs = gm + (size_t)v0 * 3;
-      __syncthreads();
-      if ((((uintptr_t)ps | (uintptr_t)gs) & 7u) == 0) {
-        for (int i = tid; i < nf / 2; i += 256) {
-          reinterpret_cast<float2*>(sp)[i] = __ldg(reinterpret_cast<const float2*>(ps) + i);
-          reinterpret_cast<float2*>(sg)[i] = __ldg(reinterpret_cast<const float2*>(gs) + i);
+    for (int k = 0; warp + 8 * k < n_tiles; ++k) {
+      issue(k + kStages - 1);                                  // refills the stage consumed in iteration k - 1
+      asm volatile("cp.async.wait_group %0;\n" ::"n"(kStages - 1) : "memory");
+      __syncwarp();
+      const int nv = min(kWarpTile, V - (warp + 8 * k) * kWarpTile);
+      const float* sp = ring[warp][k % kStages][0] + op;
+      const float* sg = ring[warp][k % kStages][1] + og;
+#pragma unroll
+      for (int u = 0; u < kWarpTile / 32; ++u) {
+        const int v = lane + 32 * u;
+        if (v < nv) {
+          // same operation order as the reference: x*1000, minus root, difference, squares, sqrt
+          const float dx = __fsub_rn(__fsub_rn(__fmul_rn(sp[v * 3], scale), rp0), __fsub_rn(__fmul_rn(sg[v * 3], scale), rg0));
+          const float dy = __fsub_rn(__fsub_rn(__fmul_rn(sp[v * 3 + 1], scale), rp1), __fsub_rn(__fmul_rn(sg[v * 3 + 1], scale), rg1));
+          const float dz = __fsub_rn(__fsub_rn(__fmul_rn(sp[v * 3 + 2], scale), rp2), __fsub_rn(__fmul_rn(sg[v * 3 + 2], scale), rg2));
+          acc += sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
         }
-        if ((nf & 1) && tid == 0) { sp[nf - 1] = ps[nf - 1]; sg[nf - 1] = gs[nf - 1]; }
-      } else {
-        for (int i = tid; i < nf; i += 256) { sp[i] = ps[i]; sg[i] = gs[i]; }
       }
-      __syncthreads();
-      for (int v = tid; v < nv; v += 256) {
-        // same operation order as the reference: x*1000, minus root, difference, squares, sqrt
-        const float dx = __fsub_rn(__fsub_rn(__fmul_rn(sp[v * 3], scale), rp0), __fsub_rn(__fmul_rn(sg[v * 3], scale), rg0));
-        const float dy = __fsub_rn(__fsub_rn(__fmul_rn(sp[v * 3 + 1], scale), rp1), __fsub_rn(__fmul_rn(sg[v * 3 + 1], scale), rg1));
-        const float dz = __fsub_rn(__fsub_rn(__fmul_rn(sp[v * 3 + 2], scale), rp2), __fsub_rn(__fmul_rn(sg[v * 3 + 2], scale), rg2));
-        acc += sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
-      }
+      __syncwarp();
     }
     const float tot = block_sum(acc, red);
     if (tid == 0) a.surface_err[b] = tot / (float)V;
   }
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 
   // 3. joint error on the evaluation joints, root-aligned
   if (tid < 32) {
@@ -191,16 +238,33 @@ eval_sample_kernel(gator_eval_args a) {
       const int j = __ldg(a.eval_joints + lane);
       const float p0 = __fsub_rn(pj[j][0], rp0), p1 = __fsub_rn(pj[j][1], rp1), p2 = __fsub_rn(pj[j][2], rp2);
       const float g0 = __fsub_rn(gj[j][0], rg0), g1 = __fsub_rn(gj[j][1], rg1), g2 = __fsub_rn(gj[j][2], rg2);
-      ea[lane][0] = p0; ea[lane][1] = p1; ea[lane][2] = p2;
-      eb[lane][0] = g0; eb[lane][1] = g1; eb[lane][2] = g2;
       const float dx = __fsub_rn(p0, g0), dy = __fsub_rn(p1, g1), dz = __fsub_rn(p2, g2);
       e = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
     }
     e = warp_sum(e);
     if (lane == 0 && a.joint_err) a.joint_err[b] = e / (float)a.n_eval;
-    __syncwarp();
-    if (lane == 0 && a.pa_joint_err) a.pa_joint_err[b] = (float)procrustes_error(ea, eb, a.n_eval);
   }
+}
+
+// PA-MPJPE: one thread per sample on the regressed joints (kept out of eval_sample_kernel so that the fp64
+// Jacobi's registers do not limit the occupancy of the bandwidth-bound mesh pass)
+__global__ void __launch_bounds__(64)
+eval_pa_kernel(const float* pred_joints, const float* gt_joints, const int32_t* eval_joints, int n_eval, int joints,
+               int root, int batch, float* pa_out) {
+  const int b = blockIdx.x * 64 + threadIdx.x;
+  if (b >= batch) return;
+  float ea[kMaxJoints][3], eb[kMaxJoints][3];
+  const float* p = pred_joints + (size_t)b * joints * 3;
+  const float* g = gt_joints + (size_t)b * joints * 3;
+  for (int i = 0; i < n_eval; ++i) {
+    const int j = __ldg(eval_joints + i);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      ea[i][c] = __fsub_rn(p[j * 3 + c], p[root * 3 + c]);
+      eb[i][c] = __fsub_rn(g[j * 3 + c], g[root * 3 + c]);
+    }
+  }
+  pa_out[b] = (float)procrustes_error(ea, eb, n_eval);
 }
 
 // mean over the batch of up to three per-sample arrays, fixed summation order, fp64 accumulation
@@ -237,8 +301,16 @@ extern "C" int gator_eval_epilogue(const gator_eval_args* a, void* stream) {
   GATOR_REQUIRE(a->pred_mesh && a->gt_joints && a->eval_joints, "gator_eval_epilogue: null buffer");
   GATOR_REQUIRE(a->pred_joints_in || (a->jreg_rowptr && a->jreg_colidx && a->jreg_values),
                 "gator_eval_epilogue: need a CSR regressor or pred_joints_in");
+  GATOR_REQUIRE(!a->pa_joint_err || a->pred_joints || a->pred_joints_in,
+                "gator_eval_epilogue: pa_joint_err needs pred_joints (or pred_joints_in)");
   eval_sample_kernel<<<a->batch, 256, 0, (cudaStream_t)stream>>>(*a);
   GATOR_TRY(check_launch("eval_sample"));
+  if (a->pa_joint_err) {
+    eval_pa_kernel<<<ceil_div(a->batch, 64), 64, 0, (cudaStream_t)stream>>>(
+        a->pred_joints_in ? a->pred_joints_in : a->pred_joints, a->gt_joints, a->eval_joints, a->n_eval, a->joints,
+        a->root, a->batch, a->pa_joint_err);
+    GATOR_TRY(check_launch("eval_pa"));
+  }
   if (a->batch_mean) {
     eval_mean_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(a->joint_err, a->surface_err && a->gt_mesh ? a->surface_err : nullptr,
                                                           a->pa_joint_err, a->batch, a->batch_mean);

@@ -296,7 +296,7 @@ typedef struct {
   float* pred_joints;          /* out (B, joints, 3) = J_regressor @ (pred_mesh*scale), or NULL */
   float* joint_err;            /* out (B) mean over the eval joints, or NULL              */
   float* surface_err;          /* out (B) mean over the vertices, or NULL                 */
-  float* pa_joint_err;         /* out (B) joint error after similarity Procrustes, or NULL */
+  float* pa_joint_err;         /* out (B) joint error after similarity Procrustes, or NULL (needs pred_joints) */
   float* batch_mean;           /* out (3) batch means of the three arrays above (0 where absent), or NULL */
 } gator_eval_args;
 

@@ -70,13 +70,20 @@ def test_eval_epilogue_matches_oracle(epilogue, batch):
     pred, gt, gt_pose = synthetic.eval_inputs(batch, reg, seed=11)
     pp = orc.eval_pred_pose(torch.from_numpy(reg), torch.from_numpy(pred)).numpy()
     mpjpe, mpvpe, pa = orc.per_sample_errors(pred * np.float32(1000), gt * np.float32(1000), pp, gt_pose)
-    # misaligned views (offset by one sample + 1 float) exercise the scalar load path
     r = epilogue(torch.from_numpy(pred).cuda(), torch.from_numpy(gt).cuda(), torch.from_numpy(gt_pose).cuda(), pa=True)
     assert np.abs(r.pred_pose.cpu().numpy() - pp).max() < TOL_MM
     assert np.abs(r.joint_err.cpu().numpy() - mpjpe).max() < TOL_MM
     assert np.abs(r.surface_err.cpu().numpy() - mpvpe).max() < TOL_MM
     assert np.abs(r.pa_joint_err.cpu().numpy() - pa).max() < TOL_MM
     assert abs(float(r.joint_error) - mpjpe.mean()) < TOL_MM
+    # meshes that are only 4-byte aligned take the narrow-copy path and must give the same numbers
+    def shifted(a):
+        buf = torch.empty(a.size + 1, device='cuda')
+        buf[1:] = torch.from_numpy(a).cuda().reshape(-1)
+        return buf[1:].view(a.shape)
+    r4 = epilogue(shifted(pred), shifted(gt), torch.from_numpy(gt_pose).cuda())
+    assert r4.pred_pose.data_ptr() % 8 == 0 and shifted(pred).data_ptr() % 8 == 4
+    assert torch.equal(r4.surface_err, r.surface_err) and torch.equal(r4.joint_err, r.joint_err)
     # without a ground-truth mesh and without PA: optional outputs are absent, means are zero
     r2 = epilogue(torch.from_numpy(pred).cuda(), None, torch.from_numpy(gt_pose).cuda())
     assert r2.surface_err is None and r2.pa_joint_err is None and float(r2.surface_error) == 0.0
