@@ -41,7 +41,7 @@ class MdrArgs(C.Structure):
 class SmplArgs(C.Structure):
     _fields_ = [('batch', C.c_int32), ('center_idx', C.c_int32), ('has_betas', C.c_int32), ('has_trans', C.c_int32),
                 ('check_zero_norm', C.c_int32), ('weights_per_vertex', C.c_int32), ('precision', C.c_int32),
-                ('reserved', C.c_int32),
+                ('out_scale', C.c_float),
                 ('parents', C.c_void_p), ('j_template', C.c_void_p), ('j_shapedirs', C.c_void_p),
                 ('default_betas', C.c_void_p), ('blend_w', C.c_void_p), ('blend_w_bf16', C.c_void_p), ('blend_w_bf16_lo', C.c_void_p),
                 ('v_template', C.c_void_p),
@@ -83,13 +83,20 @@ class Pose2dArgs(C.Structure):
                 ('valid', C.c_void_p)]
 
 
-_STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs, EvalArgs, Pose2dArgs]
+class SmplCamArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('reserved', C.c_int32),
+                ('j_template', C.c_void_p), ('j_shapedirs', C.c_void_p), ('default_betas', C.c_void_p),
+                ('pose', C.c_void_p), ('betas', C.c_void_p), ('trans', C.c_void_p), ('cam_R', C.c_void_p),
+                ('cam_t', C.c_void_p), ('pose_out', C.c_void_p), ('betas_out', C.c_void_p), ('trans_out', C.c_void_p)]
+
+
+_STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs, EvalArgs, Pose2dArgs, SmplCamArgs]
 EXPORTS = ['gator_abi_version', 'gator_last_error', 'gator_abi_sizeof', 'gator_launch_count',
            'gator_mdr_self_attention', 'gator_mdr_layer_chain', 'gator_umma_weight_layout',
            'gator_gat_slot_name', 'gator_gat_workspace_bytes', 'gator_gat_forward',
            'gator_mdr_slot_name', 'gator_mdr_workspace_bytes', 'gator_mdr_forward',
            'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_gemm',
-           'gator_eval_epilogue', 'gator_pose2d_preprocess']
+           'gator_eval_epilogue', 'gator_pose2d_preprocess', 'gator_smpl_cam_fixup']
 
 _lock = threading.Lock()
 _lib = None
@@ -122,7 +129,8 @@ def lib():
         L.gator_smpl_workspace_bytes.argtypes = [C.c_int32]
         for name, st in (('gator_gat_forward', GatArgs), ('gator_mdr_forward', MdrArgs),
                          ('gator_smpl_forward', SmplArgs), ('gator_csr_spmm', CsrArgs), ('gator_gemm', GemmArgs),
-                         ('gator_eval_epilogue', EvalArgs), ('gator_pose2d_preprocess', Pose2dArgs)):
+                         ('gator_eval_epilogue', EvalArgs), ('gator_pose2d_preprocess', Pose2dArgs),
+                         ('gator_smpl_cam_fixup', SmplCamArgs)):
             getattr(L, name).restype = C.c_int
             getattr(L, name).argtypes = [C.POINTER(st), C.c_void_p]
         L.gator_launch_count.restype = C.c_longlong

@@ -42,6 +42,7 @@ extern "C" size_t gator_abi_sizeof(int which) {
     case 4: return sizeof(gator_gemm_args);
     case 5: return sizeof(gator_eval_args);
     case 6: return sizeof(gator_pose2d_args);
+    case 7: return sizeof(gator_smpl_cam_args);
     default: return 0;
   }
 }

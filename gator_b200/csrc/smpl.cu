@@ -46,6 +46,7 @@ struct PoseParams {
   float* jtr;               // (B,24,3)
   int batch;
   int center_idx;
+  float out_scale;          // applied to jtr after the translation
 };
 
 __global__ void __launch_bounds__(128)
@@ -139,7 +140,7 @@ smpl_pose_kernel(PoseParams p) {
   }
   if (lane < NJ) {
     float* jo = p.jtr + ((size_t)b * NJ + lane) * 3;
-    jo[0] = G[3] + off[0]; jo[1] = G[7] + off[1]; jo[2] = G[11] + off[2];
+    jo[0] = (G[3] + off[0]) * p.out_scale; jo[1] = (G[7] + off[1]) * p.out_scale; jo[2] = (G[11] + off[2]) * p.out_scale;
     // G' = G - pack(G @ [j; 0]): last column becomes t - R j
     float* ao = p.amat + ((size_t)b * NJ + lane) * 12;
 #pragma unroll
@@ -166,7 +167,8 @@ constexpr int SK_SG = 16;
 
 __global__ void __launch_bounds__(SK_VT)
 smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ amat, const float* __restrict__ offset,
-                 const int* __restrict__ sidx, const float* __restrict__ sw, int KW, float* __restrict__ verts, int batch) {
+                 const int* __restrict__ sidx, const float* __restrict__ sw, int KW, float* __restrict__ verts, int batch,
+                 float out_scale) {
   __shared__ float sA[SK_SG][12 * NJ];   // component-major [e][joint]: lanes reading different joints hit different banks
   __shared__ float soff[SK_SG][4];
   __shared__ __align__(16) float stage[SK_VT / 32][96];
@@ -231,9 +233,9 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
           for (int e = 0; e < 12; ++e) T[e] = fmaf(ww, sA[s][e * NJ + jj], T[e]);
         }
       }
-      o0 = T[0] * px + T[1] * py + T[2] * pz + T[3] + soff[s][0];
-      o1 = T[4] * px + T[5] * py + T[6] * pz + T[7] + soff[s][1];
-      o2 = T[8] * px + T[9] * py + T[10] * pz + T[11] + soff[s][2];
+      o0 = (T[0] * px + T[1] * py + T[2] * pz + T[3] + soff[s][0]) * out_scale;
+      o1 = (T[4] * px + T[5] * py + T[6] * pz + T[7] + soff[s][1]) * out_scale;
+      o2 = (T[8] * px + T[9] * py + T[10] * pz + T[11] + soff[s][2]) * out_scale;
     }
     __syncwarp();                                          // everyone has read its inputs from `st`
     if (active) { st[lane * 3] = o0; st[lane * 3 + 1] = o1; st[lane * 3 + 2] = o2; }
@@ -294,6 +296,7 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     return GATOR_ERR_WORKSPACE;
   }
   const int cb = B < kChunk ? B : kChunk;
+  const float out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
   Ws w = carve(static_cast<char*>(a->workspace), cb);
   const bool flags = a->check_zero_norm && (a->has_betas || a->has_trans);
   if (flags) {
@@ -318,6 +321,7 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     p.jtr = a->jtr + (size_t)b0 * NJ * 3;
     p.batch = nb;
     p.center_idx = a->center_idx;
+    p.out_scale = out_scale;
     smpl_pose_kernel<<<ceil_div(nb, 4), 128, 0, stream>>>(p);
     GATOR_TRY(check_launch("smpl_pose"));
     Epilogue e;
@@ -325,7 +329,7 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     GATOR_TRY(gemm(a->precision, w.aop, KB, a->blend_w, KB, PackedW{a->blend_w_bf16, a->blend_w_bf16_lo}, w.vposed, VP_LD, nb, NV3, KB, e, stream));
     dim3 grid(ceil_div(NV, SK_VT), ceil_div(nb, SK_SG));
     smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w,
-                                                 a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb);
+                                                 a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb, out_scale);
     GATOR_TRY(check_launch("smpl_skin"));
   }
   return GATOR_OK;

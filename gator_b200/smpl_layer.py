@@ -128,6 +128,11 @@ class SMPL_Layer(Module):
 
     def forward(self, th_pose_axisang, th_betas=torch.zeros(1), th_trans=torch.zeros(1)):
         """pose (B,72) axis-angle, betas (B,10), trans (B,3) -> (verts (B,6890,3), joints (B,24,3)) metres."""
+        return self.forward_scaled(th_pose_axisang, th_betas, th_trans, 1.0)
+
+    def forward_scaled(self, th_pose_axisang, th_betas=torch.zeros(1), th_trans=torch.zeros(1), out_scale: float = 1.0):
+        """`forward` with both outputs multiplied by `out_scale` after the translation, in the skinning kernel
+        (the datasets' ``*= 1000``, data/Human36M/dataset.py:296, data/PW3D/dataset.py:99-100)."""
         if self._packed is None:
             self.pack()
         p = self._packed
@@ -151,7 +156,7 @@ class SMPL_Layer(Module):
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         a = _lib.SmplArgs(batch=B, center_idx=-1 if self.center_idx is None else int(self.center_idx),
                           has_betas=int(has_betas), has_trans=int(has_trans), check_zero_norm=int(check),
-                          weights_per_vertex=p['kw'], precision=self.precision, reserved=0,
+                          weights_per_vertex=p['kw'], precision=self.precision, out_scale=float(out_scale),
                           parents=_lib.ptr(p['parents']), j_template=_lib.ptr(p['j_template']),
                           j_shapedirs=_lib.ptr(p['j_shapedirs']), default_betas=_lib.ptr(p['default_betas']),
                           blend_w=_lib.ptr(p['blend_w']), blend_w_bf16=_lib.ptr(p['blend_w_bf16'][0]), blend_w_bf16_lo=_lib.ptr(p['blend_w_bf16'][1]), v_template=_lib.ptr(p['v_template']),

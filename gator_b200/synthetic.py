@@ -310,3 +310,24 @@ def pixel_poses(base17: np.ndarray, batch: int, seed: int = 9) -> np.ndarray:
         out[b, :, 1] = (out[b, :, 1] - c[1]) * sy + c[1] + 200 * r.standard_normal()
         out[b, :, :2] += 2.0 * r.standard_normal((17, 2))
     return out
+
+
+def camera_annotations(batch: int, seed: int = 13):
+    """Human3.6M-style per-item annotations for ``get_smpl_coord`` (data/Human36M/dataset.py:254-262):
+    SMPL pose (B,72) with a non-trivial root orientation, shape (B,10) incl. one implausible row (|beta| > 3),
+    trans (B,3) metres, camera rotation R (B,3,3) and translation t (B,3) in millimetres."""
+    r = _rng('camera_annotations', seed)
+    pose = r.uniform(-0.3, 0.3, size=(batch, 72)).astype(np.float32)
+    pose[:, :3] = r.uniform(-1.5, 1.5, size=(batch, 3)).astype(np.float32)
+    shape = r.standard_normal((batch, 10)).astype(np.float32)
+    if batch > 1:
+        shape[1, 4] = 3.5                                    # dataset.py:266 resets the whole row to 0
+    trans = r.standard_normal((batch, 3)).astype(np.float32)
+    q = r.standard_normal((batch, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    R = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w),
+                  2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w),
+                  2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1).reshape(batch, 3, 3)
+    t = (r.standard_normal((batch, 3)) * np.array([500.0, 500.0, 1500.0]) + np.array([0.0, 0.0, 4500.0]))
+    return pose, shape, trans, R.astype(np.float32), t.astype(np.float32)

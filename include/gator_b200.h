@@ -49,7 +49,7 @@ typedef enum {
 int gator_abi_version(void);
 const char* gator_last_error(void);
 /* sizeof() of the ABI structs as compiled, so the ctypes mirror can be verified at load time:
- * which = 0 gat, 1 mdr, 2 smpl, 3 csr, 4 gemm, 5 eval, 6 pose2d */
+ * which = 0 gat, 1 mdr, 2 smpl, 3 csr, 4 gemm, 5 eval, 6 pose2d, 7 smpl_cam */
 size_t gator_abi_sizeof(int which);
 /* number of kernels this library has launched (process-wide); reset != 0 zeroes it after reading.
  * bench.py reports it as `gpu_launches`. */
@@ -223,7 +223,8 @@ typedef struct {
   int32_t check_zero_norm;     /* 1: reproduce the reference's `norm(x)==0` switches on device */
   int32_t weights_per_vertex;  /* ELL width of the skinning weights                      */
   int32_t precision;
-  int32_t reserved;
+  float out_scale;             /* verts and jtr are multiplied by this after the translation; 0 = 1.0
+                                  (1000.0f = the datasets' metres -> mm, data/Human36M/dataset.py:296) */
   const int32_t* parents;      /* (24) DEVICE int32 kintree parents, parents[0] ignored   */
   const float* j_template;     /* (24,3)    J_regressor @ v_template                      */
   const float* j_shapedirs;    /* (24,3,10) J_regressor @ shapedirs                       */
@@ -245,6 +246,34 @@ typedef struct {
 
 size_t gator_smpl_workspace_bytes(int32_t batch);
 int gator_smpl_forward(const gator_smpl_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ground-truth mesh generation, camera fix-up - the per-item host arithmetic of Human36M.get_smpl_coord
+ * (data/Human36M/dataset.py:254-298) around its batch-1 SMPL forward, for a whole batch:
+ *   betas'      = 0 if any |beta| > 3 else betas                                      (:266)
+ *   pose'[0:3]  = axis-angle of R_cam . rodrigues(pose[0:3])  (transforms3d axangle2mat / mat2axangle, :268-274)
+ *   smpl_trans  = R_cam . trans + t_cam/1000 - root + R_cam . root                     (:289-292)
+ * with root = rest position of the root joint for betas' (what smpl_joint_coord[root] is when no translation
+ * is passed).  Feeding pose', betas', smpl_trans and out_scale = 1000 to gator_smpl_forward gives the
+ * (mesh_cam, joint_cam) of get_smpl_coord in millimetres with no pass over the mesh besides the skinning.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch;
+  int32_t reserved;
+  const float* j_template;     /* (24,3)    as in gator_smpl_args                          */
+  const float* j_shapedirs;    /* (24,3,10)                                               */
+  const float* default_betas;  /* (10) used when betas' is all zero (smpl_layer.py:87-91)  */
+  const float* pose;           /* (B,72) axis-angle, world frame                          */
+  const float* betas;          /* (B,10)                                                  */
+  const float* trans;          /* (B,3) SMPL -> world translation, metres                 */
+  const float* cam_R;          /* (B,9) row-major world -> camera rotation                */
+  const float* cam_t;          /* (B,3) world -> camera translation, millimetres          */
+  float* pose_out;             /* (B,72)                                                  */
+  float* betas_out;            /* (B,10)                                                  */
+  float* trans_out;            /* (B,3) metres                                            */
+} gator_smpl_cam_args;
+
+int gator_smpl_cam_fixup(const gator_smpl_cam_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Sparse resampling / regression - replaces spmm (lib/models/backbones/graph_layers.py:105-124) as

@@ -571,3 +571,81 @@ def preprocess_pose2d(joint_input: np.ndarray, input_shape=(384, 288), mid_pairs
     ji /= np.array([[W, H]])
     mean, std = np.mean(ji, axis=0), np.std(ji, axis=0)
     return ((ji.copy() - mean) / std).astype(np.float32), joint_img, bbox
+
+
+# ----------------------------------------------------------------------------------------------
+# ground-truth mesh generation - the checker of csrc/smpl_cam.cu + SMPL out_scale
+# ----------------------------------------------------------------------------------------------
+def axangle2mat(axis, angle, is_normalized=False):
+    """transforms3d.axangles.axangle2mat (third-party, unpinned in requirements.sh, absent from the reference
+    tree): published algorithm restated - Rodrigues matrix from a (normalised) axis and an angle."""
+    x, y, z = axis
+    if not is_normalized:
+        n = math.sqrt(x * x + y * y + z * z)
+        x, y, z = x / n, y / n, z / n
+    c, s = math.cos(angle), math.sin(angle)
+    C = 1 - c
+    xs, ys, zs = x * s, y * s, z * s
+    xC, yC, zC = x * C, y * C, z * C
+    xyC, yzC, zxC = x * yC, y * zC, z * xC
+    return np.array([[x * xC + c, xyC - zs, zxC + ys],
+                     [xyC + zs, y * yC + c, yzC - xs],
+                     [zxC - ys, yzC + xs, z * zC + c]])
+
+
+def mat2axangle(mat, unit_thresh=1e-5):
+    """transforms3d.axangles.mat2axangle restated: axis = unit eigenvector of eigenvalue 1 of the matrix (float64
+    eig), angle = atan2(sin, cos) with cos = (trace - 1) / 2 and sin recovered from an off-diagonal entry."""
+    M = np.asarray(mat, dtype=np.float64)
+    L, W = np.linalg.eig(M.T)
+    i = np.where(np.abs(L - 1.0) < unit_thresh)[0]
+    if not len(i):
+        raise ValueError('no unit eigenvector corresponding to eigenvalue 1')
+    direction = np.real(W[:, i[-1]]).squeeze()
+    cosa = (np.trace(M) - 1.0) / 2.0
+    if abs(direction[2]) > 1e-8:
+        sina = (M[1, 0] + (cosa - 1.0) * direction[0] * direction[1]) / direction[2]
+    elif abs(direction[1]) > 1e-8:
+        sina = (M[0, 2] + (cosa - 1.0) * direction[0] * direction[2]) / direction[1]
+    else:
+        sina = (M[2, 1] + (cosa - 1.0) * direction[1] * direction[2]) / direction[0]
+    return direction, math.atan2(sina, cosa)
+
+
+def h36m_smpl_coord(buf, parents, pose, shape, trans, R, t, root_idx: int = 0):
+    """Human36M.get_smpl_coord (data/Human36M/dataset.py:254-298) for one item: numpy in, (mesh (6890,3),
+    joints (24,3)) in millimetres, camera frame.  `buf` / `parents` describe the SMPL layer (smpl_forward)."""
+    smpl_pose = torch.FloatTensor(np.asarray(pose, np.float32)).view(-1, 3).clone()
+    smpl_shape = torch.FloatTensor(np.asarray(shape, np.float32)).view(1, -1).clone()
+    trans = np.array(trans, dtype=np.float32).reshape(3)
+    R, t = np.array(R, dtype=np.float32).reshape(3, 3), np.array(t, dtype=np.float32).reshape(3)
+    smpl_shape[(smpl_shape.abs() > 3).any(dim=1)] = 0.
+    root_pose = smpl_pose[root_idx, :].numpy()
+    angle = np.linalg.norm(root_pose)
+    root_pose = axangle2mat(root_pose / angle, angle)
+    root_pose = np.dot(R, root_pose)
+    axis, angle = mat2axangle(root_pose)
+    smpl_pose[root_idx] = torch.from_numpy(axis * angle)
+    verts, jtr, _ = smpl_forward(buf, parents, smpl_pose.view(1, -1), smpl_shape)
+    mesh = verts.numpy().astype(np.float32).reshape(-1, 3)
+    joints = jtr.numpy().astype(np.float32).reshape(-1, 3)
+    smpl_trans = np.dot(R, trans[:, None]).reshape(1, 3) + t.reshape(1, 3) / 1000
+    root = joints[root_idx].reshape(1, 3)
+    smpl_trans = smpl_trans - root + np.dot(R, root.transpose(1, 0)).transpose(1, 0)
+    mesh += smpl_trans
+    joints += smpl_trans
+    mesh *= 1000
+    joints *= 1000
+    return mesh, joints
+
+
+def pw3d_smpl_coord(buf, parents, pose, shape, trans):
+    """PW3D.get_smpl_coord (data/PW3D/dataset.py:84-102): SMPL forward with the world translation, then mm."""
+    verts, jtr, _ = smpl_forward(buf, parents, torch.FloatTensor(np.asarray(pose, np.float32)).view(1, -1),
+                                 torch.FloatTensor(np.asarray(shape, np.float32)).view(1, -1),
+                                 torch.FloatTensor(np.asarray(trans, np.float32)).view(-1, 3))
+    mesh = verts.numpy().astype(np.float32).reshape(-1, 3)
+    joints = jtr.numpy().astype(np.float32).reshape(-1, 3)
+    mesh *= 1000
+    joints *= 1000
+    return mesh, joints

@@ -173,9 +173,16 @@ def dataset_class(name: str = 'Human36M'):
     """The reference dataset class (data/<name>/dataset.py) without constructing it: its evaluation methods
     (`compute_both_err`, `evaluate_joint`) only read `self.human36_eval_joint` / `self.datalist`, so they can be
     called unbound on a stand-in object.  Import-time dependencies that are absent here and unused by those
-    methods are stubbed: transforms3d, pycocotools, vis (needs mpl_toolkits)."""
+    methods are stubbed: pycocotools, vis (needs mpl_toolkits).  transforms3d (absent, unpinned in requirements.sh)
+    is provided by the oracle's restatement of axangle2mat / mat2axangle."""
     install_shims()
-    for mod in ('transforms3d', 'pycocotools', 'pycocotools.coco', 'vis', 'mpl_toolkits', 'mpl_toolkits.mplot3d'):
+    if 'transforms3d' not in sys.modules:
+        # third-party, absent here: its two functions the datasets call are restated in the oracle
+        from oracle import gator_oracle as orc
+        t3 = types.ModuleType('transforms3d')
+        t3.axangles = types.SimpleNamespace(axangle2mat=orc.axangle2mat, mat2axangle=orc.mat2axangle)
+        sys.modules['transforms3d'] = t3
+    for mod in ('pycocotools', 'pycocotools.coco', 'vis', 'mpl_toolkits', 'mpl_toolkits.mplot3d'):
         if mod not in sys.modules:
             m = types.ModuleType(mod)
             m.COCO = object

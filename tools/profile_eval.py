@@ -70,3 +70,15 @@ print(json.dumps({'kernel': 'pose2d_preprocess_kernel', 'batch': B, 'ms': ms, 'p
 x1 = x[:1].contiguous()
 ms = timed(lambda: pre(x1), iters=50)
 print(json.dumps({'kernel': 'pose2d_preprocess_kernel', 'batch': 1, 'ms': ms}))
+
+# ground-truth mesh generation (row f2): batched get_smpl_coord, camera fix-up + SMPL forward in mm
+from helpers import build_b200_smpl, synthetic
+from gator_b200.gt_mesh import GtMeshGenerator
+Bg = 16384
+gen = GtMeshGenerator(build_b200_smpl(device=dev).set_precision('bf16x3'))
+ann = [torch.from_numpy(a).to(dev) for a in synthetic.camera_annotations(Bg)]
+ms = timed(lambda: gen.h36m(*ann), iters=10)
+print(json.dumps({'kernel': 'GtMeshGenerator.h36m (smpl_cam_fixup + SMPL forward bf16x3, mm out)', 'batch': Bg, 'ms': ms,
+                  'meshes_per_s': Bg / ms * 1e3, 'achieved_GBps_out': Bg * 82680 / ms / 1e6}))
+ms = timed(lambda: gen.layer.forward(ann[0], ann[1], ann[2]), iters=10)
+print(json.dumps({'kernel': 'SMPL_Layer.forward alone (same batch, metres)', 'batch': Bg, 'ms': ms}))
