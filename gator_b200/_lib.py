@@ -44,6 +44,7 @@ class SmplArgs(C.Structure):
                 ('out_scale', C.c_float),
                 ('parents', C.c_void_p), ('j_template', C.c_void_p), ('j_shapedirs', C.c_void_p),
                 ('default_betas', C.c_void_p), ('blend_w', C.c_void_p), ('blend_w_bf16', C.c_void_p), ('blend_w_bf16_lo', C.c_void_p),
+                ('blend_w_wide', C.c_void_p),
                 ('v_template', C.c_void_p),
                 ('skin_idx', C.c_void_p), ('skin_w', C.c_void_p), ('pose', C.c_void_p), ('betas', C.c_void_p),
                 ('trans', C.c_void_p), ('verts', C.c_void_p), ('jtr', C.c_void_p),
@@ -61,7 +62,8 @@ class GemmArgs(C.Structure):
     _fields_ = [('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32),
                 ('lda', C.c_int32), ('ldw', C.c_int32), ('ldc', C.c_int32), ('ldr', C.c_int32),
                 ('act', C.c_int32), ('bias_period', C.c_int32), ('precision', C.c_int32),
-                ('A', C.c_void_p), ('W', C.c_void_p), ('W_lo', C.c_void_p), ('bias', C.c_void_p), ('bias_rows', C.c_void_p),
+                ('A', C.c_void_p), ('W', C.c_void_p), ('W_lo', C.c_void_p), ('W_wide', C.c_void_p), ('a_image', C.c_void_p),
+                ('a_image_bytes', C.c_size_t), ('bias', C.c_void_p), ('bias_rows', C.c_void_p),
                 ('R', C.c_void_p), ('C', C.c_void_p)]
 
 
@@ -96,7 +98,8 @@ EXPORTS = ['gator_abi_version', 'gator_last_error', 'gator_abi_sizeof', 'gator_l
            'gator_gat_slot_name', 'gator_gat_workspace_bytes', 'gator_gat_forward',
            'gator_mdr_slot_name', 'gator_mdr_workspace_bytes', 'gator_mdr_forward',
            'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_gemm',
-           'gator_eval_epilogue', 'gator_pose2d_preprocess', 'gator_smpl_cam_fixup']
+           'gator_eval_epilogue', 'gator_pose2d_preprocess', 'gator_smpl_cam_fixup',
+           'gator_umma_wide_layout', 'gator_umma_wide_a_bytes']
 
 _lock = threading.Lock()
 _lib = None
@@ -140,6 +143,10 @@ def lib():
         L.gator_mdr_layer_chain.restype = C.c_int
         L.gator_mdr_layer_chain.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.gator_umma_wide_layout.restype = C.c_int
+        L.gator_umma_wide_layout.argtypes = [C.c_int32, C.c_int32, c_int_p, c_int_p]
+        L.gator_umma_wide_a_bytes.restype = C.c_size_t
+        L.gator_umma_wide_a_bytes.argtypes = [C.c_int32, C.c_int32]
         L.gator_umma_weight_layout.restype = C.c_int
         L.gator_umma_weight_layout.argtypes = [C.c_int32, C.c_int32, c_int_p, c_int_p, c_int_p]
         if L.gator_abi_version() != 1:

@@ -63,6 +63,13 @@ int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, const void* Wpa
                    int N, int K, const Epilogue& epi, cudaStream_t stream);
 void umma_weight_layout(int N, int K, int* BN, int* n_tiles, int* K_pad);
 
+// Wide-N variant for GATOR_PREC_BF16X3 (csrc/umma_gemm_wide.cu): persistent, warp-specialised, TMA-fed.  Wimg is the
+// tile-major split image of W (gator_b200/packing.py: pack_umma_wide); a_img is caller workspace of at least
+// wide_a_image_bytes(M, K) into which A is split first.
+size_t wide_a_image_bytes(int M, int K);
+int gemm_bf16x3_wide(const float* A, int lda, const void* Wimg, void* a_img, size_t a_img_bytes, float* C, int ldc,
+                     int M, int N, int K, const Epilogue& epi, cudaStream_t stream);
+
 // precision dispatch used by the stage drivers: bf16 only if a packed weight exists for the slot
 struct PackedW {
   const void* hi = nullptr;

@@ -186,6 +186,9 @@ extern "C" int gator_gemm(const gator_gemm_args* a, void* stream) {
   e.ldr = a->ldr;
   if (a->precision == GATOR_PREC_BF16)   // W = bf16 weights packed by gator_b200.packing.pack_umma_weight
     return gemm_bf16_umma(a->A, a->lda, a->W, nullptr, a->C, a->ldc, a->M, a->N, a->K, e, (cudaStream_t)stream);
+  if (a->precision == GATOR_PREC_BF16X3 && a->W_wide)   // tile-major split image (pack_umma_wide) + caller workspace
+    return gemm_bf16x3_wide(a->A, a->lda, a->W_wide, a->a_image, a->a_image_bytes, a->C, a->ldc, a->M, a->N, a->K, e,
+                            (cudaStream_t)stream);
   if (a->precision == GATOR_PREC_BF16X3) {
     GATOR_REQUIRE(a->W_lo, "gator_gemm: GATOR_PREC_BF16X3 needs W_lo");
     return gemm_bf16_umma(a->A, a->lda, a->W, a->W_lo, a->C, a->ldc, a->M, a->N, a->K, e, (cudaStream_t)stream);

@@ -319,7 +319,7 @@ mdr_head_kernel(const float* __restrict__ hd, const float* __restrict__ nscale, 
 
 const char* kGlobalNames[MDR_NUM_GLOBAL] = {
     "JF_WFEAT", "JF_WPOSE", "JF_BIASROWS", "VF_CONST", "VF_W3", "VJ", "HEAD_W", "HEAD_B",
-    "BNORM_SCALE", "BNORM_SHIFT", "BCONV_W", "BCONV_B", "UP_W", "UP_BIAST", "CHAIN_FINAL"};
+    "BNORM_SCALE", "BNORM_SHIFT", "BCONV_W", "BCONV_B", "UP_W", "UP_BIAST", "CHAIN_FINAL", "UP_W_WIDE"};
 const char* kLayerNames[MDRL_NUM] = {
     "N1_W", "N1_B", "WQ", "WKV", "PROJ_W", "PROJ_B", "N2_W", "N2_B", "FC1_W", "FC1_B", "FC2_W", "FC2_B",
     "CLN_A", "CLN_B", "SQKV_W", "SQKV_B", "SO_W", "SO_B", "CHAIN"};
@@ -332,8 +332,8 @@ int resolve_chunk(int batch, int chunk) {
 }
 
 struct Ws {
-  float *x, *y, *q, *hid, *jf, *yj, *kv, *hd, *coarse, *a3;
-  size_t bytes;
+  float *x, *y, *q, *hid, *jf, *yj, *kv, *hd, *coarse, *a3, *a3img;
+  size_t a3img_bytes, bytes;
 };
 
 constexpr int kSuperChunk = 8192;   // samples per upsample_conv GEMM launch (im2col rows kept for that many)
@@ -354,6 +354,8 @@ Ws carve(float* base, int nb, int J, int nsuper) {
   w.hd = take(mv * HEADN);
   w.coarse = take((size_t)nb * V * 3);
   w.a3 = take((size_t)nsuper * 3 * UPK);
+  w.a3img_bytes = wide_a_image_bytes(nsuper * 3, UPK);   // split bf16 image of a3 for the wide-N kernel
+  w.a3img = take(w.a3img_bytes / sizeof(float));
   w.bytes = off * sizeof(float);
   return w;
 }
@@ -429,6 +431,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   const int nslots = MDR_NUM_GLOBAL + GATOR_MDR_LAYERS * MDRL_NUM;
   bool have_chain = true;
   for (int i = 0; i < nslots; ++i) {
+    if (i == MDR_UP_W_WIDE) continue;
     if (i == MDR_CHAIN_FINAL || (i >= MDR_NUM_GLOBAL && (i - MDR_NUM_GLOBAL) % MDRL_NUM == MDRL_CHAIN)) {
       have_chain = have_chain && a->weights[i] != nullptr;
       continue;
@@ -557,7 +560,12 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   Epilogue e;
   e.conv3 = 1;
   e.bias_rows = G(MDR_UP_BIAST);
-  GATOR_TRY(gemm(P(16), w.a3, UPK, G(MDR_UP_W), UPK, GB(MDR_UP_W), a->mesh + (size_t)s0 * VF * 3, 0, ns * 3, VF, UPK, e, stream));
+  if (P(16) == GATOR_PREC_BF16X3 && a->weights[MDR_UP_W_WIDE]) {
+    GATOR_TRY(gemm_bf16x3_wide(w.a3, UPK, a->weights[MDR_UP_W_WIDE], w.a3img, w.a3img_bytes, a->mesh + (size_t)s0 * VF * 3, 0,
+                               ns * 3, VF, UPK, e, stream));
+  } else {
+    GATOR_TRY(gemm(P(16), w.a3, UPK, G(MDR_UP_W), UPK, GB(MDR_UP_W), a->mesh + (size_t)s0 * VF * 3, 0, ns * 3, VF, UPK, e, stream));
+  }
   }
   return GATOR_OK;
 }

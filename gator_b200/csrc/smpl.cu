@@ -250,6 +250,8 @@ constexpr int kChunk = 1024;
 
 struct Ws {
   float *aop, *amat, *offset, *vposed;
+  void* aimg;               // split bf16 image of aop for the wide-N blend-shape GEMM
+  size_t aimg_bytes;
   int* flags;
   size_t bytes;
 };
@@ -263,6 +265,8 @@ Ws carve(char* base, int nb) {
   w.amat = reinterpret_cast<float*>(take((size_t)nb * NJ * 12 * 4));
   w.offset = reinterpret_cast<float*>(take((size_t)nb * 3 * 4));
   w.vposed = reinterpret_cast<float*>(take((size_t)nb * VP_LD * 4));
+  w.aimg_bytes = wide_a_image_bytes(nb, KB);
+  w.aimg = take(w.aimg_bytes);
   w.bytes = off;
   return w;
 }
@@ -326,7 +330,11 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     GATOR_TRY(check_launch("smpl_pose"));
     Epilogue e;
     e.bias = a->v_template;
-    GATOR_TRY(gemm(a->precision, w.aop, KB, a->blend_w, KB, PackedW{a->blend_w_bf16, a->blend_w_bf16_lo}, w.vposed, VP_LD, nb, NV3, KB, e, stream));
+    if (a->precision == GATOR_PREC_BF16X3 && a->blend_w_wide) {
+      GATOR_TRY(gemm_bf16x3_wide(w.aop, KB, a->blend_w_wide, w.aimg, w.aimg_bytes, w.vposed, VP_LD, nb, NV3, KB, e, stream));
+    } else {
+      GATOR_TRY(gemm(a->precision, w.aop, KB, a->blend_w, KB, PackedW{a->blend_w_bf16, a->blend_w_bf16_lo}, w.vposed, VP_LD, nb, NV3, KB, e, stream));
+    }
     dim3 grid(ceil_div(NV, SK_VT), ceil_div(nb, SK_SG));
     smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w,
                                                  a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb, out_scale);

@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from .. import _lib, config, graph
 from ..mesh import Mesh
-from ..packing import pack_umma_weight_pair
+from ..packing import pack_umma_weight_pair, pack_umma_wide
 
 _BF16_GLOBAL = {'JF_WFEAT', 'HEAD_W', 'UP_W'}
 _BF16_LAYER = {'WQ', 'WKV', 'PROJ_W', 'FC1_W', 'FC2_W', 'SQKV_W', 'SO_W'}
@@ -179,6 +179,7 @@ class MDR(nn.Module):
             'UP_BIAST': f(self.upsample_conv.bias[:, None] + self.init_vertices_6890),
         }
         t['CHAIN_FINAL'] = None
+        t['UP_W_WIDE'] = pack_umma_wide(t['UP_W'])
         gnames, lnames = _lib.slot_names('mdr')
         layer_dicts = []
         prev_so = None

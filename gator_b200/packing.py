@@ -35,3 +35,20 @@ def pack_umma_weight_pair(W: torch.Tensor):
     Wf = W.float()
     hi = Wf.to(torch.bfloat16).float()
     return pack_umma_weight(hi), pack_umma_weight(Wf - hi)
+
+
+@torch.no_grad()
+def pack_umma_wide(W: torch.Tensor) -> torch.Tensor:
+    """W (N,K) float -> bf16 [n_tiles, kblocks, 2 (hi|lo), 32, 4, 8, 8] for the wide-N kernel (csrc/umma_gemm_wide.cu):
+    256-row tiles, 32-wide K blocks, 8x8 core matrices; one (tile, block) is a contiguous 32 KB chunk."""
+    N, K = W.shape
+    nt, kb = C.c_int32(), C.c_int32()
+    _lib.check(_lib.lib().gator_umma_wide_layout(N, K, C.byref(nt), C.byref(kb)), 'gator_umma_wide_layout')
+    nt, kb = nt.value, kb.value
+    Wp = torch.zeros((nt * 256, kb * 32), dtype=torch.float32, device=W.device)
+    Wp[:N, :K] = W.float()
+    hi = Wp.to(torch.bfloat16)
+    lo = (Wp - hi.float()).to(torch.bfloat16)
+    both = torch.stack([hi, lo])                                            # (2, N_pad, K_pad)
+    both = both.reshape(2, nt, 32, 8, kb, 4, 8)                             # (h, tile, rg, r, block, kc, e)
+    return both.permute(1, 4, 0, 2, 5, 3, 6).contiguous()                   # (tile, block, h, rg, kc, r, e)

@@ -148,6 +148,8 @@ typedef enum {
   MDR_UP_BIAST,       /* (6890,3)   upsample_conv.bias[:,None] + init_vertices_6890            */
   MDR_CHAIN_FINAL,    /* bf16 blob for the final pass of the fused layer kernel: 2 units x [hi 8 KB | lo 8 KB]: the last
                          layer's selfatt.linears.3 and HEAD_W zero-padded to 64 rows; may be NULL          */
+  MDR_UP_W_WIDE,      /* UP_W as the tile-major split image of the wide-N kernel (gator_umma_wide_layout);
+                         used by GATOR_PREC_BF16X3; may be NULL (then the generic tcgen05 GEMM runs)       */
   MDR_NUM_GLOBAL
 } gator_mdr_global_slot;
 
@@ -232,6 +234,7 @@ typedef struct {
   const float* blend_w;        /* (20670,220) [shapedirs | posedirs | 0] rows = (vertex,xyz) */
   const void* blend_w_bf16;    /* tcgen05-packed bf16 copy of blend_w, or NULL              */
   const void* blend_w_bf16_lo; /* packed residual for GATOR_PREC_BF16X3, or NULL            */
+  const void* blend_w_wide;    /* tile-major split image of blend_w for the wide-N kernel (GATOR_PREC_BF16X3), or NULL */
   const float* v_template;     /* (20670)                                                 */
   const int32_t* skin_idx;     /* (6890, weights_per_vertex) joint ids                    */
   const float* skin_w;         /* (6890, weights_per_vertex)                              */
@@ -372,6 +375,9 @@ typedef struct {
   const float* A;
   const void* W;               /* fp32 (N,K) for GATOR_PREC_FP32; packed bf16 (see below) otherwise */
   const void* W_lo;            /* packed bf16 residual for GATOR_PREC_BF16X3, else NULL   */
+  const void* W_wide;          /* GATOR_PREC_BF16X3 only: tile-major (hi|lo) image for the wide-N kernel, or NULL */
+  void* a_image;               /* workspace for the split image of A when W_wide is used  */
+  size_t a_image_bytes;        /* >= gator_umma_wide_a_bytes(M, K)                        */
   const float* bias;           /* (N) or NULL                                            */
   const float* bias_rows;      /* (bias_period, N) or NULL                               */
   const float* R;              /* (M, ldr) residual or NULL (may alias C)                */
@@ -383,6 +389,12 @@ int gator_gemm(const gator_gemm_args* a, void* stream);
 /* Layout of a bf16 weight packed for the tcgen05 GEMM: W (N,K) is zero-padded to (n_tiles*BN, K_pad) and
  * stored as [N_pad/8][K_pad/8][8][8] bf16 (8x8 core matrices, the UMMA K-major no-swizzle smem image). */
 int gator_umma_weight_layout(int32_t N, int32_t K, int32_t* BN, int32_t* n_tiles, int32_t* K_pad);
+
+/* Wide-N kernel (N in the thousands: upsample_conv, SMPL blend shapes).  W (N,K) is split into bf16 hi / lo and
+ * stored tile-major as [n_tiles][kblocks][hi|lo][32][4][8][8] bf16: 256-row tiles, 32-wide K blocks, 8x8 core
+ * matrices - one (tile, block) is one contiguous 32 KB chunk, fetched by a single TMA bulk copy. */
+int gator_umma_wide_layout(int32_t N, int32_t K, int32_t* n_tiles, int32_t* kblocks);
+size_t gator_umma_wide_a_bytes(int32_t M, int32_t K);
 
 #ifdef __cplusplus
 }

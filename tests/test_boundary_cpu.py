@@ -33,7 +33,7 @@ def test_struct_mirrors_and_slot_names(lib):
     g, b = _lib.slot_names('gat')
     assert g[0] == "EMB_W1" and g[-1] == "CHAIN_PRM" and len(g) == 16 and len(b) == 21
     g, l = _lib.slot_names('mdr')
-    assert g[-1] == "CHAIN_FINAL" and len(g) == 15 and len(l) == 19
+    assert g[-2:] == ["CHAIN_FINAL", "UP_W_WIDE"] and len(g) == 16 and len(l) == 19
     assert lib.gator_gat_workspace_bytes(64, 17, 0) > 0
     assert lib.gator_mdr_workspace_bytes(64, 17, 0) > 0
     assert lib.gator_smpl_workspace_bytes(64) > 0

@@ -60,6 +60,25 @@ def test_gemm_f32(models, M, N, K):
                       W_lo=_lib.ptr(lo), bias=_lib.ptr(bd), bias_rows=_lib.ptr(rd), R=_lib.ptr(Rd), C=_lib.ptr(Cbuf))
     _lib.check(_lib.lib().gator_gemm(a, _lib.stream_ptr()), 'gator_gemm bf16x3')
     assert (Cbuf.cpu().double() - ref).abs().max() < 1e-4 + 1e-4 * ref.abs().max()
+    # wide-N kernel (persistent, TMA-fed, tile-major split images): same contract, generic and bias-only epilogues
+    from gator_b200.packing import pack_umma_wide
+    Ww = pack_umma_wide(W.to(DEV))
+    ws = torch.empty(_lib.lib().gator_umma_wide_a_bytes(M, K), dtype=torch.uint8, device=DEV)
+    Cbuf.fill_(float('nan'))
+    a = _lib.GemmArgs(M=M, N=N, K=K, lda=K, ldw=K, ldc=N, ldr=N, act=1, bias_period=5, precision=2, A=_lib.ptr(Ad), W_wide=_lib.ptr(Ww),
+                      a_image=_lib.ptr(ws), a_image_bytes=ws.numel(), bias=_lib.ptr(bd), bias_rows=_lib.ptr(rd), R=_lib.ptr(Rd),
+                      C=_lib.ptr(Cbuf))
+    _lib.check(_lib.lib().gator_gemm(a, _lib.stream_ptr()), 'gator_gemm wide')
+    assert (Cbuf.cpu().double() - ref).abs().max() < 1e-4 + 1e-4 * ref.abs().max()
+    ldc = (N + 3) // 4 * 4
+    Cpad = torch.full((M, ldc), float('nan'), device=DEV)
+    a = _lib.GemmArgs(M=M, N=N, K=K, lda=K, ldw=K, ldc=ldc, precision=2, A=_lib.ptr(Ad), W_wide=_lib.ptr(Ww), a_image=_lib.ptr(ws),
+                      a_image_bytes=ws.numel(), bias=_lib.ptr(bd), C=_lib.ptr(Cpad))
+    _lib.check(_lib.lib().gator_gemm(a, _lib.stream_ptr()), 'gator_gemm wide (bias only)')
+    ref2 = A.double() @ W.double().t() + bias.double()
+    assert (Cpad[:, :N].cpu().double() - ref2).abs().max() < 1e-4 + 1e-4 * ref2.abs().max()
+    a.a_image_bytes = 16                                     # undersized workspace is refused, not overrun
+    assert _lib.lib().gator_gemm(a, _lib.stream_ptr()) != 0
 
 
 @pytest.mark.parametrize('tag', ['h36m', 'coco'])
