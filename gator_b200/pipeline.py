@@ -11,7 +11,7 @@ class HostPipeline:
     """forward(pose2d_host (B,J,2) pinned) -> (mesh_host (B,6890,3), pose3d_host (B,J,3)) pinned, both fp32."""
 
     def __init__(self, model, batch: int, slice_samples: int = 0):
-        """slice_samples = 0: one MDR workspace chunk per slice (1184 samples on the tensor-core path)."""
+        """slice_samples = 0: 1184 samples per slice (8 x 148 SMs; 98 MB of mesh per device-to-host copy)."""
         p = next(model.parameters())
         self.model, self.dev = model, p.device
         self.J = model.num_joint
@@ -29,7 +29,7 @@ class HostPipeline:
             raise ValueError(f'pipeline was built for batch {self.batch}, got {B}')
         main = torch.cuda.current_stream(self.dev)
         m = self.model
-        step = self.slice_samples or m.pose2mesh._chunk()
+        step = self.slice_samples or 1184
         self._keep.clear()
         # the lifter runs once over the whole batch (its outputs are small: 12 J + 512 J bytes per sample) ...
         xd = pose2d_host.to(self.dev, non_blocking=True)

@@ -318,14 +318,14 @@ def test_host_pipeline_matches_plain_forward(models):
 
 def test_config5_shard_size_tensor_path(models):
     """BASELINE config 5 per-GPU shard (65536 / 8 = 8192 samples) on the tensor-core path: crosses the GAT pass,
-    MDR chunk (1184) and super-chunk boundaries; every sample equals its own batch-1 forward bit for bit."""
+    MDR chunk (4096) and super-chunk (8192) boundaries; every sample equals its own batch-1 forward bit for bit."""
     m = models['coco'].set_precision('bf16x3')
     try:
         base = golden('fixtures')['demo_pose19']
         x = torch.from_numpy(synthetic.coco_poses2d(base, 8192 + 37, seed=4)).to(DEV)
         mesh, p3 = m(x)
         assert torch.isfinite(mesh).all() and torch.isfinite(p3).all()
-        for i in (0, 5, 6, 1183, 1184, 8191, 8192, 8228):
+        for i in (0, 5, 6, 1183, 1184, 4095, 4096, 8191, 8192, 8228):
             mi, pi = m(x[i:i + 1])
             assert torch.equal(mi[0], mesh[i]) and torch.equal(pi[0], p3[i]), i
     finally:

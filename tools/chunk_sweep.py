@@ -5,7 +5,7 @@ import torch
 from helpers import build_b200_gator, golden, synthetic
 m = build_b200_gator('coco', 'cuda:0').set_precision('bf16x3')
 x = torch.from_numpy(synthetic.coco_poses2d(golden('fixtures')['demo_pose19'], 4096)).to('cuda:0')
-for chunk in (74, 148, 222, 296, 444, 592, 1184):
+for chunk in (592, 1036, 1184, 1332, 1480, 2072, 4096):
     m.pose2mesh.chunk = chunk
     for _ in range(2): m(x)
     torch.cuda.synchronize(); t0 = time.perf_counter()
