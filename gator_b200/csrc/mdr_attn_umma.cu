@@ -60,6 +60,7 @@ __device__ __forceinline__ uint4 pack8_residual(const float* v, const uint4& hi)
                     pack_bf16(v[4] - bf16_lo_f(hi.z), v[5] - bf16_hi_f(hi.z)), pack_bf16(v[6] - bf16_lo_f(hi.w), v[7] - bf16_hi_f(hi.w)));
 }
 
+constexpr float kShiftBoundMax = 40.f;   // log2 units; see the shift-bound comment in the kernel
 constexpr int NT = 512;   // 16 warps: (lane quarter 4) x (column quarter 4): 4 threads share a score row
 
 template <bool SPLIT>
@@ -70,6 +71,8 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   __shared__ uint32_t tmem_slot;
   __shared__ float red_max[4][QT];
   __shared__ float red_sum[4][QT];
+  __shared__ float q_norm2[2][QT];        // |q_row|^2 of the staged tile (double-buffered with sQ's prefetch)
+  __shared__ float k_norm2_warp[NT / 32]; // per-warp max |k|^2
   // hi images first, lo images (SPLIT only) after them
   uint8_t* sK = smem;
   uint8_t* sVT = sK + SK_BYTES;
@@ -105,6 +108,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
         kb2[i] = *reinterpret_cast<const float4*>(src + 4);
       }
     }
+    float kmax2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
       const int c = tid + i * NT;
@@ -113,7 +117,15 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
         reinterpret_cast<uint4*>(sK)[c] = hi;
         if (SPLIT) reinterpret_cast<uint4*>(sK + LO)[c] = cvt8_residual(ka[i], kb2[i], hi);
       }
+      // |k|^2: the 4 chunks of a key sit in lanes r, r+8, r+16, r+24 of one warp (zero for padded chunks)
+      float n2 = ka[i].x * ka[i].x + ka[i].y * ka[i].y + ka[i].z * ka[i].z + ka[i].w * ka[i].w +
+                 kb2[i].x * kb2[i].x + kb2[i].y * kb2[i].y + kb2[i].z * kb2[i].z + kb2[i].w * kb2[i].w;
+      n2 += __shfl_xor_sync(0xffffffffu, n2, 8);
+      n2 += __shfl_xor_sync(0xffffffffu, n2, 16);
+      kmax2 = fmaxf(kmax2, n2);
     }
+    kmax2 = warp_max(kmax2);
+    if (lane == 0) k_norm2_warp[warp] = kmax2;
   }
   // ---- stage V^T: warp takes a group of 8 keys, lane = d; chunk (dg, kc, r): d = dg*8 + r ----
   {
@@ -165,10 +177,14 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   };
   load_q(0);
 
-  auto stage_q = [&]() {          // registers (prefetched) -> sQ images
+  auto stage_q = [&](int buf) {   // registers (prefetched) -> sQ images, and |q_row|^2 for the softmax shift bound
     const uint4 hi = cvt8(qa, qb);
     reinterpret_cast<uint4*>(sQ)[tid] = hi;
     if (SPLIT) reinterpret_cast<uint4*>(sQ + LO)[tid] = cvt8_residual(qa, qb, hi);
+    float n2 = qa.x * qa.x + qa.y * qa.y + qa.z * qa.z + qa.w * qa.w + qb.x * qb.x + qb.y * qb.y + qb.z * qb.z + qb.w * qb.w;
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 8);      // chunk (rg, kc, r) = tid: the row's 4 chunks are 8 lanes apart
+    n2 += __shfl_xor_sync(0xffffffffu, n2, 16);
+    if (((tid >> 3) & 3) == 0) q_norm2[buf][(tid >> 5) * 8 + (tid & 7)] = n2;
     fence_proxy_async();
   };
   auto issue_s = [&]() {          // one thread: S = Q K^T into TMEM columns [0, 432), commit -> bar_s
@@ -196,7 +212,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     mma_commit(&bar_s);
   };
   // prologue: S of tile 0
-  stage_q();
+  stage_q(0);
   load_q(1);
   tc_fence_before();
   __syncthreads();
@@ -209,12 +225,23 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     mbar_wait(&bar_s, qt & 1);
     tc_fence_after();
     if (qt + 1 < 4) {             // S(qt) is complete, so sQ is free: stage the next tile now; its S MMA is issued at the
-      stage_q();                  // end of this tile's exp pass and overlaps the last P V MMAs and the O write-out
+      stage_q((qt + 1) & 1);      // end of this tile's exp pass and overlaps the last P V MMAs and the O write-out
       if (qt + 2 < 4) load_q(qt + 2);
     }
 
+    // Softmax is invariant to the per-row shift, so any upper bound of the row maximum serves as long as nothing
+    // underflows: |s_ij| <= |q_i| max_j |k_j| (Cauchy-Schwarz).  With bound b (log2 units) every exponent lies in
+    // [-2b, 0]; for b <= 40 all P values and their bf16 residuals stay normal numbers, the result equals the
+    // max-shifted one to rounding, and the pass over S for the row maximum is skipped.  Decided per tile (CTA-uniform).
+    float kmax2 = k_norm2_warp[0];
+#pragma unroll
+    for (int w = 1; w < NT / 32; ++w) kmax2 = fmaxf(kmax2, k_norm2_warp[w]);
+    const float bound = sqrtf(q_norm2[qt & 1][row] * kmax2) * c_log2 * 1.001f;
+    const bool exact = __syncthreads_or(!(bound <= kShiftBoundMax));
+    float mx = bound;
+    if (exact) {
     // ---- pass 1: row max over this thread's 216 columns ----
-    float mx = -INFINITY;
+    mx = -INFINITY;
     {
       // 13 or 14 chunks of 8 columns: loads issued in batches of up to 7 before one wait
       float s[7][8];
@@ -240,6 +267,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     red_max[cq][row] = mx;
     __syncthreads();
     mx = fmaxf(fmaxf(red_max[0][row], red_max[1][row]), fmaxf(red_max[2][row], red_max[3][row])) * c_log2;
+    }
 
     // ---- pass 2 over 6 key parts: P = exp2(s*c - max*c) -> smem buffer (part & 1), O += P V asynchronously ----
     float sum = 0.f;
