@@ -320,6 +320,14 @@ def test_host_pipeline_matches_plain_forward(models):
     hm, hp = pipe.forward(x)
     torch.cuda.synchronize()
     assert torch.equal(hm, mesh.cpu()) and torch.equal(hp, p3.cpu())
+    # automatic slicing (equal slices + a short last one) at a batch that has a tail, and the empty batch
+    x = torch.from_numpy(synthetic.poses2d(700, 17, seed=10)).pin_memory()
+    mesh, p3 = m(x.to(DEV))
+    hm, hp = HostPipeline(m, 700).forward(x)
+    torch.cuda.synchronize()
+    assert torch.equal(hm, mesh.cpu()) and torch.equal(hp, p3.cpu())
+    hm, hp = HostPipeline(m, 0).forward(x[:0])
+    assert hm.shape == (0, 6890, 3) and hp.shape == (0, 17, 3)
 
 
 def test_config5_shard_size_tensor_path(models):
