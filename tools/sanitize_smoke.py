@@ -1,0 +1,38 @@
+"""Small invocations of every kernel family for compute-sanitizer (memcheck / racecheck):
+    compute-sanitizer --tool memcheck python tools/sanitize_smoke.py"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import numpy as np
+import torch
+from helpers import build_b200_gator, build_b200_smpl, golden, regressor, synthetic
+from gator_b200.evaluate import EvalEpilogue
+from gator_b200.gt_mesh import GtMeshGenerator
+from gator_b200.preprocess import COCO_MID_PAIRS, Pose2DPreprocessor
+
+dev = 'cuda:0'
+which = sys.argv[1] if len(sys.argv) > 1 else 'all'
+if which in ('all', 'gator'):
+    m = build_b200_gator('coco', dev)
+    x = torch.from_numpy(synthetic.coco_poses2d(golden('fixtures')['demo_pose19'], 13)).to(dev)
+    for prec in ('fp32', 'bf16x3'):
+        m.set_precision(prec)
+        mesh, p3 = m(x)
+        torch.cuda.synchronize()
+        print(prec, float(mesh.abs().max()))
+if which in ('all', 'smpl'):
+    layer = build_b200_smpl(device=dev).set_precision('bf16x3')
+    ann = [torch.from_numpy(a).to(dev) for a in synthetic.camera_annotations(9)]
+    v, j = GtMeshGenerator(layer).h36m(*ann)
+    torch.cuda.synchronize()
+    print('gtmesh', float(v.abs().max()))
+if which in ('all', 'eval'):
+    reg = regressor('h36m')
+    pred, gt, gtj = [torch.from_numpy(a).to(dev) for a in synthetic.eval_inputs(7, reg)]
+    r = EvalEpilogue(reg, device=dev)(pred, gt, gtj, pa=True)
+    pose = Pose2DPreprocessor((384, 288), COCO_MID_PAIRS)(torch.from_numpy(golden('preproc')['input'].astype(np.float32)).to(dev))
+    torch.cuda.synchronize()
+    print('eval', float(r.joint_error), float(r.pa_joint_error), float(pose.abs().max()))
