@@ -298,6 +298,38 @@ def run_b200(args):
             kernels.insert(0, {'kernel': 'mdr_chain_kernel<1,J> (tcgen05 fused layer chain)', 'bound': 'tensor', 'achieved': ch_tf,
                                'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': ch_tf / peaks['bf16_tflops'],
                                'launch_ms': ch_ms, 'flops_per_launch': ch_flop})
+        if pcode == 2:
+            # upsample_conv's product on the wide tcgen05 + TMA kernel (bias-only epilogue instead of the conv3 scatter)
+            from gator_b200.packing import pack_umma_wide
+            Mw, Nw, Kw = 3 * 4096, 6890, 1296
+            Aw = torch.randn(Mw, Kw, device=dev)
+            Ww = pack_umma_wide(torch.randn(Nw, Kw, device=dev) / Kw ** 0.5)
+            Cw = torch.empty(Mw, 6892, device=dev)
+            wsw = torch.empty(L.gator_umma_wide_a_bytes(Mw, Kw), dtype=torch.uint8, device=dev)
+            ga = _lib.GemmArgs(M=Mw, N=Nw, K=Kw, lda=Kw, ldw=Kw, ldc=6892, precision=2, A=_lib.ptr(Aw), W_wide=_lib.ptr(Ww),
+                               a_image=_lib.ptr(wsw), a_image_bytes=wsw.numel(), C=_lib.ptr(Cw))
+            wg_ms = time_launch(lambda: _lib.check(L.gator_gemm(ga, s), 'gator_gemm wide'))
+            wg_flop = 2.0 * Mw * Nw * Kw
+            kernels.append({'kernel': 'umma_gemm_wide_kernel (upsample_conv shape, 4096 samples; incl. the A-image pre-pass)',
+                            'bound': 'tensor', 'achieved': wg_flop / (wg_ms * 1e-3) / 1e12, 'peak': peaks['bf16_tflops'],
+                            'unit': 'TFLOP/s', 'frac': wg_flop / (wg_ms * 1e-3) / 1e12 / peaks['bf16_tflops'], 'launch_ms': wg_ms,
+                            'flops_per_launch': wg_flop, 'tensor_flops_issued': 3 * wg_flop,
+                            'frac_issued': 3 * wg_flop / (wg_ms * 1e-3) / 1e12 / peaks['bf16_tflops']})
+            del Aw, Ww, Cw, wsw
+            # evaluation epilogue (row f1): HBM-bound, 2 x 82 680 B read per sample
+            from gator_b200.evaluate import EvalEpilogue
+            from helpers import regressor as _reg
+            ep = EvalEpilogue(_reg('h36m'), device=dev)
+            pm = torch.randn(4096, 6890, 3, device=dev) * 0.3
+            gm = pm + 0.02 * torch.randn_like(pm)
+            gj = torch.randn(4096, 17, 3, device=dev) * 300
+            ev_ms = time_launch(lambda: ep(pm, gm, gj))
+            ev_bytes = 4096 * 2 * 82680
+            kernels.append({'kernel': 'eval_sample_kernel (+ eval_mean_kernel)', 'bound': 'hbm', 'achieved': ev_bytes / (ev_ms * 1e-3) / 1e9,
+                            'peak': peaks.get('hbm_gbs'), 'unit': 'GB/s',
+                            'frac': (ev_bytes / (ev_ms * 1e-3) / 1e9 / peaks['hbm_gbs']) if peaks.get('hbm_gbs') else None,
+                            'launch_ms': ev_ms, 'bytes_per_launch': ev_bytes, 'traffic': 686.8e6})
+            del pm, gm, gj
         roofline = dict(kernels[0])
         # dram__bytes_read.sum + dram__bytes_write.sum of one 592-CTA launch from the committed `ncu --set full` capture
         # (profiles/r01_ncu_full_mdr_chain_kernel.csv; ncu flushes caches, so this is an upper bound of a warm launch)
