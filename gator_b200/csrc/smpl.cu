@@ -153,8 +153,8 @@ smpl_pose_kernel(PoseParams p) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Skinning (smpl_layer.py:134-145).  HBM-bound: per mesh 82 680 B written (v_posed comes from L2, the
-// producer GEMM runs on the same 512-sample chunk).  CTA = 256 consecutive vertices x SG samples, 8 warps;
+// Skinning (smpl_layer.py:134-145).  Memory-bound: per mesh 82 680 B written and 82 680 B of v_posed read back
+// (the producer GEMM runs on the same workspace chunk).  CTA = 256 consecutive vertices x SG samples, 8 warps;
 // the SG x 24 joint transforms are staged once, then every warp runs on its own 32 vertices with no
 // block-level synchronisation: coalesced 8-byte loads of the 96-float v_posed segment -> warp-private
 // shared memory -> lane = vertex (ELL weights in registers, reused across the SG samples) -> warp-private
@@ -246,7 +246,12 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
   }
 }
 
-constexpr int kChunk = 1024;
+// Samples per workspace chunk.  Measured at B = 16384 (bf16x3): 592 -> 2.42 ms, 1024 -> 2.19, 2048 -> 1.91, 4096 -> 1.77,
+// 8192 -> 1.64: the persistent blend-shape GEMM needs many tiles per CTA to fill its waves, and keeping v_posed
+// L2-resident with small chunks does not pay.  (A variant of the skinning kernel that blends the transforms on the
+// tensor cores - T = W_skin G' as a tcgen05 GEMM with the apply step in the epilogue - was built and measured equal
+// to this one within 2 %: both are bound by the v_posed / vertex traffic, so it was not kept.)
+constexpr int kChunk = 8192;
 
 struct Ws {
   float *aop, *amat, *offset, *vposed;

@@ -240,7 +240,7 @@ def test_smpl_layer_matches_reference_golden():
 
 def test_smpl_layer_zero_norm_switches_and_chunks():
     """smpl_layer.py:87,148: all-zero betas fall back to th_betas; all-zero trans enables centring.
-    B=1100 crosses the 1024-sample workspace chunk."""
+    (The 8192-sample workspace chunk boundary is crossed by test_smpl_full_size_properties.)"""
     buf = {k: torch.from_numpy(v) for k, v in synthetic.smpl_buffers().items()}
     buf['th_betas'] = torch.full((1, 10), 0.3)
     from gator_b200.smpl_layer import SMPL_Layer
@@ -275,6 +275,15 @@ def test_smpl_full_size_properties():
     assert (v1 - trans[:, None] - v0).abs().max() <= 1e-5 and (j1 - trans[:, None] - j0).abs().max() <= 1e-5
     zv, _ = layer(torch.zeros(3, 72, device=DEV))
     assert (zv - layer.th_v_template).abs().max() <= 1e-5
+    # the batch spans two 8192-sample workspace chunks: samples on both sides of the boundary equal their own
+    # batch-1 forward bit for bit, on the fp32 and on the tensor-core path
+    for prec in ('fp32', 'bf16x3'):
+        layer.set_precision(prec)
+        vb, jb = layer(pose, betas, trans)
+        for i in (0, 8191, 8192, 16383):
+            vi, ji = layer(pose[i:i + 1], betas[i:i + 1], trans[i:i + 1])
+            assert torch.equal(vi[0], vb[i]) and torch.equal(ji[0], jb[i]), (prec, i)
+    layer.set_precision('fp32')
 
 
 def test_mesh_resampling_matches_reference_golden():

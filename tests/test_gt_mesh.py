@@ -75,7 +75,7 @@ def test_gt_mesh_matches_reference(gen):
 
 @pytest.mark.gpu
 def test_gt_mesh_matches_oracle_and_properties(gen):
-    n = 1100                                                    # crosses the SMPL kernel's 1024-sample chunk
+    n = 1100
     pose, shape, trans, R, t = synthetic.camera_annotations(n, seed=17)
     pose[3, :3] = 0.0                                           # identity root: angle 0 would divide 0/0 in the reference
     pose[3, 0] = 1e-4
