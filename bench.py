@@ -83,7 +83,7 @@ class ClockSampler:
 
 def make_inputs(batch, seed=2):
     import numpy as np
-    from helpers import golden, synthetic
+    from builders import golden, synthetic
     base = golden('fixtures')['demo_pose19']
     return synthetic.coco_poses2d(base, batch, seed=seed)
 
@@ -153,7 +153,7 @@ def run_b200(args):
         dist.init_process_group('nccl', device_id=dev)
     from gator_b200 import _lib
     from gator_b200.dist import shard_range
-    from helpers import build_b200_gator
+    from builders import build_b200_gator
     L = _lib.lib()
     model = build_b200_gator(TAG, dev).set_precision(args.precision)
     J = model.num_joint
@@ -170,6 +170,12 @@ def run_b200(args):
 
     # ---- device-resident throughput ----
     with torch.no_grad():
+        t_ramp = time.perf_counter()                       # untimed: first call packs the weights, then ~0.4 s of
+        while True:                                        # forwards so that the SM clock has ramped before the W
+            model(x)                                       # warm-up steps the contract asks for
+            torch.cuda.synchronize()
+            if time.perf_counter() - t_ramp > 0.4:
+                break
         for _ in range(args.warmup):
             model(x)
         barrier()
@@ -204,7 +210,8 @@ def run_b200(args):
     with torch.no_grad():
         def e2e_step():
             pipe.forward(x_host)
-        e2e_step()
+        for _ in range(max(args.warmup, 1)):
+            e2e_step()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -318,7 +325,7 @@ def run_b200(args):
             del Aw, Ww, Cw, wsw
             # evaluation epilogue (row f1): HBM-bound, 2 x 82 680 B read per sample
             from gator_b200.evaluate import EvalEpilogue
-            from helpers import regressor as _reg
+            from builders import regressor as _reg
             ep = EvalEpilogue(_reg('h36m'), device=dev)
             pm = torch.randn(4096, 6890, 3, device=dev) * 0.3
             gm = pm + 0.02 * torch.randn_like(pm)

@@ -1,5 +1,6 @@
+"""Development probe (accuracy of the tensor-core paths against the CPU oracle); lives under tests/ because it uses the oracle."""
 import sys, os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 from gator_b200 import _lib

@@ -1,6 +1,6 @@
 """GPU probe: bf16 (tcgen05) path vs fp32 path vs CPU oracle - attention kernel error, end-to-end drift, timing."""
 import sys, os, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np, torch
 from gator_b200 import _lib

@@ -79,6 +79,25 @@ def test_no_cpu_fallback():
         s(torch.zeros(1, 72))
 
 
+def test_product_and_tools_never_touch_the_oracle():
+    """The oracle is test infrastructure: nothing under gator_b200/ or tools/ may import it, and bench.py only inside
+    its checker legs (cpu_baseline / parity / --impl reference)."""
+    import glob
+    import os
+    import re
+    from builders import ROOT
+    pat = re.compile(r'^\s*(from|import)\s+(oracle|helpers)\b|gator_oracle|refshim', re.M)
+    files = glob.glob(os.path.join(ROOT, 'gator_b200', '**', '*.py'), recursive=True) + glob.glob(os.path.join(ROOT, 'tools', '*.py'))
+    assert files
+    for f in files:
+        assert not pat.search(open(f).read()), f
+    bench = open(os.path.join(ROOT, 'bench.py')).read()
+    top_level = [l for l in bench.splitlines() if re.match(r'(from|import)\s+(oracle|helpers)\b', l)]
+    assert not top_level, top_level
+    for f in glob.glob(os.path.join(ROOT, 'gator_b200', 'csrc', '*')):
+        assert 'oracle' not in open(f, errors='ignore').read().lower() or f.endswith('.md'), f
+
+
 def test_unsupported_configurations_fail_loudly():
     from gator_b200.models import GAT
     with pytest.raises(NotImplementedError):

@@ -2,7 +2,7 @@ import sys, os, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
-from helpers import build_b200_gator, golden, synthetic
+from builders import build_b200_gator, golden, synthetic
 m = build_b200_gator('coco', 'cuda:0').set_precision('bf16x3')
 x = torch.from_numpy(synthetic.coco_poses2d(golden('fixtures')['demo_pose19'], 4096)).to('cuda:0')
 for chunk in (592, 1036, 1184, 1332, 1480, 2072, 4096):

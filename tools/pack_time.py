@@ -1,7 +1,7 @@
 import sys, time
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import torch
-from helpers import build_b200_gator, build_b200_smpl
+from builders import build_b200_gator, build_b200_smpl
 m = build_b200_gator('coco', 'cuda:0').set_precision('bf16x3')
 torch.cuda.synchronize()
 for name, mod in (('GAT', m.pose_lifter), ('MDR', m.pose2mesh)):

@@ -1,7 +1,7 @@
 import sys, os
 sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
 import torch, time
-from helpers import build_b200_gator, golden, synthetic
+from builders import build_b200_gator, golden, synthetic
 from gator_b200.pipeline import HostPipeline
 m = build_b200_gator('coco', 'cuda:0').set_precision('bf16x3')
 x = torch.from_numpy(synthetic.coco_poses2d(golden('fixtures')['demo_pose19'], 4096)).pin_memory()

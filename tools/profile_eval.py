@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 import torch
-from helpers import golden, regressor
+from builders import golden, regressor
 from gator_b200.evaluate import EvalEpilogue
 from gator_b200.preprocess import COCO_MID_PAIRS, Pose2DPreprocessor
 
@@ -72,7 +72,7 @@ ms = timed(lambda: pre(x1), iters=50)
 print(json.dumps({'kernel': 'pose2d_preprocess_kernel', 'batch': 1, 'ms': ms}))
 
 # ground-truth mesh generation (row f2): batched get_smpl_coord, camera fix-up + SMPL forward in mm
-from helpers import build_b200_smpl, synthetic
+from builders import build_b200_smpl, synthetic
 from gator_b200.gt_mesh import GtMeshGenerator
 Bg = 16384
 gen = GtMeshGenerator(build_b200_smpl(device=dev).set_precision('bf16x3'))

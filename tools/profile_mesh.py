@@ -3,7 +3,7 @@ import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
-from helpers import base_data_root, regressor
+from builders import base_data_root, regressor
 from gator_b200.mesh import Mesh
 from gator_b200.ops import JointRegressor
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096

@@ -3,7 +3,7 @@ import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
-from helpers import build_b200_gator, golden, synthetic
+from builders import build_b200_gator, golden, synthetic
 prec = sys.argv[1] if len(sys.argv) > 1 else 'bf16x3'
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
 m = build_b200_gator('coco', 'cuda:0').set_precision(prec)

@@ -8,7 +8,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import numpy as np
 import torch
-from helpers import build_b200_gator, build_b200_smpl, golden, regressor, synthetic
+from builders import build_b200_gator, build_b200_smpl, golden, regressor, synthetic
 from gator_b200.evaluate import EvalEpilogue
 from gator_b200.gt_mesh import GtMeshGenerator
 from gator_b200.preprocess import COCO_MID_PAIRS, Pose2DPreprocessor

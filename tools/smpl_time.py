@@ -3,7 +3,7 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
-from helpers import build_b200_smpl, synthetic
+from builders import build_b200_smpl, synthetic
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 P, Bt, T = [torch.from_numpy(a).to('cuda:0') for a in synthetic.smpl_inputs(B)]
 for prec in ('bf16x3', 'fp32'):
