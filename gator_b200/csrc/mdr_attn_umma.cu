@@ -65,7 +65,7 @@ constexpr int NT = 512;   // 16 warps: (lane quarter 4) x (column quarter 4): 4 
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(NT, 1)
-mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
+mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out, int qsplit) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar_s, bar_p[2];
   __shared__ uint32_t tmem_slot;
@@ -81,7 +81,11 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   constexpr int LO = SK_BYTES + SVT_BYTES + SQ_BYTES + SP_BYTES;   // offset of the residual images
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int b = blockIdx.x >> 1, h = blockIdx.x & 1;
+  // qsplit = 1: one CTA per (sample, head) runs all 4 query tiles; qsplit = 4 (small batches): one CTA per query tile, so
+  // that a batch-1 forward uses 8 SMs instead of 2 (K and V are then staged by each of the 4 CTAs)
+  const int bh = blockIdx.x / qsplit;
+  const int b = bh >> 1, h = bh & 1;
+  const int tiles = 4 / qsplit, qt_begin = (blockIdx.x - bh * qsplit) * tiles, qt_end = qt_begin + tiles;
   const float* base = qkv + (size_t)b * V * 3 * E;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
@@ -175,7 +179,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
       qb = *reinterpret_cast<const float4*>(src + 4);
     }
   };
-  load_q(0);
+  load_q(qt_begin);
 
   auto stage_q = [&](int buf) {   // registers (prefetched) -> sQ images, and |q_row|^2 for the softmax shift bound
     const uint4 hi = cvt8(qa, qb);
@@ -213,7 +217,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
   };
   // prologue: S of tile 0
   stage_q(0);
-  load_q(1);
+  if (tiles > 1) load_q(qt_begin + 1);
   tc_fence_before();
   __syncthreads();
   if (tid == 0) {
@@ -221,12 +225,13 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     issue_s();
   }
 
-  for (int qt = 0; qt < 4; ++qt) {
-    mbar_wait(&bar_s, qt & 1);
+  for (int qt = qt_begin; qt < qt_end; ++qt) {
+    const int it = qt - qt_begin;
+    mbar_wait(&bar_s, it & 1);
     tc_fence_after();
-    if (qt + 1 < 4) {             // S(qt) is complete, so sQ is free: stage the next tile now; its S MMA is issued at the
-      stage_q((qt + 1) & 1);      // end of this tile's exp pass and overlaps the last P V MMAs and the O write-out
-      if (qt + 2 < 4) load_q(qt + 2);
+    if (qt + 1 < qt_end) {        // S(qt) is complete, so sQ is free: stage the next tile now; its S MMA is issued at the
+      stage_q((it + 1) & 1);      // end of this tile's exp pass and overlaps the last P V MMAs and the O write-out
+      if (qt + 2 < qt_end) load_q(qt + 2);
     }
 
     // Softmax is invariant to the per-row shift, so any upper bound of the row maximum serves as long as nothing
@@ -236,7 +241,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     float kmax2 = k_norm2_warp[0];
 #pragma unroll
     for (int w = 1; w < NT / 32; ++w) kmax2 = fmaxf(kmax2, k_norm2_warp[w]);
-    const float bound = sqrtf(q_norm2[qt & 1][row] * kmax2) * c_log2 * 1.001f;
+    const float bound = sqrtf(q_norm2[it & 1][row] * kmax2) * c_log2 * 1.001f;
     const bool exact = __syncthreads_or(!(bound <= kShiftBoundMax));
     float mx = bound;
     if (exact) {
@@ -323,7 +328,7 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
           }
         }
         mma_commit(&bar_p[pb]);
-        if (part == PARTS - 1 && qt + 1 < 4) issue_s();    // every thread has finished reading S(qt) (barrier above)
+        if (part == PARTS - 1 && qt + 1 < qt_end) issue_s();    // every thread has finished reading S(qt) (barrier above)
       }
     }
     // both P buffers' last MMAs (parts 3, 4) complete => O is final
@@ -361,8 +366,9 @@ int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cuda
     cudaFuncSetAttribute(mdr_self_attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(false));
     cudaFuncSetAttribute(mdr_self_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true));
   }
-  if (split) mdr_self_attn_umma_kernel<true><<<nb * 2, NT, smem_bytes(true), stream>>>(qkv, out);
-  else mdr_self_attn_umma_kernel<false><<<nb * 2, NT, smem_bytes(false), stream>>>(qkv, out);
+  const int qsplit = nb * 2 * 4 <= 160 ? 4 : 1;     // up to 20 samples: one CTA per query tile still fits one wave
+  if (split) mdr_self_attn_umma_kernel<true><<<nb * 2 * qsplit, NT, smem_bytes(true), stream>>>(qkv, out, qsplit);
+  else mdr_self_attn_umma_kernel<false><<<nb * 2 * qsplit, NT, smem_bytes(false), stream>>>(qkv, out, qsplit);
   return check_launch("mdr_self_attn_umma");
 }
 
