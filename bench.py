@@ -152,7 +152,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     from gator_b200 import _lib
-    from gator_b200.dist import shard_range
+    from gator_b200.dist import bind_to_gpu_numa_node, shard_range
+    numa_node = bind_to_gpu_numa_node(local)              # before any pinned buffer is allocated
     from builders import build_b200_gator
     L = _lib.lib()
     model = build_b200_gator(TAG, dev).set_precision(args.precision)
@@ -369,7 +370,7 @@ def run_b200(args):
                         'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': int((mesh_host.numel() + p3_host.numel()) * 4)},
                 'gpu_launches': int(launches),
                 'tflops_effective': FLOP_PER_MESH * value / 1e12,
-                'wall_s_timed_region': t_wall,
+                'numa_node': numa_node, 'wall_s_timed_region': t_wall,
                 'latency_b1': latency,
                 'roofline': roofline, 'parity': parity,
                 'cpu_baseline': {'value': cpu_v, 'unit': UNIT, 'cores': threads, 'kind': 'port',

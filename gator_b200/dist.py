@@ -29,3 +29,30 @@ def gather_meshes(local_mesh, total: int, group=None):
     out = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(out, pad, group=group)
     return torch.cat([o[:hi - lo] for o, (lo, hi) in zip(out, sizes)], 0)
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process to the CPU cores of the NUMA node the GPU hangs off, so that pinned host buffers allocated
+    afterwards are local to the GPU's PCIe root (with 8 ranks per node, device-to-host copies otherwise cross sockets).
+    Best effort: returns the node id, or None when the topology cannot be read."""
+    import os
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(device_index)
+        bus = f'{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0'
+        with open(f'/sys/bus/pci/devices/{bus}/numa_node') as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f'/sys/devices/system/node/node{node}/cpulist') as f:
+            cpus = set()
+            for part in f.read().strip().split(','):
+                lo, _, hi = part.partition('-')
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
