@@ -46,7 +46,7 @@ class SmplArgs(C.Structure):
                 ('default_betas', C.c_void_p), ('blend_w', C.c_void_p), ('blend_w_bf16', C.c_void_p), ('blend_w_bf16_lo', C.c_void_p),
                 ('blend_w_wide', C.c_void_p),
                 ('v_template', C.c_void_p),
-                ('skin_idx', C.c_void_p), ('skin_w', C.c_void_p), ('pose', C.c_void_p), ('betas', C.c_void_p),
+                ('skin_idx', C.c_void_p), ('skin_w', C.c_void_p), ('skin_w_img', C.c_void_p), ('pose', C.c_void_p), ('betas', C.c_void_p),
                 ('trans', C.c_void_p), ('verts', C.c_void_p), ('jtr', C.c_void_p),
                 ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
 

@@ -70,6 +70,11 @@ size_t wide_a_image_bytes(int M, int K);
 int gemm_bf16x3_wide(const float* A, int lda, const void* Wimg, void* a_img, size_t a_img_bytes, float* C, int ldc,
                      int M, int N, int K, const Epilogue& epi, cudaStream_t stream);
 
+// SMPL skinning with the transform blend on the tensor cores (csrc/smpl_skin_umma.cu), GATOR_PREC_BF16X3 only
+size_t skin_t_image_bytes(int S);
+int launch_smpl_skin_umma(const float* vposed, int ld, const float* amat, const float* offset, const void* Wimg, void* timg,
+                          float* verts, int S, float scale, cudaStream_t stream);
+
 // precision dispatch used by the stage drivers: bf16 only if a packed weight exists for the slot
 struct PackedW {
   const void* hi = nullptr;

@@ -164,6 +164,7 @@ smpl_pose_kernel(PoseParams p) {
 // ---------------------------------------------------------------------------------------------
 constexpr int SK_VT = 256;
 constexpr int SK_SG = 16;
+constexpr int SK_PD = 4;    // prefetch depth (samples)
 
 __global__ void __launch_bounds__(SK_VT)
 smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ amat, const float* __restrict__ offset,
@@ -196,21 +197,28 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
   const int seg2 = nvw * 3 / 2;                            // float2 per segment (nvw*3 is even: 96 or 42)
   float* st = stage[warp];
   auto seg_ptr = [&](const float* base, int s, int ld) { return base + (size_t)(s_begin + s) * ld + (size_t)v0w * 3; };
-  float2 pre0 = make_float2(0.f, 0.f), pre1 = pre0;
-  {
-    const float2* src = reinterpret_cast<const float2*>(seg_ptr(vposed, 0, VP_LD));
-    if (lane < seg2) pre0 = src[lane];
-    if (lane + 32 < seg2) pre1 = src[lane + 32];
-  }
-  for (int s = 0; s < ns; ++s) {
-    __syncwarp();                                          // previous iteration's readers of `st` are done
-    reinterpret_cast<float2*>(st)[lane] = pre0;
-    if (lane < 16) reinterpret_cast<float2*>(st)[lane + 32] = pre1;
-    if (s + 1 < ns) {
-      const float2* src = reinterpret_cast<const float2*>(seg_ptr(vposed, s + 1, VP_LD));
-      if (lane < seg2) pre0 = src[lane];
-      if (lane + 32 < seg2) pre1 = src[lane + 32];
+  // v_posed segments are requested SK_PD samples ahead: with one sample in flight per warp the kernel was bound by
+  // memory latency (~16 KB outstanding per SM), not by bandwidth
+  float2 pa[SK_PD], pb[SK_PD];
+  auto request = [&](int s, int slot) {
+    pa[slot] = pb[slot] = make_float2(0.f, 0.f);
+    if (s < ns) {
+      const float2* src = reinterpret_cast<const float2*>(seg_ptr(vposed, s, VP_LD));
+      if (lane < seg2) pa[slot] = src[lane];
+      if (lane + 32 < seg2) pb[slot] = src[lane + 32];
     }
+  };
+#pragma unroll
+  for (int u = 0; u < SK_PD; ++u) request(u, u);
+  for (int s0 = 0; s0 < ns; s0 += SK_PD) {
+#pragma unroll
+  for (int u = 0; u < SK_PD; ++u) {
+    const int s = s0 + u;
+    if (s >= ns) break;                                    // warp-uniform
+    __syncwarp();                                          // previous iteration's readers of `st` are done
+    reinterpret_cast<float2*>(st)[lane] = pa[u];
+    if (lane < 16) reinterpret_cast<float2*>(st)[lane + 32] = pb[u];
+    request(s + SK_PD, u);
     __syncwarp();
     float o0 = 0.f, o1 = 0.f, o2 = 0.f;
     if (active) {
@@ -244,6 +252,7 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
     if (lane < seg2) dst[lane] = reinterpret_cast<const float2*>(st)[lane];
     if (lane + 32 < seg2) dst[lane + 32] = reinterpret_cast<const float2*>(st)[lane + 32];
   }
+  }
 }
 
 // Samples per workspace chunk.  Measured at B = 16384 (bf16x3): 592 -> 2.42 ms, 1024 -> 2.19, 2048 -> 1.91, 4096 -> 1.77,
@@ -257,6 +266,7 @@ struct Ws {
   float *aop, *amat, *offset, *vposed;
   void* aimg;               // split bf16 image of aop for the wide-N blend-shape GEMM
   size_t aimg_bytes;
+  void* timg;               // transform tile image for the tensor-core skinning
   int* flags;
   size_t bytes;
 };
@@ -272,6 +282,7 @@ Ws carve(char* base, int nb) {
   w.vposed = reinterpret_cast<float*>(take((size_t)nb * VP_LD * 4));
   w.aimg_bytes = wide_a_image_bytes(nb, KB);
   w.aimg = take(w.aimg_bytes);
+  w.timg = take(skin_t_image_bytes(nb));
   w.bytes = off;
   return w;
 }
@@ -340,10 +351,15 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     } else {
       GATOR_TRY(gemm(a->precision, w.aop, KB, a->blend_w, KB, PackedW{a->blend_w_bf16, a->blend_w_bf16_lo}, w.vposed, VP_LD, nb, NV3, KB, e, stream));
     }
-    dim3 grid(ceil_div(NV, SK_VT), ceil_div(nb, SK_SG));
-    smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w,
-                                                 a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb, out_scale);
-    GATOR_TRY(check_launch("smpl_skin"));
+    if (a->precision == GATOR_PREC_BF16X3 && a->skin_w_img) {
+      GATOR_TRY(launch_smpl_skin_umma(w.vposed, VP_LD, w.amat, w.offset, a->skin_w_img, w.timg, a->verts + (size_t)b0 * NV3, nb,
+                                      out_scale, stream));
+    } else {
+      dim3 grid(ceil_div(NV, SK_VT), ceil_div(nb, SK_SG));
+      smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w,
+                                                   a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb, out_scale);
+      GATOR_TRY(check_launch("smpl_skin"));
+    }
   }
   return GATOR_OK;
 }

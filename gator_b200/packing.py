@@ -52,3 +52,18 @@ def pack_umma_wide(W: torch.Tensor) -> torch.Tensor:
     both = torch.stack([hi, lo])                                            # (2, N_pad, K_pad)
     both = both.reshape(2, nt, 32, 8, kb, 4, 8)                             # (h, tile, rg, r, block, kc, e)
     return both.permute(1, 4, 0, 2, 5, 3, 6).contiguous()                   # (tile, block, h, rg, kc, r, e)
+
+
+@torch.no_grad()
+def pack_umma_wide_a(W: torch.Tensor) -> torch.Tensor:
+    """W (M,K) float -> bf16 [m_tiles, kblocks, 2 (hi|lo), 16, 4, 8, 8]: the 128-row (M-side) tile image of the wide
+    kernels - the layout csrc/umma_gemm_wide.cu's wide_a_image_kernel produces for activations, here for a constant
+    operand (the SMPL skinning weights of csrc/smpl_skin_umma.cu)."""
+    M, K = W.shape
+    mt, kb = (M + 127) // 128, (K + 31) // 32
+    Wp = torch.zeros((mt * 128, kb * 32), dtype=torch.float32, device=W.device)
+    Wp[:M, :K] = W.float()
+    hi = Wp.to(torch.bfloat16)
+    lo = (Wp - hi.float()).to(torch.bfloat16)
+    both = torch.stack([hi, lo]).reshape(2, mt, 16, 8, kb, 4, 8)            # (h, tile, rg, r, block, kc, e)
+    return both.permute(1, 4, 0, 2, 5, 3, 6).contiguous()                   # (tile, block, h, rg, kc, r, e)

@@ -18,7 +18,7 @@ import torch
 from torch.nn import Module
 
 from . import _lib
-from .packing import pack_umma_weight_pair, pack_umma_wide
+from .packing import pack_umma_weight_pair, pack_umma_wide, pack_umma_wide_a
 
 N_JOINTS, N_VERTS, K_BLEND = 24, 6890, 220
 
@@ -123,6 +123,7 @@ class SMPL_Layer(Module):
             'betas_nonzero': bool((self.th_betas != 0).any().item()),
             'blend_w': blend, 'blend_w_bf16': pack_umma_weight_pair(blend), 'blend_w_wide': pack_umma_wide(blend), 'v_template': self.th_v_template.reshape(-1).float().contiguous(),
             'skin_idx': idx.to(torch.int32).contiguous(), 'skin_w': skin_w.float().contiguous(),
+            'skin_w_img': pack_umma_wide_a(W.float()),
         }
         return self
 
@@ -160,7 +161,8 @@ class SMPL_Layer(Module):
                           parents=_lib.ptr(p['parents']), j_template=_lib.ptr(p['j_template']),
                           j_shapedirs=_lib.ptr(p['j_shapedirs']), default_betas=_lib.ptr(p['default_betas']),
                           blend_w=_lib.ptr(p['blend_w']), blend_w_bf16=_lib.ptr(p['blend_w_bf16'][0]), blend_w_bf16_lo=_lib.ptr(p['blend_w_bf16'][1]), blend_w_wide=_lib.ptr(p['blend_w_wide']), v_template=_lib.ptr(p['v_template']),
-                          skin_idx=_lib.ptr(p['skin_idx']), skin_w=_lib.ptr(p['skin_w']), pose=_lib.ptr(pose),
+                          skin_idx=_lib.ptr(p['skin_idx']), skin_w=_lib.ptr(p['skin_w']), skin_w_img=_lib.ptr(p['skin_w_img']),
+                          pose=_lib.ptr(pose),
                           betas=_lib.ptr(betas), trans=_lib.ptr(trans), verts=_lib.ptr(verts), jtr=_lib.ptr(jtr),
                           workspace=_lib.ptr(self._ws), workspace_bytes=self._ws.numel())
         with torch.cuda.device(dev):

@@ -238,6 +238,8 @@ typedef struct {
   const float* v_template;     /* (20670)                                                 */
   const int32_t* skin_idx;     /* (6890, weights_per_vertex) joint ids                    */
   const float* skin_w;         /* (6890, weights_per_vertex)                              */
+  const void* skin_w_img;      /* dense th_weights (6890,24) as the 128-row tile image of the tensor-core skinning
+                                  kernel ([54][hi|lo][16][4][8][8] bf16, K padded to 32); GATOR_PREC_BF16X3, or NULL */
   const float* pose;           /* (B,72) axis-angle                                       */
   const float* betas;          /* (B,10) or NULL                                          */
   const float* trans;          /* (B,3) or NULL                                           */
