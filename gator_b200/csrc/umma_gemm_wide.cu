@@ -9,15 +9,15 @@
 //   W image [n_tile][k_block][hi|lo][32 row groups][4 k-cores][8 rows][8 k]   32 KB per (tile, block)
 // (8x8 core matrices, K-major, no swizzle: LBO 128 B between K-adjacent cores, SBO 512 B between row groups).
 //
-// CTA = 6 warps, one CTA per SM, looping over 128 x 256 output tiles (m fastest, so concurrently running CTAs
+// CTA = 10 warps, one CTA per SM, looping over 128 x 256 output tiles (m fastest, so concurrently running CTAs
 // share W tiles in L2):
 //   warp 0    producer: waits for a free stage, arms its mbarrier with the byte count, issues the two bulk copies
 //   warp 1    MMA: waits for a full stage, issues 2 k-steps x 3 tcgen05.mma (128x256x16), commits the stage back
 //             to the producer; after the last K block commits the accumulator to the epilogue
-//   warps 2-5 epilogue: TMEM -> registers -> shared-memory transpose -> coalesced stores (+bias / conv3 scatter),
-//             then hand the accumulator buffer back.  Two 256-column accumulators (all 512 TMEM columns) let the
+//   warps 2-9 epilogue (two groups of four warps taking alternate 32-column slabs): TMEM -> registers -> shared-memory
+//             transpose -> coalesced stores (+bias / conv3 scatter), then hand the accumulator buffer back.  Two 256-column accumulators (all 512 TMEM columns) let the
 //             epilogue of tile i overlap the main loop of tile i+1.
-// 4 stages x 48 KB = 192 KB of operand ring + 17 KB staging.
+// 4 stages x 48 KB = 192 KB of operand ring + 2 x 16 KB staging.
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -31,8 +31,10 @@ constexpr int A_HALF = WBM * WBK * 2;                  // 8 KB: hi or lo of an A
 constexpr int W_HALF = WBN * WBK * 2;                  // 16 KB
 constexpr int A_STAGE = 2 * A_HALF, W_STAGE = 2 * W_HALF;
 constexpr int STAGE_BYTES = A_STAGE + W_STAGE;         // 48 KB
-constexpr int STG_LD = 36;                             // floats per staged row: 16-byte aligned, conflict-free float4
-constexpr int WIDE_SMEM = WSTAGES * STAGE_BYTES + WBM * STG_LD * 4;
+constexpr int STG_LD = 32;                             // floats per staged row; 16-byte chunks are XOR-swizzled by the row
+constexpr int EPI_GROUPS = 2;                          // epilogue warp groups (4 warps each), alternating 32-column slabs
+constexpr int WIDE_SMEM = WSTAGES * STAGE_BYTES + EPI_GROUPS * WBM * STG_LD * 4;
+constexpr int WIDE_THREADS = (2 + 4 * EPI_GROUPS) * 32;
 
 struct WideParams {
   const uint8_t* Aimg;
@@ -67,21 +69,24 @@ wide_a_image_kernel(const float* __restrict__ A, int lda, int M, int K, int kblo
   dst[A_HALF / 16] = cvt8_residual(a, b, hi);
 }
 
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar(int group) { asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory"); }
+// staged element (row, col): rows are 32 floats, the 16-byte chunk index is XORed with the row so that both the row-wise
+// float4 writes (8 lanes = 8 rows) and the row-segment reads (8 lanes = 8 chunks of one row) are bank-conflict free
+__device__ __forceinline__ int stg_idx(int r, int col) { return r * STG_LD + ((((col >> 2) ^ r) & 7) << 2) + (col & 3); }
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(WIDE_THREADS, 1)
 umma_gemm_wide_kernel(WideParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[WSTAGES], empty[WSTAGES], acc_full[2], acc_empty[2];
   __shared__ uint32_t tmem_slot;
-  float* stg = reinterpret_cast<float*>(smem + WSTAGES * STAGE_BYTES);
+  float* stg_all = reinterpret_cast<float*>(smem + WSTAGES * STAGE_BYTES);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int s = 0; s < WSTAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
-    mbar_init(&acc_empty[0], 128); mbar_init(&acc_empty[1], 128);
+    mbar_init(&acc_empty[0], 128 * EPI_GROUPS); mbar_init(&acc_empty[1], 128 * EPI_GROUPS);
     mbar_init_fence();
   }
   tc_fence_before();
@@ -135,9 +140,12 @@ umma_gemm_wide_kernel(WideParams p) {
       }
     }
   } else {
-    const int et = tid - 64;                           // 0..127
+    const int grp = (warp - 2) >> 2;                   // epilogue group: slabs grp, grp + EPI_GROUPS, ...
+    const int gw = (warp - 2) & 3;                     // warp within the group
+    const int et = gw * 32 + lane;                     // 0..127 within the group
     const int q = warp & 3;                            // this warp's TMEM lane quarter
     const int row = q * 32 + lane;
+    float* stg = stg_all + grp * WBM * STG_LD;
     const Epilogue& e = p.epi;
     int ti = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++ti) {
@@ -146,16 +154,16 @@ umma_gemm_wide_kernel(WideParams p) {
       const int buf = ti & 1;
       mbar_wait(&acc_full[buf], (ti >> 1) & 1);
       tc_fence_after();
-      for (int slab = 0; slab < WBN / 32; ++slab) {
+      for (int slab = grp; slab < WBN / 32; slab += EPI_GROUPS) {
         const int nb = n0 + slab * 32;
-        if (nb >= p.N) break;                          // uniform over the CTA
+        if (nb >= p.N) break;                          // uniform over the group
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * WBN + slab * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(stg + row * STG_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        epi_bar();
+          *reinterpret_cast<float4*>(stg + stg_idx(row, j)) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        epi_bar(grp);
         if (e.conv3) {
           // rows are (b, t) = (m / 3, m % 3); for one b the 32 columns x 3 taps are 96 contiguous floats of C
           const int b_first = m0 / 3;
@@ -165,19 +173,19 @@ umma_gemm_wide_kernel(WideParams p) {
             const int no = rem / 3, tt = rem - no * 3;
             const int m = (b_first + bl) * 3 + tt, r = m - m0, n = nb + no;
             if (r >= 0 && r < WBM && m < p.M && n < p.N)
-              p.C[((size_t)(b_first + bl) * p.N + n) * 3 + tt] = stg[r * STG_LD + no] + __ldg(e.bias_rows + (size_t)n * 3 + tt);
+              p.C[((size_t)(b_first + bl) * p.N + n) * 3 + tt] = stg[stg_idx(r, no)] + __ldg(e.bias_rows + (size_t)n * 3 + tt);
           }
         } else if (p.vec) {
           // 8 lanes x float4 = one 128-byte row segment; a warp stores 4 rows per instruction
           const int c4 = (lane & 7) * 4, n = nb + c4;
-          const int rs = (warp - 2) * 4 + (lane >> 3);
+          const int rs = gw * 4 + (lane >> 3);
           if (n + 3 < p.N) {
             const float4 bn = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
             for (int i = 0; i < WBM / 16; ++i) {
               const int r = rs + i * 16, m = m0 + r;
               if (m < p.M) {
-                float4 x = *reinterpret_cast<const float4*>(stg + r * STG_LD + c4);
+                float4 x = *reinterpret_cast<const float4*>(stg + stg_idx(r, c4));
                 x.x += bn.x; x.y += bn.y; x.z += bn.z; x.w += bn.w;
                 *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = x;
               }
@@ -186,18 +194,18 @@ umma_gemm_wide_kernel(WideParams p) {
             for (int i = 0; i < WBM / 16; ++i) {
               const int r = rs + i * 16, m = m0 + r;
               for (int j = 0; j < 4; ++j)
-                if (m < p.M && n + j < p.N) p.C[(size_t)m * p.ldc + n + j] = stg[r * STG_LD + c4 + j] + (e.bias ? __ldg(e.bias + n + j) : 0.f);
+                if (m < p.M && n + j < p.N) p.C[(size_t)m * p.ldc + n + j] = stg[stg_idx(r, c4 + j)] + (e.bias ? __ldg(e.bias + n + j) : 0.f);
             }
           }
         } else {
           const int n = nb + lane;
-          const int ew = warp - 2;
+          const int ew = gw;
           if (n < p.N) {
             const float bn = e.bias ? __ldg(e.bias + n) : 0.f;
             for (int r = ew; r < WBM; r += 4) {
               const int m = m0 + r;
               if (m >= p.M) break;
-              float x = stg[r * STG_LD + lane] + bn;
+              float x = stg[stg_idx(r, lane)] + bn;
               if (e.bias_rows) x += __ldg(e.bias_rows + (size_t)(m % e.bias_period) * p.N + n);
               if (e.act == 1) x = gelu_erf(x);
               if (e.R) x += e.R[(size_t)m * e.ldr + n];
@@ -205,7 +213,7 @@ umma_gemm_wide_kernel(WideParams p) {
             }
           }
         }
-        epi_bar();
+        epi_bar(grp);
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[buf]);
@@ -258,7 +266,7 @@ int gemm_bf16x3_wide(const float* A, int lda, const void* Wimg, void* a_img, siz
   }
   const int sms = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
   const int total = p.m_tiles * p.n_tiles;
-  umma_gemm_wide_kernel<<<total < sms ? total : sms, 192, WIDE_SMEM, stream>>>(p);
+  umma_gemm_wide_kernel<<<total < sms ? total : sms, WIDE_THREADS, WIDE_SMEM, stream>>>(p);
   return check_launch("umma_gemm_wide");
 }
 
