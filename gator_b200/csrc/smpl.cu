@@ -3,7 +3,8 @@
 //                         one warp per sample, lane = joint, tree walked level by level with shuffles.
 //   K3b blend shapes    : v_posed = T + [S|P] . [beta | R-I]   (:87-99) - dense GEMM, K = 217 (+3 pad).
 //   K5 smpl_skin_kernel : per-vertex blend of the joint transforms + apply (:134-145), ELL weights,
-//                         output staged through shared memory and written as aligned float4.
+//                         output staged through shared memory and written as aligned float4 (fp32 path;
+//                         GATOR_PREC_BF16X3 uses the tensor-core kernel in smpl_skin_umma.cu).
 #include "common.cuh"
 
 namespace gator {
@@ -257,9 +258,8 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
 
 // Samples per workspace chunk.  Measured at B = 16384 (bf16x3): 592 -> 2.42 ms, 1024 -> 2.19, 2048 -> 1.91, 4096 -> 1.77,
 // 8192 -> 1.64: the persistent blend-shape GEMM needs many tiles per CTA to fill its waves, and keeping v_posed
-// L2-resident with small chunks does not pay.  (A variant of the skinning kernel that blends the transforms on the
-// tensor cores - T = W_skin G' as a tcgen05 GEMM with the apply step in the epilogue - was built and measured equal
-// to this one within 2 %: both are bound by the v_posed / vertex traffic, so it was not kept.)
+// L2-resident with small chunks does not pay.  (Numbers taken with the CUDA-core skinning kernel and 4 epilogue warps
+// in the GEMM; with the tensor-core skinning kernel of smpl_skin_umma.cu and 8-16 epilogue warps the same batch takes 1.05 ms.)
 constexpr int kChunk = 8192;
 
 struct Ws {

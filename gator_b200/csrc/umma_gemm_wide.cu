@@ -26,15 +26,17 @@ namespace {
 
 using namespace umma;
 
-constexpr int WBM = 128, WBN = 256, WBK = 32, WSTAGES = 4;
+constexpr int WBM = 128, WBN = 256, WBK = 32;
 constexpr int A_HALF = WBM * WBK * 2;                  // 8 KB: hi or lo of an A stage
 constexpr int W_HALF = WBN * WBK * 2;                  // 16 KB
 constexpr int A_STAGE = 2 * A_HALF, W_STAGE = 2 * W_HALF;
 constexpr int STAGE_BYTES = A_STAGE + W_STAGE;         // 48 KB
 constexpr int STG_LD = 32;                             // floats per staged row; 16-byte chunks are XOR-swizzled by the row
-constexpr int EPI_GROUPS = 2;                          // epilogue warp groups (4 warps each), alternating 32-column slabs
-constexpr int WIDE_SMEM = WSTAGES * STAGE_BYTES + EPI_GROUPS * WBM * STG_LD * 4;
-constexpr int WIDE_THREADS = (2 + 4 * EPI_GROUPS) * 32;
+// Two shapes of the same kernel (operand ring depth x epilogue warp groups of 4 warps, alternating 32-column slabs):
+//   <4, 2>  long K loops (upsample_conv, 41 K blocks per tile): tensor-bound, the deeper ring matters
+//   <3, 4>  short K loops (SMPL blend shapes, 7 K blocks per tile): bound by draining 128 KB per tile, more drain warps
+constexpr int wide_smem(int stages, int groups) { return stages * STAGE_BYTES + groups * WBM * STG_LD * 4; }
+constexpr int wide_threads(int groups) { return (2 + 4 * groups) * 32; }
 
 struct WideParams {
   const uint8_t* Aimg;
@@ -74,7 +76,8 @@ __device__ __forceinline__ void epi_bar(int group) { asm volatile("bar.sync %0, 
 // float4 writes (8 lanes = 8 rows) and the row-segment reads (8 lanes = 8 chunks of one row) are bank-conflict free
 __device__ __forceinline__ int stg_idx(int r, int col) { return r * STG_LD + ((((col >> 2) ^ r) & 7) << 2) + (col & 3); }
 
-__global__ void __launch_bounds__(WIDE_THREADS, 1)
+template <int WSTAGES, int EPI_GROUPS>
+__global__ void __launch_bounds__(wide_threads(EPI_GROUPS), 1)
 umma_gemm_wide_kernel(WideParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t full[WSTAGES], empty[WSTAGES], acc_full[2], acc_empty[2];
@@ -261,12 +264,16 @@ int gemm_bf16x3_wide(const float* A, int lda, const void* Wimg, void* a_img, siz
   int dev = 0;
   cudaGetDevice(&dev);
   if (first_use_on_device(&attr_seen)) {
-    cudaFuncSetAttribute(umma_gemm_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM);
+    cudaFuncSetAttribute(umma_gemm_wide_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem(4, 2));
+    cudaFuncSetAttribute(umma_gemm_wide_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem(3, 4));
     cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
   }
   const int sms = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
   const int total = p.m_tiles * p.n_tiles;
-  umma_gemm_wide_kernel<<<total < sms ? total : sms, WIDE_THREADS, WIDE_SMEM, stream>>>(p);
+  if (p.kblocks <= 8)
+    umma_gemm_wide_kernel<3, 4><<<total < sms ? total : sms, wide_threads(4), wide_smem(3, 4), stream>>>(p);
+  else
+    umma_gemm_wide_kernel<4, 2><<<total < sms ? total : sms, wide_threads(2), wide_smem(4, 2), stream>>>(p);
   return check_launch("umma_gemm_wide");
 }
 
