@@ -112,6 +112,100 @@ csr_spmm3_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx,
   }
 }
 
+
+// xyz fast path for operators whose input fits shared memory twice (Mesh.upsample: 431 -> 1723 -> 6890).
+// "Row-stationary": a CTA owns a slice of 1024 output rows for a strided set of samples; every lane keeps the <= 4
+// non-zeros of its 4 rows in registers for the whole kernel, so per sample only the input (cols x 3 floats, copied
+// with cp.async into one of two shared-memory buffers while the previous sample is processed) and the outputs move:
+// 12 KB of contiguous output per CTA and sample, written as 128-byte coalesced stores through warp-private staging.
+constexpr int RS_ROWS = 1024;          // output rows per CTA: 8 warps x 4 groups x 32 lanes
+__global__ void __launch_bounds__(256)
+csr_spmm3_rows_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx, const float* __restrict__ values,
+                      const float* __restrict__ x, float* __restrict__ y, int rows, int cols, float scale, int batch,
+                      int slices, int parts) {
+  extern __shared__ __align__(16) float sx[];          // [2][cols*3]
+  __shared__ __align__(16) float stage[8][4][96];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = blockIdx.x % slices, part = blockIdx.x / slices;
+  const int xs = cols * 3;
+  const int v0 = slice * RS_ROWS + warp * 128;         // first row of this warp
+  int c[4][4], k0[4], nnz[4];
+  float w[4][4];
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const int r = v0 + g * 32 + lane;
+    k0[g] = 0; nnz[g] = 0;
+    if (r < rows) { k0[g] = __ldg(rowptr + r); nnz[g] = __ldg(rowptr + r + 1) - k0[g]; }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      c[g][k] = 0; w[g][k] = 0.f;
+      if (k < nnz[g]) { c[g][k] = __ldg(colidx + k0[g] + k) * 3; w[g][k] = __ldg(values + k0[g] + k); }
+    }
+  }
+  // sample s -> sx[buf].  A sample starts 4-byte aligned (cols * 12 B is not a multiple of 16), so the enclosing 16-byte
+  // aligned range is copied with 16-byte cp.async and read at an offset of `shift` floats; the last sample, whose
+  // enclosing range could run past the end of x, is copied in 4-byte pieces.
+  const int xbuf = (xs + 6) & ~3;                      // floats per buffer: room for shift <= 3, a multiple of 16 bytes
+  auto copy_in = [&](int s, int buf) -> int {
+    const float* src = x + (size_t)s * xs;
+    const int shift = (int)((reinterpret_cast<uintptr_t>(src) >> 2) & 3);
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(sx + buf * xbuf);
+    if (s + 1 < batch) {
+      const float* a0 = src - shift;
+      const int n16 = (shift + xs + 3) >> 2;
+      for (int i = tid; i < n16; i += 256)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst + i * 16), "l"(a0 + i * 4) : "memory");
+    } else {
+      for (int i = tid; i < xs; i += 256)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst + (shift + i) * 4), "l"(src + i) : "memory");
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    return shift;
+  };
+  int shift_cur = 0, shift_next = 0;
+  if (part < batch) shift_cur = copy_in(part, 0);
+  int it = 0;
+  for (int s = part; s < batch; s += parts, ++it) {
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    __syncthreads();                                   // sample s has landed; everyone is done with the other buffer
+    if (s + parts < batch) shift_next = copy_in(s + parts, (it + 1) & 1);
+    const float* xb = sx + (it & 1) * xbuf + shift_cur;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      if (nnz[g] <= 4) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (k < nnz[g]) {
+            a0 = fmaf(w[g][k], xb[c[g][k]], a0); a1 = fmaf(w[g][k], xb[c[g][k] + 1], a1); a2 = fmaf(w[g][k], xb[c[g][k] + 2], a2);
+          }
+        }
+      } else {
+        for (int k = k0[g]; k < k0[g] + nnz[g]; ++k) {
+          const float ww = __ldg(values + k);
+          const float* xp = xb + __ldg(colidx + k) * 3;
+          a0 = fmaf(ww, xp[0], a0); a1 = fmaf(ww, xp[1], a1); a2 = fmaf(ww, xp[2], a2);
+        }
+      }
+      float* st = stage[warp][g];
+      st[lane * 3] = a0 * scale; st[lane * 3 + 1] = a1 * scale; st[lane * 3 + 2] = a2 * scale;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int r0 = v0 + g * 32;
+      const int seg = max(0, min(32, rows - r0)) * 3;
+      const float* st = stage[warp][g];
+      float* dst = y + ((size_t)s * rows + r0) * 3;
+      if (lane < seg) dst[lane] = st[lane];
+      if (lane + 32 < seg) dst[lane + 32] = st[lane + 32];
+      if (lane + 64 < seg) dst[lane + 64] = st[lane + 64];
+    }
+    __syncwarp();
+    shift_cur = shift_next;
+  }
+}
+
 }  // namespace
 }  // namespace gator
 
@@ -122,6 +216,18 @@ extern "C" int gator_csr_spmm(const gator_csr_args* a, void* stream) {
   const long long total = (long long)a->batch * a->rows * a->feat;
   if (total == 0) return GATOR_OK;
   GATOR_REQUIRE(a->rowptr && a->colidx && a->values && a->x && a->y, "gator_csr_spmm: null buffer");
+  if (a->feat == 3 && a->rows >= 256 && (size_t)a->cols * 24 + 64 <= 48 * 1024 && (reinterpret_cast<uintptr_t>(a->x) & 15u) == 0) {
+    // row-stationary kernel: input double-buffered in shared memory, up to 4 CTAs per SM
+    const int slices = ceil_div(a->rows, RS_ROWS);
+    int parts = (148 * 4) / slices;
+    parts = parts < 1 ? 1 : (parts > a->batch ? a->batch : parts);
+    static unsigned long long attr_seen2 = 0;
+    if (first_use_on_device(&attr_seen2))
+      cudaFuncSetAttribute(csr_spmm3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+    csr_spmm3_rows_kernel<<<slices * parts, 256, (size_t)a->cols * 24 + 64, (cudaStream_t)stream>>>(
+        a->rowptr, a->colidx, a->values, a->x, a->y, a->rows, a->cols, a->scale, a->batch, slices, parts);
+    return check_launch("csr_spmm3_rows");
+  }
   if (a->feat == 3 && a->rows >= 64 && (size_t)a->cols * 12 <= 96 * 1024) {
     const int per_sample = a->cols * 12;
     int NS = 96 * 1024 / per_sample;                 // <= 96 KB of staged inputs per CTA (2 CTAs / SM)
