@@ -1,5 +1,8 @@
-import sys, time
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+"""pack() time of the three modules on the device (why a disk cache of packed weights is not needed)."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import time
 import torch
 from builders import build_b200_gator, build_b200_smpl
 m = build_b200_gator('coco', 'cuda:0').set_precision('bf16x3')

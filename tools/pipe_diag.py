@@ -1,5 +1,7 @@
-import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tests')
+"""Device-to-host bandwidth and HostPipeline step time for a few slicing schemes."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch, time
 from builders import build_b200_gator, golden, synthetic
 from gator_b200.pipeline import HostPipeline

@@ -1,5 +1,7 @@
-import sys, os
-sys.path.insert(0, '/root/repo'); sys.path.insert(0, '/root/repo/tools')
+"""One wide-GEMM launch at the SMPL blend-shape shape, for ncu."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
 from gator_b200 import _lib
 from gator_b200.packing import pack_umma_weight_pair, pack_umma_wide
