@@ -10,7 +10,7 @@
 //   x3  = a2 (x - mean) / (std_unbiased + 1e-6) + b2                (vanilla_transformer_encoder.py:31-34)
 //   qkv = x3 [Wq;Wk;Wv]^T + b                                       (:88-90)          -> x3, qkv to HBM
 //
-// One CTA = 256 consecutive vertex rows of one sample (two M=128 tiles), 512 threads, two threads per row (one
+// One CTA = 128 consecutive rows of the flat (sample, vertex) row space, 256 threads, two threads per row (one
 // 32-column half each): the fp32 residual row x lives in those threads' registers, every GEMM is a sequence of 64x64 "units"
 // (A: 128 x 64 bf16 hi/lo image written by the row owners, W: 64 x 64 bf16 hi/lo image streamed from L2 with
 // cp.async into a 3-slot ring, D: 64 TMEM columns per tile), LayerNorm / GELU / the cross-attention run on the
@@ -53,6 +53,7 @@ struct ChainParams {
   float* hd_out;          // non-null: FINAL pass - only x = x_in + att_in Wo^T + b, then hd = x W_head^T + b_head (nb*431, 28);
                           // blob = [linears[3] of the last layer, head (28 rows zero-padded to 64)], prm[0] = so_b, prm[1] = head_b
   int J;
+  long long rows_total;   // nb * 431
   int split;              // 1: 3-term bf16 split products
 };
 
@@ -98,20 +99,28 @@ mdr_chain_kernel(ChainParams p) {
   __shared__ uint32_t tmem_slot;
   __shared__ float2 xch_buf[2][TILES][128][2];      // [LayerNorm # parity][tile][row][{mine, partner} by column half]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  constexpr int CPS = 4 / TILES;                   // CTAs per sample
-  const int b = blockIdx.x / CPS, part = blockIdx.x % CPS;
+  // Tiles are cut from the flat (sample, vertex) row space, so a tile may hold the tail of one sample and the head of the
+  // next (431 = 3 x 128 + 47: per-sample tiling would leave every 4th tile 63 % empty).  Everything here is row-wise;
+  // the only per-sample data, the cross-attention K|V of the row's sample, is read through L1 (see below).
   const int tile = warp >> 3;                      // which M=128 tile of the CTA
   const int ch = (warp >> 2) & 1;                  // which 32-column half of the 64-wide row this thread owns
   const int row = (warp & 3) * 32 + lane;          // row in tile = TMEM lane
-  const int vrow = (part * TILES + tile) * 128 + row;   // vertex index in the sample
-  const bool valid = vrow < V;
-  const size_t grow = (size_t)b * V + (valid ? vrow : 0);
+  const long long flat = ((long long)blockIdx.x * TILES + tile) * 128 + row;   // row in the (nb * 431) row space
+  const bool valid = flat < p.rows_total;
+  const size_t grow = valid ? (size_t)flat : 0;
+  const int b = (int)(grow / V);                   // sample of this row
   const int pair_id = 1 + tile * 4 + (warp & 3);   // named barrier shared by the two warps that own the same rows
   constexpr int OFF_W = TILES * 2 * A_BUF;
-  constexpr int OFF_KV = OFF_W + W_SLOTS * UNIT_BYTES;
   uint8_t* a0 = smem + tile * 2 * A_BUF;           // this tile's buffer 0 (n / generic) ...
   uint8_t* a1 = a0 + A_BUF;                        // ... and buffer 1 (GELU(fc1) quarter)
+  // K|V (J x 128 fp32 = 9.7 KB per sample): the sample of the tile's first row is staged in shared memory; the rows of
+  // a tile that belong to the next sample (30 % of the tiles contain a boundary) read theirs through L1 instead
+  // (measured: reading all K|V through L1 costs 28 % per tile, a second shared-memory copy does not fit twice per SM)
+  constexpr int OFF_KV = OFF_W + W_SLOTS * UNIT_BYTES;
   float* skv = reinterpret_cast<float*>(smem + OFF_KV);
+  const int b_first = (int)(((long long)blockIdx.x * TILES * 128) / V);
+  const bool kv_smem = b == b_first;
+  const float* kvp = p.kv + (size_t)b * (JT ? JT : p.J) * 128;
   const int J = JT ? JT : p.J;
   constexpr int JU = JT ? JT : MAXJ;               // unrolled trip count of the per-joint loops
   // per-channel parameters come straight from global memory (L1-resident: ~4 KB per layer, shared by all CTAs)
@@ -140,8 +149,8 @@ mdr_chain_kernel(ChainParams p) {
   }
   const int first_unit = p.att_in ? U_SO : U_Q;   // (the FINAL pass needs att_in: unit 0 = linears[3], unit 1 = head)
   prefetch_w(first_unit, 0);
-  {   // K|V of the sample: asynchronous 16-byte copies, completed by the cp.async wait of the first unit
-    const float* src = p.kv + (size_t)b * J * 128;
+  {   // K|V of the tile's first sample: asynchronous 16-byte copies, completed by the cp.async wait of the first unit
+    const float* src = p.kv + (size_t)b_first * J * 128;
     const uint32_t dst = smem_u32(skv);
     for (int i = tid; i < J * 32; i += NT) cp_async16(dst + i * 16, src + i * 4);
     cp_async_commit();
@@ -262,16 +271,17 @@ mdr_chain_kernel(ChainParams p) {
   {
     float q[DK];
     ld32(acc, q);
+    auto cross = [&](const float* kvb, auto ld4) {
     float s[JU];
     float mx = -INFINITY;
 #pragma unroll
     for (int j = 0; j < JU; ++j) {
       if (JT || j < J) {
-        const float4* kr = reinterpret_cast<const float4*>(skv + j * 128 + c0);
+        const float4* kr = reinterpret_cast<const float4*>(kvb + j * 128 + c0);
         float a0_ = 0.f, a1_ = 0.f, a2_ = 0.f, a3_ = 0.f;       // 4 independent FMA chains
 #pragma unroll
         for (int d4 = 0; d4 < DK / 4; ++d4) {
-          const float4 kk = kr[d4];
+          const float4 kk = ld4(kr + d4);
           a0_ = fmaf(q[4 * d4], kk.x, a0_); a1_ = fmaf(q[4 * d4 + 1], kk.y, a1_);
           a2_ = fmaf(q[4 * d4 + 2], kk.z, a2_); a3_ = fmaf(q[4 * d4 + 3], kk.w, a3_);
         }
@@ -290,15 +300,18 @@ mdr_chain_kernel(ChainParams p) {
     for (int j = 0; j < JU; ++j) {
       if (JT || j < J) {
         const float pj = s[j] * inv;
-        const float4* vr = reinterpret_cast<const float4*>(skv + j * 128 + E + c0);
+        const float4* vr = reinterpret_cast<const float4*>(kvb + j * 128 + E + c0);
 #pragma unroll
         for (int d4 = 0; d4 < DK / 4; ++d4) {
-          const float4 vv = vr[d4];
+          const float4 vv = ld4(vr + d4);
           v[4 * d4] = fmaf(pj, vv.x, v[4 * d4]); v[4 * d4 + 1] = fmaf(pj, vv.y, v[4 * d4 + 1]);
           v[4 * d4 + 2] = fmaf(pj, vv.z, v[4 * d4 + 2]); v[4 * d4 + 3] = fmaf(pj, vv.w, v[4 * d4 + 3]);
         }
       }
     }
+    };
+    if (kv_smem) cross(skv, [](const float4* q_) { return *q_; });
+    else cross(kvp, [](const float4* q_) { return __ldg(q_); });
     write_a<4>(a0, row, ch * 4, v);
   }
   run_unit(0, 0, false, U_FC1);
@@ -373,20 +386,20 @@ int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, co
                      float* x3_out, float* qkv_out, float* hd_out, int nb, int J, bool split, cudaStream_t stream) {
   static unsigned long long attr_seen = 0;
   if (first_use_on_device(&attr_seen)) {
-    cudaFuncSetAttribute(mdr_chain_kernel<1, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, 17));
-    cudaFuncSetAttribute(mdr_chain_kernel<1, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, 19));
+    cudaFuncSetAttribute(mdr_chain_kernel<1, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
+    cudaFuncSetAttribute(mdr_chain_kernel<1, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
     cudaFuncSetAttribute(mdr_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
-    cudaFuncSetAttribute(mdr_chain_kernel<2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(2, MAXJ));
   }
   ChainParams p;
   p.x_in = x_in; p.att_in = att_in; p.kv = kv; p.blob = static_cast<const uint8_t*>(blob);
   for (int i = 0; i < 11; ++i) p.prm[i] = prm[i];
   p.x3_out = x3_out; p.qkv_out = qkv_out; p.hd_out = hd_out; p.J = J; p.split = split ? 1 : 0;
-  // one tile per CTA fits twice on an SM (2 x ~107 KB) as long as J <= 24; otherwise two tiles per CTA
-  if (J == 17) mdr_chain_kernel<1, 17><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);
-  else if (J == 19) mdr_chain_kernel<1, 19><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);
-  else if (smem_bytes(1, J) <= 110 * 1024) mdr_chain_kernel<1, 0><<<nb * 4, 256, smem_bytes(1, J), stream>>>(p);
-  else mdr_chain_kernel<2, 0><<<nb * 2, 512, smem_bytes(2, J), stream>>>(p);
+  p.rows_total = (long long)nb * V;
+  // one 128-row tile per CTA; two CTAs per SM as long as J <= 24 (2 x ~107 KB)
+  const unsigned grid = (unsigned)((p.rows_total + 127) / 128);
+  if (J == 17) mdr_chain_kernel<1, 17><<<grid, 256, smem_bytes(1, J), stream>>>(p);
+  else if (J == 19) mdr_chain_kernel<1, 19><<<grid, 256, smem_bytes(1, J), stream>>>(p);
+  else mdr_chain_kernel<1, 0><<<grid, 256, smem_bytes(1, J), stream>>>(p);
   return check_launch("mdr_chain");
 }
 
