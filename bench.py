@@ -267,7 +267,7 @@ def run_b200(args):
     if rank == 0:
         peaks = measured_peaks()
         # ---- dominant kernels alone (C-ABI entry points, CUDA events on the launching stream) ----
-        nb = 148
+        nb = 1184                                               # 8 x 148 samples: 3987 chain tiles, 2368 attention CTAs
         pcode = _lib.PRECISIONS[args.precision]
         s = _lib.stream_ptr()
 
@@ -339,11 +339,12 @@ def run_b200(args):
                             'launch_ms': ev_ms, 'bytes_per_launch': ev_bytes, 'traffic': 686.8e6})
             del pm, gm, gj
         roofline = dict(kernels[0])
-        # dram__bytes_read.sum + dram__bytes_write.sum of one 592-CTA launch from the committed `ncu --set full` capture
-        # (profiles/r01_ncu_full_mdr_chain_kernel.csv; ncu flushes caches, so this is an upper bound of a warm launch)
-        roofline.update({'traffic': 52.9e6 if pcode != 0 else None, 'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)',
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu launch list of a 4096-sample forward
+        # (profiles/r01_launches_bf16x3_b4096_flat.csv, layers 1-2: 944.5 MB read + 1750 MB written per 4096 samples), scaled to
+        # this launch's 1184 samples; ncu flushes caches between kernels, so this is an upper bound of a warm launch
+        roofline.update({'traffic': 779e6 if pcode != 0 else None, 'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)',
                          'note': 'algorithmic flops (2*MAC of the layer\'s 14 64x64 products + cross-attention, or of QK^T + PV) per launch of '
-                                 '148 samples; the 3-term split issues 3x that many tensor-core MACs, which are not counted; both kernels are '
+                                 '1184 samples; the 3-term split issues 3x that many tensor-core MACs, which are not counted; both kernels are '
                                  'bound by CUDA-core softmax/GELU/LayerNorm/operand-conversion work and MMA round-trip latency, not by the tensor pipe',
                          'other_kernels': kernels[1:]})
         # parity of this very configuration against the CPU oracle (64 samples)
