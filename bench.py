@@ -49,6 +49,13 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.rows, self.proc, self.index = [], None, index
+        self.t0 = self.t1 = None                        # timed region (perf_counter); samples outside it are dropped
+
+    def mark(self, begin: bool):
+        if begin:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
 
     def start(self):
         try:
@@ -60,7 +67,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(',')])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(',')]))
 
     def stop(self):
         if self.proc is None:
@@ -68,7 +75,10 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         sm, smax, reasons = [], None, set()
-        for r in self.rows:
+        rows = [r for t, r in self.rows if self.t0 is None or (self.t0 <= t <= (self.t1 or t) + 0.12)]
+        if not rows:                                    # region shorter than one polling period: closest samples
+            rows = [r for _, r in self.rows[-2:]]
+        for r in rows:
             try:
                 sm.append(float(r[1]))
                 smax = float(r[2])
@@ -170,20 +180,23 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ----
+    # nvidia-smi is started well before the timed region: its start-up (NVML initialisation) was seen to stall the GPU for
+    # tens of milliseconds when it coincided with the first timed steps (one run measured 41 ms per step instead of 20)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     with torch.no_grad():
-        t_ramp = time.perf_counter()                       # untimed: first call packs the weights, then ~0.4 s of
+        t_ramp = time.perf_counter()                       # untimed: first call packs the weights, then ~0.8 s of
         while True:                                        # forwards so that the SM clock has ramped before the W
             model(x)                                       # warm-up steps the contract asks for
             torch.cuda.synchronize()
-            if time.perf_counter() - t_ramp > 0.4:
+            if time.perf_counter() - t_ramp > 0.8:
                 break
         for _ in range(args.warmup):
             model(x)
         barrier()
         L.gator_launch_count(1)
-        sampler = ClockSampler(local)
-        if rank == 0:
-            sampler.start()
+        sampler.mark(True)
         evs = []
         t_wall = time.perf_counter()
         for _ in range(args.steps):
@@ -195,6 +208,7 @@ def run_b200(args):
             evs.append((e0, e1))
         barrier()
         t_wall = time.perf_counter() - t_wall
+        sampler.mark(False)
         launches = L.gator_launch_count(1)
         clocks = sampler.stop() if rank == 0 else None
     step_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
