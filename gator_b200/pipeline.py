@@ -7,6 +7,25 @@ from __future__ import annotations
 import torch
 
 
+def plan_slices(batch: int, ratio: float, floor: int = 148):
+    """Slice boundaries [0, ..., batch]: sizes s, s r, s r^2, ... (each >= `floor` = one CTA per SM) that sum to the batch,
+    so that each slice's device-to-host copy is shorter than the next slice's kernels and only a short last copy is exposed."""
+    if batch <= 2 * floor:
+        return [0, batch]
+    sizes, nxt, left = [], float(batch) * (1.0 - ratio), batch
+    while left > 0:
+        sz = min(left, max(floor, int(nxt)))
+        if left - sz < floor:
+            sz = left
+        sizes.append(sz)
+        left -= sz
+        nxt *= ratio
+    bounds = [0]
+    for sz in sizes:
+        bounds.append(bounds[-1] + sz)
+    return bounds
+
+
 class HostPipeline:
     """forward(pose2d_host (B,J,2) pinned) -> (mesh_host (B,6890,3), pose3d_host (B,J,3)) pinned, both fp32."""
 
@@ -30,22 +49,7 @@ class HostPipeline:
         self._bounds = None
 
     def _plan(self):
-        """Slice boundaries: sizes s, s r, s r^2, ... (each >= 148 = one CTA per SM) that sum to the batch."""
-        B, ratio = self.batch, self.RATIO
-        if B <= 296:
-            return [0, B]
-        sizes, nxt, left = [], float(B) * (1.0 - ratio), B
-        while left > 0:
-            sz = min(left, max(148, int(nxt)))
-            if left - sz < 148:
-                sz = left
-            sizes.append(sz)
-            left -= sz
-            nxt *= ratio
-        bounds = [0]
-        for sz in sizes:
-            bounds.append(bounds[-1] + sz)
-        return bounds
+        return plan_slices(self.batch, self.RATIO)
 
     @torch.no_grad()
     def forward(self, pose2d_host: torch.Tensor):
