@@ -188,14 +188,15 @@ def run_b200(args):
     with torch.no_grad():
         t_ramp = time.perf_counter()                       # untimed: first call packs the weights, then ~0.8 s of
         while True:                                        # forwards so that the SM clock has ramped before the W
-            model(x)                                       # warm-up steps the contract asks for
+            mesh_w = model(x)                              # warm-up steps the contract asks for
             torch.cuda.synchronize()
             if time.perf_counter() - t_ramp > 0.8:
                 break
+        mesh = p3 = None
         for _ in range(args.warmup):
-            model(x)
-        barrier()
-        L.gator_launch_count(1)
+            mesh, p3 = model(x)                            # same binding pattern as the timed loop: the previous step's
+        barrier()                                          # outputs are still alive while the next ones are allocated, so
+        L.gator_launch_count(1)                            # the caching allocator's second 340 MB block exists before timing
         sampler.mark(True)
         evs = []
         t_wall = time.perf_counter()
@@ -211,7 +212,8 @@ def run_b200(args):
         sampler.mark(False)
         launches = L.gator_launch_count(1)
         clocks = sampler.stop() if rank == 0 else None
-    step_ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    per_step = [a.elapsed_time(b) for a, b in evs]
+    step_ms = sum(per_step) / args.steps
     t = torch.tensor([step_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -385,7 +387,7 @@ def run_b200(args):
                         'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': int((mesh_host.numel() + p3_host.numel()) * 4)},
                 'gpu_launches': int(launches),
                 'tflops_effective': FLOP_PER_MESH * value / 1e12,
-                'numa_node': numa_node, 'wall_s_timed_region': t_wall,
+                'numa_node': numa_node, 'wall_s_timed_region': t_wall, 'step_ms': [round(t_, 3) for t_ in per_step],
                 'latency_b1': latency,
                 'roofline': roofline, 'parity': parity,
                 'cpu_baseline': {'value': cpu_v, 'unit': UNIT, 'cores': threads, 'kind': 'port',

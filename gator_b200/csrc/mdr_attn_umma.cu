@@ -95,7 +95,8 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     mbar_init(&bar_p[1], 1);
     mbar_init_fence();
   }
-  // ---- stage K: chunk c = (kg, kc, r) -> key = kg*8 + r, d = kc*8 ----
+  // ---- stage K and V^T: all global loads of both (64 registers) are issued before the first conversion, so the two
+  //      memory latencies overlap.  K: chunk c = (kg, kc, r) -> key = kg*8 + r, d = kc*8 ----
   {
     // all global loads of this thread are issued before the first conversion (4 chunks x 2 x 16 B in flight)
     constexpr int NCH = (VP * 4 + NT - 1) / NT;
@@ -110,6 +111,18 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
         const float* src = base + (size_t)key * 3 * E + E + h * DK + kc * 8;
         ka[i] = *reinterpret_cast<const float4*>(src);
         kb2[i] = *reinterpret_cast<const float4*>(src + 4);
+      }
+    }
+    // V^T: warp takes a group of 8 keys, lane = d; chunk (dg, kc, r): d = dg*8 + r
+    constexpr int NG = (KCH + NT / 32 - 1) / (NT / 32);   // key groups per warp (4)
+    float vv[NG][8];
+#pragma unroll
+    for (int g = 0; g < NG; ++g) {
+      const int kc = warp + g * (NT / 32);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = kc * 8 + i;
+        vv[g][i] = (kc < KCH && key < V) ? base[(size_t)key * 3 * E + 2 * E + h * DK + lane] : 0.f;
       }
     }
     float kmax2 = 0.f;
@@ -130,20 +143,6 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
     }
     kmax2 = warp_max(kmax2);
     if (lane == 0) k_norm2_warp[warp] = kmax2;
-  }
-  // ---- stage V^T: warp takes a group of 8 keys, lane = d; chunk (dg, kc, r): d = dg*8 + r ----
-  {
-    constexpr int NG = (KCH + NT / 32 - 1) / (NT / 32);   // key groups per warp (4)
-    float vv[NG][8];
-#pragma unroll
-    for (int g = 0; g < NG; ++g) {
-      const int kc = warp + g * (NT / 32);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int key = kc * 8 + i;
-        vv[g][i] = (kc < KCH && key < V) ? base[(size_t)key * 3 * E + 2 * E + h * DK + lane] : 0.f;
-      }
-    }
     const int dg = lane >> 3, r = lane & 7;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
