@@ -61,3 +61,12 @@ def test_host_pipeline_slice_plan():
         if B >= 700:
             assert len(sizes) >= 2 and sizes[-1] <= 0.4 * B                    # only a short copy is left exposed
     assert plan_slices(4096, 0.35) == [0, 2662, 3593, 3919, 4096]
+
+
+def test_numa_binding_is_best_effort():
+    """bind_to_gpu_numa_node never raises: without a GPU / topology it reports None and leaves the affinity alone."""
+    import os
+    from gator_b200.dist import bind_to_gpu_numa_node
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)
+    assert os.sched_getaffinity(0) <= before
