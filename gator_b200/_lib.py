@@ -30,7 +30,7 @@ class GatArgs(C.Structure):
 
 class MdrArgs(C.Structure):
     _fields_ = [('num_joint', C.c_int32), ('batch', C.c_int32), ('chunk', C.c_int32), ('alpha', C.c_int32),
-                ('precision', C.c_int32), ('reserved', C.c_int32),
+                ('precision', C.c_int32), ('reserved', C.c_int32), ('pose3d_metres', C.c_int32), ('reserved2', C.c_int32),
                 ('weights', C.POINTER(C.c_void_p)), ('weights_bf16', C.POINTER(C.c_void_p)),
                 ('weights_bf16_lo', C.POINTER(C.c_void_p)),
                 ('pose2d', C.c_void_p), ('pose3d', C.c_void_p),
@@ -94,7 +94,7 @@ class SmplCamArgs(C.Structure):
 
 _STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs, EvalArgs, Pose2dArgs, SmplCamArgs]
 EXPORTS = ['gator_abi_version', 'gator_last_error', 'gator_abi_sizeof', 'gator_launch_count',
-           'gator_mdr_self_attention', 'gator_mdr_layer_chain', 'gator_umma_weight_layout',
+           'gator_mdr_self_attention', 'gator_mdr_self_attention_image_bytes', 'gator_mdr_self_attention_f16', 'gator_mdr_layer_chain', 'gator_umma_weight_layout',
            'gator_gat_slot_name', 'gator_gat_workspace_bytes', 'gator_gat_forward',
            'gator_mdr_slot_name', 'gator_mdr_workspace_bytes', 'gator_mdr_forward',
            'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_gemm',
@@ -140,6 +140,10 @@ def lib():
         L.gator_launch_count.argtypes = [C.c_int]
         L.gator_mdr_self_attention.restype = C.c_int
         L.gator_mdr_self_attention.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.gator_mdr_self_attention_image_bytes.restype = C.c_size_t
+        L.gator_mdr_self_attention_image_bytes.argtypes = [C.c_int32]
+        L.gator_mdr_self_attention_f16.restype = C.c_int
+        L.gator_mdr_self_attention_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.gator_mdr_layer_chain.restype = C.c_int
         L.gator_mdr_layer_chain.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
@@ -149,7 +153,7 @@ def lib():
         L.gator_umma_wide_a_bytes.argtypes = [C.c_int32, C.c_int32]
         L.gator_umma_weight_layout.restype = C.c_int
         L.gator_umma_weight_layout.argtypes = [C.c_int32, C.c_int32, c_int_p, c_int_p, c_int_p]
-        if L.gator_abi_version() != 1:
+        if L.gator_abi_version() != 2:
             raise RuntimeError('gator_b200: ABI version mismatch between _lib.py and libgator_b200.so')
         for i, st in enumerate(_STRUCTS):
             if L.gator_abi_sizeof(i) != C.sizeof(st):

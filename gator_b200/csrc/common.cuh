@@ -5,6 +5,8 @@
 #include <stdio.h>
 #include <stdarg.h>
 
+#include <mutex>
+
 #include "../../include/gator_b200.h"
 
 namespace gator {
@@ -27,15 +29,35 @@ int check_launch(const char* what);   // cudaGetLastError -> status
     if (_st != GATOR_OK) return _st;                   \
   } while (0)
 
-// cudaFuncSetAttribute is per device: returns true the first time it is called for the current device with this
-// flag word (one static uint64_t per call site; devices 0..63), so each kernel's attributes are set once per GPU.
-static inline bool first_use_on_device(unsigned long long* seen) {
-  int dev = 0;
-  cudaGetDevice(&dev);
-  const unsigned long long bit = 1ull << (dev & 63);
-  const unsigned long long old = __atomic_fetch_or(seen, bit, __ATOMIC_RELAXED);
-  return (old & bit) == 0;
-}
+// One-time per-device setup of a kernel (cudaFuncSetAttribute is per device).  Thread-safe: concurrent first callers
+// block until the setup has run, a device is only marked done after every call succeeded, a failure is reported through
+// gator_last_error() and retried by the next call.  One static DeviceOnce per call site; devices 0..63.
+struct DeviceOnce {
+  std::mutex mu;
+  unsigned long long done = 0;
+  template <class F>
+  int run(const char* what, F&& init) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (__atomic_load_n(&done, __ATOMIC_ACQUIRE) & bit) return GATOR_OK;
+    std::lock_guard<std::mutex> lock(mu);
+    if (done & bit) return GATOR_OK;
+    const cudaError_t e = init(dev);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      set_error("%s: kernel attribute setup failed on device %d: %s", what, dev, cudaGetErrorString(e));
+      return GATOR_ERR_LAUNCH;
+    }
+    __atomic_or_fetch(&done, bit, __ATOMIC_RELEASE);
+    return GATOR_OK;
+  }
+};
+#define GATOR_CUDA_OK(expr)                            \
+  do {                                                 \
+    const cudaError_t _ce = (expr);                    \
+    if (_ce != cudaSuccess) return _ce;                \
+  } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -90,10 +112,21 @@ inline int gemm(int precision, const float* A, int lda, const float* W, int ldw,
 // tcgen05 version of the MDR self-attention core: qkv (nb*431, 192) -> out (nb*431, 64)
 int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream);
 
+// round-2 self-attention core (csrc/mdr_attn2_umma.cu): fp16 [Q | K | V] operand images per (sample, head) -> out (nb*431, 64)
+size_t self_attn2_image_bytes(int nb);
+int launch_qkv_image(const float* qkv, void* img, int nb, cudaStream_t stream);
+int launch_self_attn2(const void* img, float* out, int nb, cudaStream_t stream);
+
 // Fused row-wise chain of one MDR layer (csrc/mdr_chain_umma.cu): x3_prev/att_prev -> x3, qkv
 // hd_out != null selects the final pass (x3 + linears[3](att) -> MDR head projection -> hd (rows, 28))
 int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
                      float* x3_out, float* qkv_out, float* hd_out, int nb, int J, bool split, cudaStream_t stream);
+
+// Round-2 version of the same chain (csrc/mdr_chain2_umma.cu): A operands and the residual stream in tensor memory,
+// warp-specialised, TMA-fed weight ring.  q|k|v leave as fp32 rows (qkv_out) and / or as the fp16 operand images of
+// launch_self_attn2 (img_out); either may be null.
+int launch_mdr_chain2(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
+                      float* x3_out, float* qkv_out, void* img_out, float* hd_out, int nb, int J, cudaStream_t stream);
 
 // All GATBlocks of the lifter in one kernel (csrc/gat_chain_umma.cu).  blobs_dev / prm_dev are DEVICE arrays of
 // pointers: [depth] weight-piece blobs and [depth * 14] fp32 parameter arrays.

@@ -252,11 +252,11 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
   float* h = o + rows_max * 128;
   float* g = h + rows_max * 256;
 
-  static unsigned long long attr_seen = 0;
+  static DeviceOnce attr_once;
   const int attn_smem = J * (3 * C + 1) * (int)sizeof(float);
-  if (first_use_on_device(&attr_seen)) {
-    cudaFuncSetAttribute(gat_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXJ * (3 * C + 1) * (int)sizeof(float));
-  }
+  GATOR_TRY(attr_once.run("gat_attn", [&](int) -> cudaError_t {
+    return cudaFuncSetAttribute(gat_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MAXJ * (3 * C + 1) * (int)sizeof(float));
+  }));
 
   for (int b0 = 0; b0 < B; b0 += cb) {
     const int nb = (B - b0 < cb) ? B - b0 : cb;

@@ -430,13 +430,12 @@ bool gat_chain_supported(int J) { return J >= 2 && J <= 21; }   // attention-bia
 
 int launch_gat_chain(float* x, int rows, int J, int depth, const void* const* blobs_dev, const float* const* prm_dev,
                      const float* attn_bias, const float* mask1, const float* mask2, bool split, cudaStream_t stream) {
-  static unsigned long long attr_seen = 0;
-  if (first_use_on_device(&attr_seen)) {
-    cudaFuncSetAttribute(gat_chain_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(17));
-    cudaFuncSetAttribute(gat_chain_kernel<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(19));
-    cudaFuncSetAttribute(gat_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(21));
-    (void)cudaGetLastError();
-  }
+  static DeviceOnce attr_once;
+  GATOR_TRY(attr_once.run("gat_chain", [&](int) -> cudaError_t {
+    GATOR_CUDA_OK(cudaFuncSetAttribute(gat_chain_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(17)));
+    GATOR_CUDA_OK(cudaFuncSetAttribute(gat_chain_kernel<19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(19)));
+    return cudaFuncSetAttribute(gat_chain_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(21));
+  }));
   GATOR_REQUIRE(gat_chain_supported(J), "gat_chain: num_joint=%d does not fit the fused kernel", J);
   GatChainParams p;
   p.x = x; p.rows = rows; p.J = J; p.S = 128 / J; p.depth = depth;

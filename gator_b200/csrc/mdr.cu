@@ -22,7 +22,7 @@ constexpr int UPK = GATOR_UP_K;       // 1296
 __global__ void __launch_bounds__(256)
 mdr_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ pose3d, const float* __restrict__ wpose,
                  const float* __restrict__ vconst, const float* __restrict__ w3, const int* __restrict__ vj,
-                 float* __restrict__ jf, float* __restrict__ x, int J) {
+                 float* __restrict__ jf, float* __restrict__ x, int J, int metres) {
   // jf == nullptr: vertices only; x == nullptr: joints only
   __shared__ float p5[MAXJ][5];
   __shared__ float sw3[E * 3];
@@ -32,7 +32,10 @@ mdr_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ pos
     p5[tid][0] = pose2d[((size_t)b * J + tid) * 2 + 0];
     p5[tid][1] = pose2d[((size_t)b * J + tid) * 2 + 1];
 #pragma unroll
-    for (int t = 0; t < 3; ++t) p5[tid][2 + t] = pose3d[((size_t)b * J + tid) * 3 + t] / 1000.0f;
+    for (int t = 0; t < 3; ++t) {
+      const float pv = pose3d[((size_t)b * J + tid) * 3 + t];
+      p5[tid][2 + t] = metres ? pv : pv / 1000.0f;
+    }
   }
   for (int i = tid; i < E * 3; i += 256) sw3[i] = w3[i];
   for (int i = tid; i < E * 5; i += 256) swp[i] = wpose[i];
@@ -381,10 +384,10 @@ namespace gator {
 namespace {
 int launch_self_attn(const float* qkv, float* out, int nb, cudaStream_t stream) {
   constexpr int sa_smem = 2 * SA_VPAD * DK * (int)sizeof(float);
-  static unsigned long long attr_seen = 0;
-  if (first_use_on_device(&attr_seen)) {
-    cudaFuncSetAttribute(mdr_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sa_smem);
-  }
+  static DeviceOnce attr_once;
+  GATOR_TRY(attr_once.run("mdr_self_attn", [&](int) -> cudaError_t {
+    return cudaFuncSetAttribute(mdr_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sa_smem);
+  }));
   mdr_self_attn_kernel<<<nb * 2, SA_THREADS, sa_smem, stream>>>(qkv, out);
   return check_launch("mdr_self_attn");
 }
@@ -398,6 +401,16 @@ extern "C" int gator_mdr_self_attention(const float* qkv, float* out, int32_t ba
   if (batch == 0) return GATOR_OK;
   if (precision != GATOR_PREC_FP32) return launch_self_attn_umma(qkv, out, batch, precision == GATOR_PREC_BF16X3, (cudaStream_t)stream);
   return launch_self_attn(qkv, out, batch, (cudaStream_t)stream);
+}
+
+extern "C" size_t gator_mdr_self_attention_image_bytes(int32_t batch) { return batch > 0 ? gator::self_attn2_image_bytes(batch) : 0; }
+
+extern "C" int gator_mdr_self_attention_f16(const float* qkv, void* image, float* out, int32_t batch, void* stream) {
+  using namespace gator;
+  GATOR_REQUIRE(qkv && out && image && batch >= 0, "gator_mdr_self_attention_f16: bad argument");
+  if (batch == 0) return GATOR_OK;
+  GATOR_TRY(launch_qkv_image(qkv, image, batch, (cudaStream_t)stream));
+  return launch_self_attn2(image, out, batch, (cudaStream_t)stream);
 }
 
 extern "C" int gator_mdr_layer_chain(const void* const* weights, int32_t layer, int32_t num_joint, int32_t precision,
@@ -447,7 +460,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   auto GB = [&](int s) { PackedW w; w.hi = a->weights_bf16 ? a->weights_bf16[s] : nullptr; w.lo = a->weights_bf16_lo ? a->weights_bf16_lo[s] : nullptr; return w; };
   // debug/ablation: `reserved` is a bit mask of the groups that take the bf16 kernels (0 = all):
   //   2 layer GEMMs, 4 self-attention, 8 head GEMM, 16 upsample_conv, 32 joint-feature GEMM
-  const int mask = a->reserved ? a->reserved : ~0;
+  const int mask = (a->reserved & ~128) ? (a->reserved & ~128) : ~0;
   auto P = [&](int bit) { return (a->precision != GATOR_PREC_FP32 && (mask & bit)) ? a->precision : (int)GATOR_PREC_FP32; };
   const int prec = P(2);
   const int cb = resolve_chunk(B, a->chunk);
@@ -462,7 +475,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     const int Msj = ns * J;
     mdr_embed_kernel<<<ns, 256, 0, stream>>>(a->pose2d + (size_t)s0 * J * 2, a->pose3d + (size_t)s0 * J * 3,
                                              G(MDR_JF_WPOSE), G(MDR_VF_CONST), G(MDR_VF_W3),
-                                             static_cast<const int*>(a->weights[MDR_VJ]), w.jf, nullptr, J);
+                                             static_cast<const int*>(a->weights[MDR_VJ]), w.jf, nullptr, J, a->pose3d_metres);
     GATOR_TRY(check_launch("mdr_embed_joints"));
     Epilogue e;
     e.bias_rows = G(MDR_JF_BIASROWS);
@@ -483,13 +496,15 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
     const int Mv = nb * V;
     mdr_embed_kernel<<<nb, 256, 0, stream>>>(a->pose2d + (size_t)b0 * J * 2, a->pose3d + (size_t)b0 * J * 3,
                                              G(MDR_JF_WPOSE), G(MDR_VF_CONST), G(MDR_VF_W3),
-                                             static_cast<const int*>(a->weights[MDR_VJ]), nullptr, w.x, J);
+                                             static_cast<const int*>(a->weights[MDR_VJ]), nullptr, w.x, J, a->pose3d_metres);
     GATOR_TRY(check_launch("mdr_embed"));
     Epilogue e;
     auto KV = [&](int l) { return w.kv + ((size_t)l * ns + (b0 - s0)) * J * 2 * E; };   // this chunk's K|V rows of layer l
 
     // bit 64 of the ablation mask disables the fused layer kernel
-    const bool fused = a->precision != GATOR_PREC_FP32 && have_chain && a->reserved == 0;
+    // bit 128 (development A/B switch): the round-1 fused kernels instead of the round-2 ones
+    const bool round1 = (a->reserved & 128) != 0;
+    const bool fused = a->precision != GATOR_PREC_FP32 && have_chain && (a->reserved & ~128) == 0;
     for (int l = 0; fused && l < GATOR_MDR_LAYERS; ++l) {
       const int base = MDR_NUM_GLOBAL + l * MDRL_NUM;
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
@@ -498,12 +513,22 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
       const float* prm[11] = {static_cast<const float*>(a->weights[pbase + MDRL_SO_B]), W(MDRL_N1_W), W(MDRL_N1_B),
                               W(MDRL_PROJ_B), W(MDRL_N2_W), W(MDRL_N2_B), W(MDRL_FC1_B), W(MDRL_FC2_B),
                               W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
+      const float* prm2[11] = {W(MDRL_SO_B), G(MDR_HEAD_B), W(MDRL_N1_B), W(MDRL_PROJ_B), W(MDRL_N2_W), W(MDRL_N2_B),
+                               W(MDRL_FC1_B), W(MDRL_FC2_B), W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
+      if (a->precision == GATOR_PREC_BF16X3 && !round1) {
+        // round-2 kernels: chain (3-term bf16 split, operands in tensor memory) -> fp16 operand images (in w.hid) ->
+        // fp16 self-attention core
+        GATOR_TRY(launch_mdr_chain2(l == 0 ? w.x : w.q, l == 0 ? nullptr : w.y, KV(l), a->weights[base + MDRL_CHAIN], prm,
+                                    w.q, nullptr, w.hid, nullptr, nb, J, stream));
+        GATOR_TRY(launch_self_attn2(w.hid, w.y, nb, stream));
+        if (l == GATOR_MDR_LAYERS - 1)   // last layer: x = x3 + linears.3(att) + b and the head projection, fused
+          GATOR_TRY(launch_mdr_chain2(w.q, w.y, KV(l), a->weights[MDR_CHAIN_FINAL], prm2, nullptr, nullptr, nullptr, w.hd, nb, J, stream));
+        continue;
+      }
       GATOR_TRY(launch_mdr_chain(l == 0 ? w.x : w.q, l == 0 ? nullptr : w.y, KV(l), a->weights[base + MDRL_CHAIN], prm,
                                  w.q, w.hid, nullptr, nb, J, a->precision == GATOR_PREC_BF16X3, stream));
       GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, a->precision == GATOR_PREC_BF16X3, stream));
       if (l == GATOR_MDR_LAYERS - 1) {   // last layer: x = x3 + linears.3(att) + b and the head projection, fused
-        const float* prm2[11] = {W(MDRL_SO_B), G(MDR_HEAD_B), W(MDRL_N1_B), W(MDRL_PROJ_B), W(MDRL_N2_W), W(MDRL_N2_B),
-                                 W(MDRL_FC1_B), W(MDRL_FC2_B), W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
         GATOR_TRY(launch_mdr_chain(w.q, w.y, KV(l), a->weights[MDR_CHAIN_FINAL], prm2, nullptr, nullptr, w.hd, nb, J,
                                    a->precision == GATOR_PREC_BF16X3, stream));
       }

@@ -1,0 +1,350 @@
+// MDR 431 x 431 self-attention core (lib/models/vanilla_transformer_encoder.py:36-46), round-2 kernel:
+//   out = softmax(q k^T / sqrt(32)) v      per (sample, head), fp16 operands / fp32 accumulate on tcgen05.
+//
+// Operands arrive PRE-PACKED: per (sample, head) one contiguous 82 944-byte record [Q | K | V], each a 432 x 32 fp16
+// image in the tcgen05 no-swizzle core-matrix layout  offset(row, d) = (row/8)*512 + (d/8)*128 + (row%8)*16 + (d%8)*2
+// (row 431 = zero padding), written by the layer-chain kernel's q|k|v epilogue (csrc/mdr_chain_umma.cu) or by
+// `qkv_image_kernel` below.  Q and K are K-major operands; the same image of V is the MN-major B operand of P V, so no
+// transpose of V exists anywhere.
+//
+// Persistent, warp-specialised, one CTA per SM, 18 warps:
+//   warp 17      TMA producer: one bulk copy per image into a 2-stage ring (the next (sample, head) loads while this one runs)
+//   warp 16      MMA issuer (one lane)
+//   warps 0..15  four softmax warpgroups; warpgroup t owns query tile t (rows 128t..128t+127), thread = query row, and
+//                tensor-memory columns [128t, 128t+128): S block (96 keys, fp32) in [0,96), O accumulator in [96,128).
+// Per key block j (96, 96, 96, 96, 48 keys) and tile t:   S = Q_t K_j^T  ->  warpgroup t: block max, P = exp2(S c - m) as
+// fp16 written IN PLACE over S with tcgen05.st (P is the tensor-memory A operand of the next MMA - it never touches shared
+// memory)  ->  O_t += P V_j, S_t = Q_t K_{j+1}^T.   The four tiles are at different points of this loop, so the MMA
+// latency of one tile is covered by the exp work of the other three; there is no block-wide barrier in the loop.
+// Softmax is the online form with a lazily updated running maximum: the row maximum only moves (and O is rescaled, in
+// tensor memory) when a block exceeds it by more than 2^8 - fp16 holds P <= 2^8 exactly as well as P <= 1.
+// fp16 (11-bit significand) instead of the round-1 3-term bf16 split: 2.2e-5 m end-to-end vertex error (CPU emulation,
+// tests/probes/attn_precision_cpu.py; plain bf16 would be 1.6e-4 m, over the 1e-4 m budget) at a third of the MMAs and
+// none of the residual arithmetic.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace gator {
+namespace {
+
+using namespace umma;
+
+constexpr int V = GATOR_V_COARSE;   // 431
+constexpr int VP = 432;
+constexpr int DK = 32;
+constexpr int E = 64;
+constexpr int IMG = VP * DK * 2;          // 27 648 B per image
+constexpr int ITEM = 3 * IMG;             // 82 944 B per (sample, head)
+constexpr int STAGES = 2;
+constexpr int KB = 96;                    // keys per block
+constexpr int NBLK = 5;                   // 4 x 96 + 48
+constexpr int NSOFT = 16;                 // softmax warps
+constexpr int NT = (NSOFT + 2) * 32;      // 576 threads
+constexpr int SMEM = STAGES * ITEM;       // 165 888 B dynamic
+constexpr float kScaleLog2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32)
+constexpr float kLazy = 8.0f;             // the running maximum moves only when exceeded by 2^8
+
+struct Bars {
+  uint64_t kv_full[STAGES], kv_empty[STAGES];
+  uint64_t s_full[4], p_full[4], o_full[4];
+};
+
+// One key block of one query row.  NK = 96 (full block) or 48 (last block: 47 keys + the zero pad row of K).
+// s_addr: this thread's lane + first column of the S block; o_addr: lane + first column of O.
+template <int NK>
+__device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t o_addr, bool first, bool valid, float& m, float& l) {
+  constexpr int NVAL = NK == KB ? KB : NK - 1;   // the last column of the last block is the pad key
+  uint32_t a[32], b[32];
+  // ---- pass A: block maximum (software-pipelined tensor-memory loads) ----
+  float mb;
+  tmem_ld32_async(s_addr, a);
+  tmem_ld_wait_dep32(a);
+  if (NK == KB) {
+    tmem_ld32_async(s_addr + 32, b);
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      m0 = fmax3(m0, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+      m1 = fmax3(m1, __uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
+    }
+    tmem_ld_wait_dep32(b);
+    tmem_ld32_async(s_addr + 64, a);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      m0 = fmax3(m0, __uint_as_float(b[i]), __uint_as_float(b[i + 1]));
+      m1 = fmax3(m1, __uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
+    }
+    tmem_ld_wait_dep32(a);
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      m0 = fmax3(m0, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+      m1 = fmax3(m1, __uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
+    }
+    mb = fmaxf(m0, m1);
+  } else {
+    tmem_ld16_async(s_addr + 32, b);
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      m0 = fmax3(m0, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+      m1 = fmax3(m1, __uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
+    }
+    tmem_ld_wait_dep16(b);
+#pragma unroll
+    for (int i = 0; i < 15; i += 3) m0 = fmax3(m0, __uint_as_float(b[i]), __uint_as_float(b[i + 1])), m1 = fmaxf(m1, __uint_as_float(b[i + 2]));
+    mb = fmaxf(m0, m1);
+  }
+  mb *= kScaleLog2;
+  // ---- running maximum (lazy) and, rarely, the rescale of O in tensor memory ----
+  if (first) {
+    m = mb;
+  } else {
+    const bool need = valid && (mb > m + kLazy);
+    if (__ballot_sync(0xffffffffu, need)) {   // warp-uniform: tcgen05.ld / st are warp-collective
+      const float f = need ? ex2_approx(m - mb) : 1.0f;
+      if (need) { l *= f; m = mb; }
+      // O_t is quiescent here: S of this block was committed after the previous block's P V, which has therefore completed
+      tmem_ld32_async(o_addr, a);
+      tmem_ld_wait_dep32(a);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) * f);
+      tmem_st32(o_addr, a);
+      tmem_st_wait();
+    }
+  }
+  // ---- pass B: P = exp2(s c - m) -> fp16, in place; row sum in fp32 ----
+  const float nm = -m;
+  float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+  auto chunk = [&](const uint32_t* s, uint32_t* p, int n, int nvalid) {   // n columns (32 or 16) -> n/2 packed registers
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      if (i < n) {
+        const float p0 = (i < nvalid) ? ex2_approx(fmaf(__uint_as_float(s[i]), kScaleLog2, nm)) : 0.f;
+        const float p1 = (i + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(s[i + 1]), kScaleLog2, nm)) : 0.f;
+        const float p2 = (i + 2 < nvalid) ? ex2_approx(fmaf(__uint_as_float(s[i + 2]), kScaleLog2, nm)) : 0.f;
+        const float p3 = (i + 3 < nvalid) ? ex2_approx(fmaf(__uint_as_float(s[i + 3]), kScaleLog2, nm)) : 0.f;
+        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+        p[i / 2] = pack_f16(p0, p1);
+        p[i / 2 + 1] = pack_f16(p2, p3);
+      }
+    }
+  };
+  uint32_t pk[16];
+  tmem_ld32_async(s_addr, a);
+  tmem_ld_wait_dep32(a);
+  tmem_ld32_async(s_addr + 32, b);          // (for NK = 48 only the first 16 of these columns are used)
+  chunk(a, pk, 32, 32);
+  tmem_ld_wait_dep32(b);
+  tmem_st16(s_addr, pk);                    // P columns [0,16) over S columns [0,16): S chunk 0 is in registers
+  if (NK == KB) {
+    tmem_ld32_async(s_addr + 64, a);
+    chunk(b, pk, 32, 32);
+    tmem_ld_wait_dep32(a);
+    tmem_st16(s_addr + 16, pk);
+    chunk(a, pk, 32, 32);
+    tmem_st16(s_addr + 32, pk);
+  } else {
+    chunk(b, pk, 16, NVAL - 32);
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(s_addr + 16), "r"(pk[0]), "r"(pk[1]),
+                 "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                 : "memory");
+  }
+  l += (l0 + l1) + (l2 + l3);
+  tmem_st_wait();
+}
+
+__global__ void __maxnreg__(112) mdr_self_attn2_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, int items) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ Bars bars;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (warp == 0) tmem_alloc(&tmem_slot, 512);
+  if (tid == 32) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.kv_full[s], 1); mbar_init(&bars.kv_empty[s], 1); }
+    for (int t = 0; t < 4; ++t) {
+      // warpgroup 3 holds rows 384..511 of which 384..430 exist: warps 2, 3 of it have no row at all and take no part
+      mbar_init(&bars.s_full[t], 1);
+      mbar_init(&bars.p_full[t], t < 3 ? 4 : 2);
+      mbar_init(&bars.o_full[t], 1);
+    }
+    mbar_init_fence();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int n_my = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA: blockIdx.x + i * gridDim.x
+
+  if (warp == NSOFT + 1) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      for (int i = 0; i < n_my; ++i) {
+        const int s = i % STAGES;
+        if (i >= STAGES) mbar_wait(&bars.kv_empty[s], ((i / STAGES) - 1) & 1);
+        const uint8_t* src = img + (size_t)(blockIdx.x + (size_t)i * gridDim.x) * ITEM;
+        uint8_t* dst = smem + s * ITEM;
+        mbar_arrive_expect_tx(&bars.kv_full[s], ITEM);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) bulk_copy_g2s(dst + c * IMG, src + c * IMG, IMG, &bars.kv_full[s]);
+      }
+    }
+  } else if (warp == NSOFT) {
+    // ===== MMA issuer =====
+    constexpr uint32_t id_s96 = idesc_f16(128, KB), id_s48 = idesc_f16(128, 48), id_pv = idesc_f16(128, DK, 1);
+    auto issue_qk = [&](uint32_t stage_base, int t, int j) {   // S_t = Q_t K_j^T (2 k-steps of 16)
+      const uint32_t q0 = stage_base + t * (16 * 512), k0 = stage_base + IMG + j * (KB / 8) * 512;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+        mma_bf16(tmem + t * 128, smem_desc(q0 + ks * 256, 128, 512), smem_desc(k0 + ks * 256, 128, 512), j < NBLK - 1 ? id_s96 : id_s48, ks);
+    };
+    auto issue_pv = [&](uint32_t stage_base, int t, int j) {   // O_t (+)= P V_j: A = P in tensor memory, B = V MN-major
+      const uint32_t v0 = stage_base + 2 * IMG + j * (KB / 8) * 512;
+      const int ksteps = j < NBLK - 1 ? KB / 16 : 3;
+      for (int ks = 0; ks < ksteps; ++ks)
+        mma_ts(tmem + t * 128 + KB, tmem + t * 128 + ks * 8, smem_desc(v0 + ks * 1024, 512, 128), id_pv, (j | ks) != 0);
+    };
+    uint32_t ph_p = 0;   // parity of the next p_full completion (same for all four tiles: they advance in lockstep here)
+    for (int i = 0; i < n_my; ++i) {
+      const int s = i % STAGES;
+      const uint32_t sb = smem_u32(smem + s * ITEM);
+      if (i == 0) {
+        mbar_wait(&bars.kv_full[s], 0);
+        if (lane == 0) {
+          for (int t = 0; t < 4; ++t) { issue_qk(sb, t, 0); mma_commit(&bars.s_full[t]); }
+        }
+        __syncwarp();
+      }
+      for (int j = 0; j < NBLK; ++j) {
+        const bool last = j == NBLK - 1;
+        uint32_t sb_next = 0;
+        if (last && i + 1 < n_my) {
+          const int s1 = (i + 1) % STAGES;
+          mbar_wait(&bars.kv_full[s1], ((i + 1) / STAGES) & 1);
+          sb_next = smem_u32(smem + s1 * ITEM);
+        }
+        for (int t = 0; t < 4; ++t) {
+          mbar_wait(&bars.p_full[t], ph_p);
+          tc_fence_after();
+          if (lane == 0) {
+            issue_pv(sb, t, j);
+            if (!last) {
+              issue_qk(sb, t, j + 1);
+              mma_commit(&bars.s_full[t]);
+            } else {
+              mma_commit(&bars.o_full[t]);
+              if (t == 3) mma_commit(&bars.kv_empty[s]);   // every MMA that reads this stage has been issued
+              if (sb_next) {                                // first block of the next (sample, head) right behind it
+                issue_qk(sb_next, t, 0);
+                mma_commit(&bars.s_full[t]);
+              }
+            }
+          }
+          __syncwarp();
+        }
+        ph_p ^= 1;
+      }
+    }
+  } else {
+    // ===== softmax warpgroups =====
+    const int t = warp >> 2;                        // query tile
+    const int row = (warp & 3) * 32 + lane;         // row in tile = tensor-memory lane
+    const int q = t * 128 + row;
+    const bool valid = q < V;
+    const bool warp_active = t * 128 + (warp & 3) * 32 < V;
+    if (warp_active) {
+      const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
+      const uint32_t s_addr = tmem + lane_addr + t * 128, o_addr = s_addr + KB;
+      uint32_t ph_s = 0, ph_o = 0;
+      for (int i = 0; i < n_my; ++i) {
+        const int item = blockIdx.x + i * gridDim.x;
+        float m = 0.f, l = 0.f;
+#pragma unroll 1
+        for (int j = 0; j < NBLK; ++j) {
+          mbar_wait(&bars.s_full[t], ph_s);
+          ph_s ^= 1;
+          tc_fence_after();
+          if (j < NBLK - 1) softmax_block<KB>(s_addr, o_addr, j == 0, valid, m, l);
+          else softmax_block<48>(s_addr, o_addr, false, valid, m, l);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars.p_full[t]);
+        }
+        // ---- O out: thread = row, 32 fp32 = one 128-byte line of out[b, q, h*32 .. h*32+31] ----
+        mbar_wait(&bars.o_full[t], ph_o);
+        ph_o ^= 1;
+        tc_fence_after();
+        uint32_t o[32];
+        tmem_ld32_async(o_addr, o);
+        tmem_ld_wait_dep32(o);
+        if (valid) {
+          const float inv = 1.0f / l;
+          float4* dst = reinterpret_cast<float4*>(out + ((size_t)(item >> 1) * V + q) * E + (item & 1) * DK);
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            dst[c] = make_float4(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv, __uint_as_float(o[4 * c + 2]) * inv,
+                                 __uint_as_float(o[4 * c + 3]) * inv);
+        }
+        // the next item's first P V (accumulate = 0) overwrites O only after this thread's p_full arrival for its block 0
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// fp32 qkv rows (nb*431, 192) -> per (sample, head) [Q | K | V] fp16 images.  One thread per 16-byte chunk
+// (8 consecutive d of one row of one tensor); row 431 is written as zeros.
+__global__ void __launch_bounds__(256) qkv_image_kernel(const float* __restrict__ qkv, uint8_t* __restrict__ img, int nb) {
+  const long long idx = (long long)blockIdx.x * 256 + threadIdx.x;
+  const long long total = (long long)nb * 2 * 3 * VP * 4;
+  if (idx >= total) return;
+  const int kc = (int)(idx & 3);
+  long long r = idx >> 2;
+  const int row = (int)(r % VP);
+  r /= VP;
+  const int which = (int)(r % 3);
+  r /= 3;
+  const int h = (int)(r & 1);
+  const long long b = r >> 1;
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (row < V) {
+    const float4* src = reinterpret_cast<const float4*>(qkv + ((size_t)b * V + row) * (3 * E) + which * E + h * DK + kc * 8);
+    const float4 x = __ldg(src), y = __ldg(src + 1);
+    o = make_uint4(pack_f16(x.x, x.y), pack_f16(x.z, x.w), pack_f16(y.x, y.y), pack_f16(y.z, y.w));
+  }
+  uint8_t* dst = img + ((size_t)(b * 2 + h) * 3 + which) * IMG + (row >> 3) * 512 + kc * 128 + (row & 7) * 16;
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+
+}  // namespace
+
+size_t self_attn2_image_bytes(int nb) { return (size_t)nb * 2 * ITEM; }
+
+int launch_qkv_image(const float* qkv, void* img, int nb, cudaStream_t stream) {
+  const long long total = (long long)nb * 2 * 3 * VP * 4;
+  qkv_image_kernel<<<(unsigned)((total + 255) / 256), 256, 0, stream>>>(qkv, static_cast<uint8_t*>(img), nb);
+  return check_launch("qkv_image");
+}
+
+// img: self_attn2_image_bytes(nb) bytes of [Q | K | V] records; out (nb*431, 64) fp32
+int launch_self_attn2(const void* img, float* out, int nb, cudaStream_t stream) {
+  static DeviceOnce attr_once;
+  static int num_sms[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  GATOR_TRY(attr_once.run("mdr_self_attn2", [&](int d) -> cudaError_t {
+    GATOR_CUDA_OK(cudaFuncSetAttribute(mdr_self_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    return cudaDeviceGetAttribute(&num_sms[d & 63], cudaDevAttrMultiProcessorCount, d);
+  }));
+  const int items = nb * 2;
+  const int sms = num_sms[dev & 63] > 0 ? num_sms[dev & 63] : 148;
+  const int grid = items < sms ? items : sms;
+  mdr_self_attn2_kernel<<<grid, NT, SMEM, stream>>>(static_cast<const uint8_t*>(img), out, items);
+  return check_launch("mdr_self_attn2");
+}
+
+}  // namespace gator

@@ -360,11 +360,11 @@ mdr_self_attn_umma_kernel(const float* __restrict__ qkv, float* __restrict__ out
 }  // namespace
 
 int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream) {
-  static unsigned long long attr_seen = 0;
-  if (first_use_on_device(&attr_seen)) {
-    cudaFuncSetAttribute(mdr_self_attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(false));
-    cudaFuncSetAttribute(mdr_self_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true));
-  }
+  static DeviceOnce attr_once;
+  GATOR_TRY(attr_once.run("mdr_self_attn_umma", [&](int) -> cudaError_t {
+    GATOR_CUDA_OK(cudaFuncSetAttribute(mdr_self_attn_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(false)));
+    return cudaFuncSetAttribute(mdr_self_attn_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(true));
+  }));
   const int qsplit = nb * 2 * 4 <= 160 ? 4 : 1;     // up to 20 samples: one CTA per query tile still fits one wave
   if (split) mdr_self_attn_umma_kernel<true><<<nb * 2 * qsplit, NT, smem_bytes(true), stream>>>(qkv, out, qsplit);
   else mdr_self_attn_umma_kernel<false><<<nb * 2 * qsplit, NT, smem_bytes(false), stream>>>(qkv, out, qsplit);

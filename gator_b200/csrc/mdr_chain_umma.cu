@@ -384,12 +384,12 @@ mdr_chain_kernel(ChainParams p) {
 // x_in / att_in / kv / outputs as in ChainParams; prm = 11 device pointers (so_b of the PREVIOUS layer first).
 int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
                      float* x3_out, float* qkv_out, float* hd_out, int nb, int J, bool split, cudaStream_t stream) {
-  static unsigned long long attr_seen = 0;
-  if (first_use_on_device(&attr_seen)) {
-    cudaFuncSetAttribute(mdr_chain_kernel<1, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
-    cudaFuncSetAttribute(mdr_chain_kernel<1, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
-    cudaFuncSetAttribute(mdr_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
-  }
+  static DeviceOnce attr_once;
+  GATOR_TRY(attr_once.run("mdr_chain", [&](int) -> cudaError_t {
+    GATOR_CUDA_OK(cudaFuncSetAttribute(mdr_chain_kernel<1, 17>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ)));
+    GATOR_CUDA_OK(cudaFuncSetAttribute(mdr_chain_kernel<1, 19>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ)));
+    return cudaFuncSetAttribute(mdr_chain_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(1, MAXJ));
+  }));
   ChainParams p;
   p.x_in = x_in; p.att_in = att_in; p.kv = kv; p.blob = static_cast<const uint8_t*>(blob);
   for (int i = 0; i < 11; ++i) p.prm[i] = prm[i];

@@ -230,14 +230,14 @@ int launch_smpl_skin_umma(const float* vposed, int ld, const float* amat, const 
   const long long chunks = (long long)p.n_tiles * 1024;
   skin_t_image_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(amat, S, chunks, static_cast<uint8_t*>(timg));
   GATOR_TRY(check_launch("skin_t_image"));
-  static unsigned long long attr_seen = 0;
+  static DeviceOnce attr_once;
   static int sm_count[64];
   int dev = 0;
   cudaGetDevice(&dev);
-  if (first_use_on_device(&attr_seen)) {
-    cudaFuncSetAttribute(smpl_skin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-  }
+  GATOR_TRY(attr_once.run("smpl_skin_umma", [&](int d) -> cudaError_t {
+    GATOR_CUDA_OK(cudaFuncSetAttribute(smpl_skin_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    return cudaDeviceGetAttribute(&sm_count[d & 63], cudaDevAttrMultiProcessorCount, d);
+  }));
   const int sms = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
   const int total = p.m_tiles * p.n_tiles;
   smpl_skin_umma_kernel<<<total < sms ? total : sms, NTHREADS, SMEM, stream>>>(p);

@@ -221,9 +221,10 @@ extern "C" int gator_csr_spmm(const gator_csr_args* a, void* stream) {
     const int slices = ceil_div(a->rows, RS_ROWS);
     int parts = (148 * 4) / slices;
     parts = parts < 1 ? 1 : (parts > a->batch ? a->batch : parts);
-    static unsigned long long attr_seen2 = 0;
-    if (first_use_on_device(&attr_seen2))
-      cudaFuncSetAttribute(csr_spmm3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+    static DeviceOnce attr_once2;
+    GATOR_TRY(attr_once2.run("csr_spmm3_rows", [&](int) -> cudaError_t {
+      return cudaFuncSetAttribute(csr_spmm3_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024);
+    }));
     csr_spmm3_rows_kernel<<<slices * parts, 256, (size_t)a->cols * 24 + 64, (cudaStream_t)stream>>>(
         a->rowptr, a->colidx, a->values, a->x, a->y, a->rows, a->cols, a->scale, a->batch, slices, parts);
     return check_launch("csr_spmm3_rows");
@@ -232,10 +233,10 @@ extern "C" int gator_csr_spmm(const gator_csr_args* a, void* stream) {
     const int per_sample = a->cols * 12;
     int NS = 96 * 1024 / per_sample;                 // <= 96 KB of staged inputs per CTA (2 CTAs / SM)
     NS = NS > 8 ? 8 : NS;
-    static unsigned long long attr_seen = 0;
-    if (first_use_on_device(&attr_seen)) {
-      cudaFuncSetAttribute(csr_spmm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    }
+    static DeviceOnce attr_once;
+    GATOR_TRY(attr_once.run("csr_spmm3", [&](int) -> cudaError_t {
+      return cudaFuncSetAttribute(csr_spmm3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    }));
     csr_spmm3_kernel<<<ceil_div(a->batch, NS), 256, (size_t)NS * per_sample, (cudaStream_t)stream>>>(
         a->rowptr, a->colidx, a->values, a->x, a->y, a->rows, a->cols, a->scale, a->batch, NS);
     return check_launch("csr_spmm3");

@@ -230,9 +230,10 @@ int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, const void* Wpa
   p.stages = (p.K_pad / BKE <= 2) ? 1 : 2;
   const int operand = (p.Wlo ? 2 : 1) * p.stages * (A_STAGE + p.BN * BKE * 2);
   const int smem = operand > 2 * STG_BYTES ? operand : 2 * STG_BYTES;
-  static unsigned long long attr_seen = 0;
-  if (first_use_on_device(&attr_seen))
-    cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * A_STAGE + 2 * 128 * BKE * 2));
+  static DeviceOnce attr_once;
+  GATOR_TRY(attr_once.run("umma_gemm", [&](int) -> cudaError_t {
+    return cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * A_STAGE + 2 * 128 * BKE * 2));
+  }));
   dim3 grid(ceil_div(M, BM), n_tiles);
   umma_gemm_kernel<<<grid, 256, smem, stream>>>(p);
   return check_launch("umma_gemm");

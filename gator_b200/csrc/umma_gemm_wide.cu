@@ -259,15 +259,15 @@ int gemm_bf16x3_wide(const float* A, int lda, const void* Wimg, void* a_img, siz
   const long long chunks = (long long)p.m_tiles * p.kblocks * 512;
   wide_a_image_kernel<<<(unsigned)((chunks + 255) / 256), 256, 0, stream>>>(A, lda, M, K, p.kblocks, chunks, static_cast<uint8_t*>(a_img));
   GATOR_TRY(check_launch("wide_a_image"));
-  static unsigned long long attr_seen = 0;
+  static DeviceOnce attr_once;
   static int sm_count[64];
   int dev = 0;
   cudaGetDevice(&dev);
-  if (first_use_on_device(&attr_seen)) {
-    cudaFuncSetAttribute(umma_gemm_wide_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem(4, 2));
-    cudaFuncSetAttribute(umma_gemm_wide_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem(3, 4));
-    cudaDeviceGetAttribute(&sm_count[dev & 63], cudaDevAttrMultiProcessorCount, dev);
-  }
+  GATOR_TRY(attr_once.run("umma_gemm_wide", [&](int d) -> cudaError_t {
+    GATOR_CUDA_OK(cudaFuncSetAttribute(umma_gemm_wide_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem(4, 2)));
+    GATOR_CUDA_OK(cudaFuncSetAttribute(umma_gemm_wide_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, wide_smem(3, 4)));
+    return cudaDeviceGetAttribute(&sm_count[d & 63], cudaDevAttrMultiProcessorCount, d);
+  }));
   const int sms = sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148;
   const int total = p.m_tiles * p.n_tiles;
   if (p.kblocks <= 8)

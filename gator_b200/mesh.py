@@ -33,6 +33,8 @@ class _Csr:
         """y[..., r, :] = scale * sum_k val_k x[..., col_k, :] for x of shape (N,F) or (B,N,F)."""
         if not x.is_cuda:
             raise RuntimeError('gator_b200.Mesh: CUDA tensors only (no CPU fallback)')
+        if x.device != self.rowptr.device:
+            raise RuntimeError(f'gator_b200.Mesh: input on {x.device} but the operator is on {self.rowptr.device}')
         if x.dtype != torch.float32:
             raise TypeError('gator_b200.Mesh: float32 only')
         squeeze = x.dim() == 2

@@ -18,7 +18,7 @@ import torch
 import torch.nn as nn
 
 from .. import _lib, config, graph
-from ..packing import pack_umma_weight_pair
+from ..packing import pack_umma_weight_pair, pack_umma_weight_pairs, pack_umma_blob
 
 _BF16_GLOBAL = {'LIFT_W'}
 _BF16_BLOCK = {'QKV_W', 'PROJ_W', 'GCN_W01', 'XF_W01', 'XF_WB', 'FC1_W', 'FC2_W'}
@@ -197,9 +197,13 @@ class GAT(nn.Module):
         self._packed = None
         return out
 
+    def _need_full_pack(self):
+        return not (self.fused and 2 <= self.num_joint <= 21)
+
     @torch.no_grad()
     def pack(self):
         """Fold constants and lay the weights out for the kernels; one device tensor per ABI slot."""
+        full = self._need_full_pack()
         dev = self.lifter.weight.device
         if dev.type != 'cuda':
             raise RuntimeError('gator_b200.GAT: parameters must be on a CUDA device (no CPU fallback)')
@@ -257,12 +261,8 @@ class GAT(nn.Module):
                 pieces += [w01[64 * u:64 * u + 64], wb[:, 64 * u:64 * u + 64]]
             for u in range(8):
                 pieces += [b['FC1_W'][64 * u:64 * u + 64], b['FC2_W'][:, 64 * u:64 * u + 64]]
-            parts = []
-            for w in pieces:
-                hi, lo = pack_umma_weight_pair(w.contiguous())
-                assert hi.numel() == 64 * 128
-                parts += [hi.reshape(-1), lo.reshape(-1)]
-            blob = torch.cat(parts).contiguous()
+            blob = pack_umma_blob(pieces)
+            assert blob.numel() == len(pieces) * 2 * 64 * 128
             xfb = torch.zeros(192, device=dev)
             xfb[:144] = b['XF_B01']
             plist = [b['LN1_W'], b['LN1_B'], b['QKV_B'], b['PROJ_B'], b['GCN_M'], b['GCN_ADIAG'], b['GCN_AOFF'],
@@ -274,16 +274,22 @@ class GAT(nn.Module):
             t['CHAIN_BLOBS'] = torch.tensor(blobs, dtype=torch.int64, device=dev)
             t['CHAIN_PRM'] = torch.tensor(prms, dtype=torch.int64, device=dev)
         tensors = [t[n] for n in gnames]
-        packed = [pack_umma_weight_pair(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
         for b in block_dicts:
             tensors += [b[n] for n in bnames]
-            packed += [pack_umma_weight_pair(b[n]) if n in _BF16_BLOCK else None for n in bnames]
+        # per-slot tcgen05 images: the lifter always; the per-block matrices only for the kernel-per-op tensor-core path
+        # (fused = False or J outside the fused kernel's range) - the fused kernel reads CHAIN_BLOBS instead
+        want = [(n in _BF16_GLOBAL) for n in gnames]
+        for _ in block_dicts:
+            want += [(n in _BF16_BLOCK) and full for n in bnames]
+        pairs = iter(pack_umma_weight_pairs([tensors[i] for i, w_ in enumerate(want) if w_]))
+        packed = [next(pairs) if w_ else None for w_ in want]
         tensors += keep
         table = (ctypes.c_void_p * (len(gnames) + len(bnames) * len(block_dicts)))(
             *[(t_.data_ptr() if t_ is not None else None) for t_ in tensors[:len(gnames) + len(bnames) * len(block_dicts)]])
         table16 = (ctypes.c_void_p * len(packed))(*[(t_[0].data_ptr() if t_ is not None else None) for t_ in packed])
         table16lo = (ctypes.c_void_p * len(packed))(*[(t_[1].data_ptr() if t_ is not None else None) for t_ in packed])
         self._packed = ((tensors, packed, table16, table16lo), table, dev)
+        self._packed_full = full
         return self
 
     def _workspace(self, batch, dev):
@@ -297,11 +303,13 @@ class GAT(nn.Module):
         """pose2d (B, 2J) [or (B,J,2)] -> (x_out (B,3J) mm, x (B,J,128))  (GAT.py:133-152)."""
         if self.training:
             raise NotImplementedError('gator_b200.GAT implements the eval() forward only')
-        if self._packed is None:
+        if self._packed is None or (self._need_full_pack() and not self._packed_full):
             self.pack()
         (_, _, table16, table16lo), table, dev = self._packed
         if not pose2d.is_cuda:
             raise RuntimeError('gator_b200.GAT: input must be a CUDA tensor (no CPU fallback)')
+        if pose2d.device != dev:
+            raise RuntimeError(f'gator_b200.GAT: input on {pose2d.device} but the packed weights are on {dev}')
         B = pose2d.shape[0]
         J = self.num_joint
         x = pose2d.detach().reshape(B, J * 2).to(torch.float32).contiguous()

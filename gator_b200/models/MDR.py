@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from .. import _lib, config, graph
 from ..mesh import Mesh
-from ..packing import pack_umma_weight_pair, pack_umma_wide
+from ..packing import pack_umma_blob, pack_umma_weight_pairs, pack_umma_wide
 
 _BF16_GLOBAL = {'JF_WFEAT', 'HEAD_W', 'UP_W'}
 _BF16_LAYER = {'WQ', 'WKV', 'PROJ_W', 'FC1_W', 'FC2_W', 'SQKV_W', 'SO_W'}
@@ -102,6 +102,10 @@ class MDR(nn.Module):
         J_regressor = torch.from_numpy(np.load(config.base_data_path('J_regressor_h36m.npy')).astype(np.float32))
         self.joints_template = torch.matmul(J_regressor, init_vertices)          # MDR.py:85-86
         self.vj_relation = graph.nearest_joint(self.joints_template.numpy(), v431.numpy())
+        if int(np.max(self.vj_relation)) >= num_joint:
+            # the reference indexes x[:, self.vj_relation, 2:5] (MDR.py:127) and raises IndexError here
+            raise IndexError(f'vj_relation refers to joint {int(np.max(self.vj_relation))} of the 17-joint h36m regressor, '
+                             f'but num_joint = {num_joint}')
         self.num_verts = v431.shape[0]
         if self.num_verts != V_COARSE or init_vertices.shape[0] != V_FULL:
             raise NotImplementedError('kernels are built for the 6890 -> 431 SMPL hierarchy')
@@ -144,8 +148,12 @@ class MDR(nn.Module):
         self._packed = None
         return out
 
+    def _need_full_pack(self):
+        return self.bf16_mask != 0 or self.precision == _lib.PREC_BF16
+
     @torch.no_grad()
     def pack(self):
+        full = self._need_full_pack()
         dev = self.upsample_conv.weight.device
         if dev.type != 'cuda':
             raise RuntimeError('gator_b200.MDR: parameters must be on a CUDA device (no CPU fallback)')
@@ -202,29 +210,28 @@ class MDR(nn.Module):
             units = [prev_so if prev_so is not None else torch.zeros(E, E, device=dev), l['WQ'], l['PROJ_W']]
             units += [fc1[64 * q:64 * q + 64] for q in range(4)] + [fc2[:, 64 * q:64 * q + 64] for q in range(4)]
             units += [f(sa.linears[i].weight) for i in range(3)]
-            blob = []
-            for u in units:
-                hi, lo = pack_umma_weight_pair(u.contiguous())
-                blob += [hi.reshape(-1), lo.reshape(-1)]
-            l['CHAIN'] = torch.cat(blob).contiguous()
+            l['CHAIN'] = pack_umma_blob(units)
             prev_so = l['SO_W']
             layer_dicts.append(l)
         head64 = torch.zeros(E, E, device=dev)
         head64[:28] = t['HEAD_W']
-        fin = []
-        for u in (prev_so, head64):
-            hi, lo = pack_umma_weight_pair(u.contiguous())
-            fin += [hi.reshape(-1), lo.reshape(-1)]
-        t['CHAIN_FINAL'] = torch.cat(fin).contiguous()
+        t['CHAIN_FINAL'] = pack_umma_blob([prev_so, head64])
         tensors = [t[n] for n in gnames]
-        packed = [pack_umma_weight_pair(t[n]) if n in _BF16_GLOBAL else None for n in gnames]
         for l in layer_dicts:
             tensors += [l[n] for n in lnames]
-            packed += [pack_umma_weight_pair(l[n]) if n in _BF16_LAYER else None for n in lnames]
+        # per-slot tcgen05 images: the fused path reads the CHAIN blobs and UP_W_WIDE and needs only the joint-token
+        # matrices here; the rest serves the kernel-per-op tensor-core path (ablation mask) and plain bf16 upsample_conv
+        always_g, always_l = {'JF_WFEAT'}, {'WKV'}
+        want = [(n in _BF16_GLOBAL) and (full or n in always_g) for n in gnames]
+        for _ in layer_dicts:
+            want += [(n in _BF16_LAYER) and (full or n in always_l) for n in lnames]
+        pairs = iter(pack_umma_weight_pairs([tensors[i] for i, w_ in enumerate(want) if w_]))
+        packed = [next(pairs) if w_ else None for w_ in want]
         table = (ctypes.c_void_p * len(tensors))(*[t_.data_ptr() for t_ in tensors])
         table16 = (ctypes.c_void_p * len(packed))(*[(t_[0].data_ptr() if t_ is not None else None) for t_ in packed])
         table16lo = (ctypes.c_void_p * len(packed))(*[(t_[1].data_ptr() if t_ is not None else None) for t_ in packed])
         self._packed = ((tensors, packed, table16, table16lo), table, dev)
+        self._packed_full = full
         return self
 
     def _chunk(self):
@@ -232,6 +239,8 @@ class MDR(nn.Module):
         to stay L2-resident between kernels; tensor-core path (fused layer kernel): 4096 - fewer launches and a
         smaller partial last wave (measured on B200, B = 4096: 148 -> 25.3 ms/step, 1184 -> 20.4 ms, 4096 -> 19.9 ms;
         820 KB of workspace per sample)."""
+        if self.chunk and self.chunk > 0:
+            return int(self.chunk)
         return 148 if self.precision == _lib.PREC_FP32 else 4096
 
     def _workspace(self, batch, dev):
@@ -240,17 +249,20 @@ class MDR(nn.Module):
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         return self._ws
 
-    def forward_parts(self, pose2d, pose3d_mm, feat, want_coarse=False):
+    def forward_parts(self, pose2d, pose3d_mm, feat, want_coarse=False, pose3d_metres=False):
         """The fused entry: what GATOR.forward feeds MDR, without materialising the (B,J,133) concat
-        (GATOR.py:19).  pose2d (B,J,2), pose3d_mm (B,J,3) millimetres, feat (B,J,128) -> (B,6890,3) m."""
+        (GATOR.py:19).  pose2d (B,J,2), pose3d_mm (B,J,3) millimetres (metres with pose3d_metres=True),
+        feat (B,J,128) -> (B,6890,3) m."""
         if self.training:
             raise NotImplementedError('gator_b200.MDR implements the eval() forward only')
-        if self._packed is None:
+        if self._packed is None or (self._need_full_pack() and not self._packed_full):
             self.pack()
         (_, _, table16, table16lo), table, dev = self._packed
         for t_ in (pose2d, pose3d_mm, feat):
             if not t_.is_cuda:
                 raise RuntimeError('gator_b200.MDR: inputs must be CUDA tensors (no CPU fallback)')
+            if t_.device != dev:
+                raise RuntimeError(f'gator_b200.MDR: input on {t_.device} but the packed weights are on {dev}')
         B, J = pose2d.shape[0], self.num_joint
         p2 = pose2d.detach().reshape(B, J, 2).float().contiguous()
         p3 = pose3d_mm.detach().reshape(B, J, 3).float().contiguous()
@@ -260,7 +272,7 @@ class MDR(nn.Module):
         if B > 0:
             ws = self._workspace(B, dev)
             a = _lib.MdrArgs(num_joint=J, batch=B, chunk=self._chunk(), alpha=int(self.alpha), precision=self.precision,
-                             reserved=self.bf16_mask, weights=table, weights_bf16=table16, weights_bf16_lo=table16lo, pose2d=_lib.ptr(p2), pose3d=_lib.ptr(p3), feat=_lib.ptr(ft),
+                             reserved=self.bf16_mask, pose3d_metres=int(pose3d_metres), weights=table, weights_bf16=table16, weights_bf16_lo=table16lo, pose2d=_lib.ptr(p2), pose3d=_lib.ptr(p3), feat=_lib.ptr(ft),
                              mesh=_lib.ptr(mesh), coarse=_lib.ptr(coarse), workspace=_lib.ptr(ws),
                              workspace_bytes=ws.numel())
             with torch.cuda.device(dev):
@@ -269,7 +281,7 @@ class MDR(nn.Module):
 
     def forward(self, x):
         """x = pose_combine (B, J, 2+3+128), columns [pose2d | pose3d in metres | feat] (MDR.py:124-170)."""
-        return self.forward_parts(x[:, :, 0:2], x[:, :, 2:5] * 1000.0, x[:, :, 5:])
+        return self.forward_parts(x[:, :, 0:2], x[:, :, 2:5], x[:, :, 5:], pose3d_metres=True)
 
 
 def get_model(num_joint, embed_dim):

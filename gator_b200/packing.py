@@ -37,6 +37,50 @@ def pack_umma_weight_pair(W: torch.Tensor):
     return pack_umma_weight(hi), pack_umma_weight(Wf - hi)
 
 
+def _pack_groups(ws):
+    """Stack matrices of equal shape and pack each stack with one set of device ops.
+    Yields (indices, both) with both = bf16 (n, 2 (hi|lo), N_pad/8, K_pad/8, 8, 8)."""
+    groups = {}
+    for i, w in enumerate(ws):
+        groups.setdefault(tuple(w.shape), []).append(i)
+    for (N, K), idx in groups.items():
+        BN, n_tiles, K_pad = umma_weight_layout(N, K)
+        N_pad = BN * n_tiles
+        W = torch.stack([ws[i].float() for i in idx])                       # (n, N, K)
+        if (N_pad, K_pad) != (N, K):
+            Wp = torch.zeros((len(idx), N_pad, K_pad), dtype=torch.float32, device=W.device)
+            Wp[:, :N, :K] = W
+            W = Wp
+        hi = W.to(torch.bfloat16)
+        lo = (W - hi.float()).to(torch.bfloat16)
+        both = torch.stack([hi, lo], 1)                                     # (n, 2, N_pad, K_pad)
+        yield idx, both.reshape(len(idx), 2, N_pad // 8, 8, K_pad // 8, 8).permute(0, 1, 2, 4, 3, 5).contiguous()
+
+
+@torch.no_grad()
+def pack_umma_weight_pairs(ws):
+    """[W_i (N_i, K_i)] -> [(hi_i, lo_i)], the same images as pack_umma_weight_pair, but matrices of equal shape are stacked
+    and packed together (pack() of a model issues a few dozen launches instead of several thousand)."""
+    out = [None] * len(ws)
+    for idx, both in _pack_groups(ws):
+        for j, i in enumerate(idx):
+            out[i] = (both[j, 0], both[j, 1])
+    return out
+
+
+@torch.no_grad()
+def pack_umma_blob(ws) -> torch.Tensor:
+    """[W_i] -> one contiguous bf16 tensor [hi_0 | lo_0 | hi_1 | lo_1 | ...] (the weight-unit blobs of the fused kernels);
+    every W_i must pack to the same number of elements."""
+    blob = None
+    for idx, both in _pack_groups(ws):
+        flat = both.reshape(len(idx), 2, -1)
+        if blob is None:
+            blob = torch.empty((len(ws), 2, flat.shape[2]), dtype=torch.bfloat16, device=flat.device)
+        blob[torch.tensor(idx, device=flat.device)] = flat
+    return blob.reshape(-1)
+
+
 @torch.no_grad()
 def pack_umma_wide(W: torch.Tensor) -> torch.Tensor:
     """W (N,K) float -> bf16 [n_tiles, kblocks, 2 (hi|lo), 32, 4, 8, 8] for the wide-N kernel (csrc/umma_gemm_wide.cu):

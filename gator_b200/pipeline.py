@@ -27,7 +27,9 @@ def plan_slices(batch: int, ratio: float, floor: int = 148):
 
 
 class HostPipeline:
-    """forward(pose2d_host (B,J,2) pinned) -> (mesh_host (B,6890,3), pose3d_host (B,J,3)) pinned, both fp32."""
+    """forward(pose2d_host (B,J,2) pinned) -> (mesh_host (B,6890,3), pose3d_host (B,J,3)) pinned, both fp32.
+    The call returns after the device-to-host copies have completed (it synchronises its copy stream), so the results can
+    be read immediately; the two pinned buffers belong to the pipeline and are overwritten by the next forward()."""
 
     RATIO = 0.35
 
@@ -88,4 +90,8 @@ class HostPipeline:
             mesh.record_stream(self.copy_stream)
             self._keep.append(mesh)
         main.wait_stream(self.copy_stream)
+        # host-to-host contract: the returned pinned buffers are complete when this call returns (the caller reads them
+        # with numpy straight away, base.py:223-229).  They are reused by the next forward(): consume or copy them first.
+        self.copy_stream.synchronize()
+        self._keep.clear()
         return self.mesh_host, self.pose3d_host

@@ -140,6 +140,8 @@ class SMPL_Layer(Module):
         dev = p['dev']
         if not th_pose_axisang.is_cuda:
             raise RuntimeError('gator_b200.SMPL_Layer: inputs must be CUDA tensors (no CPU fallback)')
+        if th_pose_axisang.device != dev:
+            raise RuntimeError(f'gator_b200.SMPL_Layer: input on {th_pose_axisang.device} but the buffers are on {dev}')
         B = th_pose_axisang.shape[0]
         pose = th_pose_axisang.detach().reshape(B, 72).float().contiguous()
         has_betas = th_betas is not None and th_betas.numel() != 1      # zeros(1) is the "not given" sentinel

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define GATOR_ABI_VERSION 1
+#define GATOR_ABI_VERSION 2
 
 typedef enum {
   GATOR_OK = 0,
@@ -182,11 +182,14 @@ typedef struct {
   int32_t alpha;               /* cfg.MODEL.alpha (MDR.py:115,162)                      */
   int32_t precision;           /* gator_precision                                       */
   int32_t reserved;
+  int32_t pose3d_metres;       /* 0: pose3d is in millimetres and divided by 1000 inside (GATOR.py:19);
+                                  1: pose3d is already in metres (MDR.forward's pose_combine[:, :, 2:5], MDR.py:127)  */
+  int32_t reserved2;
   const void* const* weights;  /* HOST array of MDR_NUM_GLOBAL + 3*MDRL_NUM device pointers */
   const void* const* weights_bf16; /* same indexing, tcgen05-packed bf16 matrices (may be NULL) */
   const void* const* weights_bf16_lo; /* packed residuals for GATOR_PREC_BF16X3 (may be NULL) */
   const float* pose2d;         /* (B,J,2)                                               */
-  const float* pose3d;         /* (B,J,3) millimetres (divided by 1000 inside)          */
+  const float* pose3d;         /* (B,J,3) millimetres, or metres with pose3d_metres = 1  */
   const float* feat;           /* (B,J,128)                                             */
   float* mesh;                 /* (B,6890,3) metres                                     */
   float* coarse;               /* optional (B,431,3) coarse vertices, may be NULL        */
@@ -200,6 +203,12 @@ int gator_mdr_forward(const gator_mdr_args* a, void* stream);
 /* The dominant kernel on its own, for roofline measurement: 2-head 431x431 self-attention core
  * (vanilla_transformer_encoder.py:36-46) over qkv (B*431, 192) -> out (B*431, 64). */
 int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_t precision, void* stream);
+/* Round-2 core of the same op: fp16 operands (fp32 accumulate), persistent warp-specialised tcgen05 kernel fed by TMA
+ * bulk copies (csrc/mdr_attn2_umma.cu).  `image` is caller workspace of gator_mdr_self_attention_image_bytes(batch)
+ * bytes: qkv is first re-packed into per-(sample, head) [Q | K | V] fp16 operand images (inside gator_mdr_forward the
+ * layer-chain kernel writes these images itself). */
+size_t gator_mdr_self_attention_image_bytes(int32_t batch);
+int gator_mdr_self_attention_f16(const float* qkv, void* image, float* out, int32_t batch, void* stream);
 /* The fused row-wise chain of MDR layer `layer` (0..2) on its own (csrc/mdr_chain_umma.cu; tensor-core precisions
  * only): everything of MDR.py:140-153 between two self-attention cores.  `weights` is the gator_mdr_args table;
  * x_in (B*431,64) = embedded vertices (layer 0) or the previous layer's x3; att_in (B*431,64) = previous
