@@ -192,7 +192,7 @@ def gat_block(sd, p, c, x, bias, num_heads=8):
     h1 = torch.matmul(n, W[1])
     adj = c['graph_adj'].to(x.dtype) + sd[p + 'gcn.adj2']
     adj = (adj.T + adj) / 2
-    E = torch.eye(adj.size(0), dtype=x.dtype)
+    E = torch.eye(adj.size(0), dtype=x.dtype, device=x.device)
     g = torch.matmul(adj * E, M * h0) + torch.matmul(adj * (1 - E), M * h1) + sd[p + 'gcn.bias'].view(1, 1, -1)
     s = a + g
     # X_Feat
@@ -223,7 +223,7 @@ def gat_forward(sd, c, pose2d, prefix='pose_lifter.', depth=6, trace=None):
     x = F.gelu(x)
     x = torch.matmul(sd[p + 'GLinear.3.W'][None, :], x) + sd[p + 'GLinear.3.b'][None, :, None]
     x = x.permute(0, 2, 1)
-    x = x + F.embedding(torch.arange(1, J + 1), sd[p + 'pos_id_embed.weight'])
+    x = x + F.embedding(torch.arange(1, J + 1, device=x.device), sd[p + 'pos_id_embed.weight'])
     pos_num = sd[p + 'graph_adj'].long().sum(dim=1).view(-1)
     x = x + F.embedding(pos_num, sd[p + 'pos_num_embed.weight'])
     if trace is not None:
@@ -286,12 +286,12 @@ def mdr_forward(sd, c, x, alpha: bool, prefix='pose2mesh.', trace=None):
     B, J = x.shape[0], x.shape[1]
     iv = sd[p + 'init_vertices']
     V = iv.shape[0]
-    vj = torch.from_numpy(np.asarray(c['vj_relation'])).long()
+    vj = torch.from_numpy(np.asarray(c['vj_relation'])).long().to(x.device)
     verts = torch.cat([iv.unsqueeze(0).expand(B, -1, -1), x[:, vj, 2:5]], dim=2)
     joint = F.linear(x, sd[p + 'get_joint_feature.weight'], sd[p + 'get_joint_feature.bias'])
     verts = F.linear(verts, sd[p + 'get_verts_feature.weight'], sd[p + 'get_verts_feature.bias'])
-    joint = joint + F.embedding(torch.arange(1, J + 1), sd[p + 'pos_j_id_embed.weight'])
-    verts = verts + F.embedding(torch.arange(1, V + 1), sd[p + 'pos_v_id_embed.weight'])
+    joint = joint + F.embedding(torch.arange(1, J + 1, device=x.device), sd[p + 'pos_j_id_embed.weight'])
+    verts = verts + F.embedding(torch.arange(1, V + 1, device=x.device), sd[p + 'pos_v_id_embed.weight'])
     if trace is not None:
         trace['mdr_verts_embed'] = verts
         trace['mdr_joint_embed'] = joint

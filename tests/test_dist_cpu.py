@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from gator_b200.dist import gather_meshes, shard_range
+from gator_b200.dist import forward_gathered, gather_meshes, rank_span, round_plan, shard_range
 
 
 def test_shard_range_partitions():
@@ -29,6 +29,54 @@ def _worker(rank, world, port, total, q):
     got = gather_meshes(full[lo:hi].clone(), total)
     q.put((rank, bool(torch.equal(got, full))))
     dist.destroy_process_group()
+
+
+def test_round_plan_covers_batch_once():
+    for total in (0, 1, 7, 4096, 65536, 65537):
+        for world in (1, 2, 3, 8):
+            for block in (1, 5, 1024):
+                seen = 0
+                for start, n in round_plan(total, world, block):
+                    assert start == seen and n > 0
+                    spans = [rank_span(total, start, n, r) for r in range(world)]
+                    assert all(0 <= hi - lo <= n for lo, hi in spans)
+                    assert spans[0][0] == start and all(a[1] == b[0] for a, b in zip(spans, spans[1:]) if b[1] > b[0])
+                    seen = max(hi for _, hi in spans)
+                assert seen == total
+
+
+def _worker_rounds(rank, world, port, total, block, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    full = torch.arange(total * 5 * 3, dtype=torch.float32).reshape(total, 5, 3)
+    calls = []
+
+    def fn(lo, hi):
+        calls.append((lo, hi))
+        return full[lo:hi].clone()
+    got = forward_gathered(fn, total, (5, 3), block)
+    mine = sum(hi - lo for lo, hi in calls)
+    q.put((rank, bool(torch.equal(got, full)), mine))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('total,block', [(16, 2), (13, 3), (5, 4)])
+def test_forward_gathered_world2_gloo(total, block):
+    """Block-cyclic deal + chunked all_gather_into_tensor: every rank ends with the full batch, each sample computed once."""
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_rounds, args=(r, 2, port, total, block, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert sorted(r[:2] for r in res) == [(0, True), (1, True)]
+    assert sum(r[2] for r in res) == total
 
 
 @pytest.mark.parametrize('total', [8, 7])

@@ -179,6 +179,29 @@ def test_self_attention_kernels_agree(scale):
         assert (o.cpu().double() - ref).abs().max().item() <= tol * max(1.0, scale) ** (2 if prec else 1), prec
 
 
+@pytest.mark.parametrize('scale,tail', [(0.3, 1.0), (1.5, 1.0), (4.0, 1.0), (1.0, 6.0)])
+def test_self_attention_f16_core(scale, tail):
+    """Round-2 self-attention core (fp16 operands, P in tensor memory, lazily rescaled online softmax) against fp64.
+    `tail` scales the keys of the last 131 vertices so that later key blocks exceed the running maximum by far more than
+    2^8: the rescale of O in tensor memory is exercised.  Batch 301 > 148 SMs: the persistent loop and both ring stages."""
+    from gator_b200 import _lib
+    L = _lib.lib()
+    for nb in (1, 3, 301):
+        g = torch.Generator().manual_seed(nb)
+        qkv = torch.randn(nb * 431, 192, generator=g) * scale
+        if tail != 1.0:
+            qkv.view(nb, 431, 192)[:, 300:, 64:128] *= tail
+        qkv = qkv.to(DEV)
+        q, k, v = [t.view(nb, 431, 2, 32).transpose(1, 2).double() for t in qkv.cpu().split(64, dim=1)]
+        ref = (torch.softmax(q @ k.transpose(-1, -2) / 32 ** 0.5, -1) @ v).transpose(1, 2).reshape(nb * 431, 64)
+        img = torch.empty(L.gator_mdr_self_attention_image_bytes(nb), dtype=torch.uint8, device=DEV)
+        o = torch.full((nb * 431, 64), float('nan'), device=DEV)
+        _lib.check(L.gator_mdr_self_attention_f16(qkv.data_ptr(), img.data_ptr(), o.data_ptr(), nb, _lib.stream_ptr()), 'self_attention_f16')
+        err = (o.cpu().double() - ref).abs().max().item()
+        # fp16 operands: relative 2^-11 on q, k (logit error ~ |s| 2^-11, |s| up to ~6 scale^2 tail) and on P, v
+        assert err <= 2e-3 * max(1.0, scale) ** 2 * max(1.0, scale * tail), (nb, scale, tail, err)
+
+
 def test_edge_batches_and_chunking(models):
     """Empty batch, batch 1, ragged chunking: per-sample results do not depend on how the batch is cut."""
     m = models['h36m']
@@ -209,6 +232,45 @@ def test_full_size_batch_is_sample_independent(models):
     for i in (0, 147, 148, 2047, 4095):
         mi, pi = m(x[i:i + 1])
         assert torch.equal(mi[0], mesh[i]) and torch.equal(pi[0], p3[i])
+
+
+def test_full_size_tensor_path_vs_oracle(models):
+    """B = 4096 on the tensor-core path: 64 samples drawn from all over the batch (every chain tile phase, both ends of
+    the persistent kernels' work lists) against the CPU oracle, within the fp32 tolerance."""
+    m = models['coco'].set_precision('bf16x3')
+    try:
+        sd, gc, mc, alpha = oracle_setup('coco')
+        base = golden('fixtures')['demo_pose19']
+        xh = torch.from_numpy(synthetic.coco_poses2d(base, 4096, seed=9))
+        mesh, p3 = m(xh.to(DEV))
+        idx = torch.from_numpy(np.random.default_rng(0).choice(4096, 64, replace=False)).sort().values
+        idx[0], idx[-1] = 0, 4095
+        with torch.no_grad():
+            ref_mesh, ref_p3 = orc.gator_forward(sd, gc, mc, xh[idx], alpha)
+        err = (mesh[idx.to(DEV)].cpu() - ref_mesh).abs().max().item()
+        print(f'B=4096 bf16x3, 64 samples vs oracle: max-abs {err:.3e} m')
+        assert err <= TOL_M and (p3[idx.to(DEV)].cpu() - ref_p3).abs().max().item() <= 0.1
+    finally:
+        m.set_precision('fp32')
+
+
+@pytest.mark.parametrize('tag', ['h36m', 'coco'])
+def test_mdr_forward_standalone(models, tag):
+    """models.MDR.forward(pose_combine) (MDR.py:124-170) on its own, pose3d columns in metres as the reference feeds them."""
+    sd, gc, mc, alpha = oracle_setup(tag)
+    J = gc['J']
+    g = torch.Generator().manual_seed(5)
+    x = torch.cat([torch.randn(6, J, 2, generator=g), torch.randn(6, J, 3, generator=g) * 0.3, torch.randn(6, J, 128, generator=g)], 2)
+    with torch.no_grad():
+        ref = orc.mdr_forward(sd, mc, x, alpha)
+    m = models[tag]
+    for prec in ('fp32', 'bf16x3'):
+        m.set_precision(prec)
+        try:
+            out = m.pose2mesh(x.to(DEV))
+        finally:
+            m.set_precision('fp32')
+        assert (out.cpu() - ref).abs().max().item() <= TOL_M, prec
 
 
 def test_state_dict_reload_repacks(models):
@@ -261,6 +323,19 @@ def test_smpl_tensor_core_path():
     layer = build_b200_smpl(device=DEV).set_precision('bf16x3')
     v, j = layer(pose, betas, trans)
     assert np.abs(v.cpu().numpy() - s['full/verts']).max() <= 2e-5 and np.abs(j.cpu().numpy() - s['full/jtr']).max() <= 1e-5
+
+
+@pytest.mark.parametrize('B', [41, 8193])
+def test_smpl_tensor_core_path_vs_oracle(B):
+    """bf16x3 SMPL against the oracle beyond one 20-sample skinning tile (B = 41) and across the 8192-sample workspace
+    chunk (B = 8193; the oracle is evaluated on a slice around the boundary and both ends)."""
+    buf = {k: torch.from_numpy(v) for k, v in synthetic.smpl_buffers().items()}
+    pose, betas, trans = [torch.from_numpy(a) for a in synthetic.smpl_inputs(B)]
+    layer = build_b200_smpl(device=DEV).set_precision('bf16x3')
+    v, j = layer(pose.to(DEV), betas.to(DEV), trans.to(DEV))
+    idx = torch.arange(B) if B <= 64 else torch.cat([torch.arange(0, 24), torch.arange(8180, 8193)])
+    rv, rj, _ = orc.smpl_forward(buf, synthetic.SMPL_PARENTS, pose[idx], betas[idx], trans[idx])
+    assert (v[idx.to(DEV)].cpu() - rv).abs().max() <= 2e-5 and (j[idx.to(DEV)].cpu() - rj).abs().max() <= 2e-5
 
 
 def test_smpl_full_size_properties():
