@@ -144,17 +144,21 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
 // GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. at the
-// fp32 rounding level of erff itself) - ~15 instructions instead of ~30 for erff's two-branch polynomial.
+// fp32 rounding level of erff itself) - 15 instructions: the reciprocal and the exponential are the raw MUFU
+// approximations (rcp.approx / ex2.approx, ~1 ulp; __frcp_rn and exp2f wrap the same MUFU ops in range checks, a
+// Newton step and a slow-path branch, which made this 35 instructions - measured in the MDR chain, profiles/r02_*).
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = exp2f(-z * z * 1.4426950408889634f);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * (x * -0.72134752044448170368f)));   // exp(-z^2) = 2^(-x^2 log2(e) / 2)
   const float erf_abs = fmaf(-poly * t, e, 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float hx = 0.5f * x;
+  return fmaf(hx, copysignf(erf_abs, x), hx);
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

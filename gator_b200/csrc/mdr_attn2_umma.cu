@@ -7,11 +7,13 @@
 // `qkv_image_kernel` below.  Q and K are K-major operands; the same image of V is the MN-major B operand of P V, so no
 // transpose of V exists anywhere.
 //
-// Persistent, warp-specialised, one CTA per SM, 18 warps:
-//   warp 17      TMA producer: one bulk copy per image into a 2-stage ring (the next (sample, head) loads while this one runs)
-//   warp 16      MMA issuer (one lane)
-//   warps 0..15  four softmax warpgroups; warpgroup t owns query tile t (rows 128t..128t+127), thread = query row, and
-//                tensor-memory columns [128t, 128t+128): S block (96 keys, fp32) in [0,96), O accumulator in [96,128).
+// Persistent, warp-specialised, one CTA per SM, 16 warps (512 threads x 128 registers = the whole register file; a 17th
+// warp would be allocated as four - the hardware hands out warps in groups of four):
+//   warps 0..13  softmax warps in four warpgroups; warpgroup t owns query tile t (rows 128t..128t+127), thread = query
+//                row, and tensor-memory columns [128t, 128t+128): S block (96 keys, fp32) in [0,96), O accumulator in
+//                [96,128).  Tile 3 holds rows 384..430 only, so its warps 14 and 15 have no row at all; they are
+//   warp 14      the MMA issuer (one lane), and
+//   warp 15      the TMA producer: one bulk copy per image into a 2-stage ring (the next (sample, head) loads while this one runs).
 // Per key block j (96, 96, 96, 96, 48 keys) and tile t:   S = Q_t K_j^T  ->  warpgroup t: block max, P = exp2(S c - m) as
 // fp16 written IN PLACE over S with tcgen05.st (P is the tensor-memory A operand of the next MMA - it never touches shared
 // memory)  ->  O_t += P V_j, S_t = Q_t K_{j+1}^T.   The four tiles are at different points of this loop, so the MMA
@@ -40,8 +42,8 @@ constexpr int ITEM = 3 * IMG;             // 82 944 B per (sample, head)
 constexpr int STAGES = 2;
 constexpr int KB = 96;                    // keys per block
 constexpr int NBLK = 5;                   // 4 x 96 + 48
-constexpr int NSOFT = 16;                 // softmax warps
-constexpr int NT = (NSOFT + 2) * 32;      // 576 threads
+constexpr int NT = 512;                   // 16 warps
+constexpr int W_MMA = 14, W_TMA = 15;     // the two row-less warps of query tile 3
 constexpr int SMEM = STAGES * ITEM;       // 165 888 B dynamic
 constexpr float kScaleLog2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32)
 constexpr float kLazy = 8.0f;             // the running maximum moves only when exceeded by 2^8
@@ -155,7 +157,7 @@ __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t o_addr, 
   tmem_st_wait();
 }
 
-__global__ void __maxnreg__(112) mdr_self_attn2_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, int items) {
+__global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, int items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
@@ -178,7 +180,7 @@ __global__ void __maxnreg__(112) mdr_self_attn2_kernel(const uint8_t* __restrict
   const uint32_t tmem = tmem_slot;
   const int n_my = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA: blockIdx.x + i * gridDim.x
 
-  if (warp == NSOFT + 1) {
+  if (warp == W_TMA) {
     // ===== TMA producer =====
     if (lane == 0) {
       for (int i = 0; i < n_my; ++i) {
@@ -191,7 +193,7 @@ __global__ void __maxnreg__(112) mdr_self_attn2_kernel(const uint8_t* __restrict
         for (int c = 0; c < 3; ++c) bulk_copy_g2s(dst + c * IMG, src + c * IMG, IMG, &bars.kv_full[s]);
       }
     }
-  } else if (warp == NSOFT) {
+  } else if (warp == W_MMA) {
     // ===== MMA issuer =====
     constexpr uint32_t id_s96 = idesc_f16(128, KB), id_s48 = idesc_f16(128, 48), id_pv = idesc_f16(128, DK, 1);
     auto issue_qk = [&](uint32_t stage_base, int t, int j) {   // S_t = Q_t K_j^T (2 k-steps of 16)
@@ -253,8 +255,7 @@ __global__ void __maxnreg__(112) mdr_self_attn2_kernel(const uint8_t* __restrict
     const int row = (warp & 3) * 32 + lane;         // row in tile = tensor-memory lane
     const int q = t * 128 + row;
     const bool valid = q < V;
-    const bool warp_active = t * 128 + (warp & 3) * 32 < V;
-    if (warp_active) {
+    {
       const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
       const uint32_t s_addr = tmem + lane_addr + t * 128, o_addr = s_addr + KB;
       uint32_t ph_s = 0, ph_o = 0;

@@ -16,9 +16,11 @@
 //    (linears[3], proj, fc2 accumulate straight into it; their biases are added when x is next read);
 //  * GELU(fc1) is converted IN PLACE (32 fp32 columns -> 16 hi + 16 lo columns) and read back as the A operand of fc2;
 //  * 7 MMA round trips per tile instead of 18 (fc1 / fc2 in halves of 128 columns, q|k|v as one group);
-//  * warp-specialised: a TMA producer warp streams the 14 weight units (16 KB each) through a 5-slot ring with
-//    cp.async.bulk + mbarriers, an MMA warp issues, 8 compute warps own the rows (two threads per row); no block-wide
-//    barrier in the tile loop; persistent CTAs, two per SM (256 tensor-memory columns each);
+//  * the 14 weight units (16 KB each) stream through a 6-slot ring with cp.async.bulk + mbarriers, issued a whole compute
+//    phase ahead; 8 warps own the rows (two threads per row) and lane 0 of warp 0 doubles as MMA issuer and TMA producer
+//    (256 threads x 128 registers x 2 CTAs = the whole register file; a 9th warp would be allocated as four); the only
+//    block-wide synchronisation in the tile loop is the mbarrier pair around each MMA group; persistent CTAs, two per SM
+//    (256 tensor-memory columns each);
 //  * q|k|v leave as the fp16 operand images the self-attention kernel (csrc/mdr_attn2_umma.cu) loads with bulk copies.
 #include <cuda_fp16.h>
 
@@ -37,9 +39,9 @@ constexpr int DK = 32;
 constexpr int MAXJ = 32;
 constexpr int UNIT_IMG = 64 * 64 * 2;          // 8 KB: one 64x64 bf16 image
 constexpr int UNIT_BYTES = 2 * UNIT_IMG;       // hi | lo
-constexpr int SLOTS = 5;
-constexpr int NCOMP = 8;                       // compute warps
-constexpr int NT = (NCOMP + 2) * 32;           // + MMA warp + TMA warp
+constexpr int SLOTS = 6;
+constexpr int NCOMP = 8;                       // warps: all of them own rows
+constexpr int NT = NCOMP * 32;
 constexpr int QKV_IMG = VP * DK * 2;           // one fp16 operand image of the self-attention kernel
 // tensor-memory columns (256 per CTA)
 constexpr int C_X = 0;        // residual stream / accumulator of the residual GEMMs (fp32, 64 columns)
@@ -69,9 +71,11 @@ struct Chain2Params {
 };
 
 struct Bars {
-  uint64_t w_full[SLOTS], w_empty[SLOTS];
-  uint64_t a_ready, d_ready;
+  uint64_t w_full[SLOTS];        // weight unit landed (TMA transaction bytes)
+  uint64_t a_ready, d_ready;     // A operands written by all 8 warps / MMA group complete (which also frees its ring slots)
 };
+// MMA groups of a tile, in order
+enum Step { S_SO, S_Q, S_PROJ, S_FC1A, S_MID, S_FC2B, S_QKV, S_HEAD };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
 
   if (warp == 0) tmem_alloc(&tmem_slot, 256);
   if (tid == 32) {
-    for (int s = 0; s < SLOTS; ++s) { mbar_init(&bars.w_full[s], 1); mbar_init(&bars.w_empty[s], 1); }
+    for (int s = 0; s < SLOTS; ++s) mbar_init(&bars.w_full[s], 1);
     mbar_init(&bars.a_ready, NCOMP);
     mbar_init(&bars.d_ready, 1);
     mbar_init_fence();
@@ -118,62 +122,59 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
   const int first_unit = final_pass ? 0 : (has_so ? 0 : 1);
   const int units_per_tile = final_pass ? 2 : 14 - first_unit;
 
-  if (warp == NCOMP + 1) {
-    // ===== TMA producer: weight units through the ring =====
-    if (lane == 0) {
-      int u = 0;
-      for (int it = 0; it < n_my; ++it) {
-        for (int k = 0; k < units_per_tile; ++k, ++u) {
-          const int s = u % SLOTS;
-          if (u >= SLOTS) mbar_wait(&bars.w_empty[s], ((u / SLOTS) - 1) & 1);
-          const int unit = final_pass ? k : kUnitOrder[first_unit + k];
-          mbar_arrive_expect_tx(&bars.w_full[s], UNIT_BYTES);
-          bulk_copy_g2s(smem + s * UNIT_BYTES, p.blob + (size_t)unit * UNIT_BYTES, UNIT_BYTES, &bars.w_full[s]);
-        }
-      }
+  // ---- leader (warp 0, lane 0): TMA producer + MMA issuer ----
+  const int total_units = n_my * units_per_tile;
+  int u_use = 0, u_load = 0;                         // weight units consumed by issued MMAs / requested from L2
+  uint32_t ph_a = 0;
+  auto refill = [&]() {                              // every unit below u_use has been read (d_ready): its slot is free
+    while (u_load < total_units && u_load - u_use < SLOTS) {
+      const int s = u_load % SLOTS, k = u_load % units_per_tile;
+      const int unit = final_pass ? k : kUnitOrder[first_unit + k];
+      mbar_arrive_expect_tx(&bars.w_full[s], UNIT_BYTES);
+      bulk_copy_g2s(smem + s * UNIT_BYTES, p.blob + (size_t)unit * UNIT_BYTES, UNIT_BYTES, &bars.w_full[s]);
+      ++u_load;
     }
-  } else if (warp == NCOMP) {
-    // ===== MMA issuer =====
+  };
+  // one 64x64 unit: D[dcol .. dcol+64) (+)= A . W^T with the 3-term split; A hi k-step ks at a_hi + (ks>>1)*a_grp2 + (ks&1)*8
+  // (8 columns each), lo a_lo_off columns further
+  auto unit_mma = [&](uint32_t dcol, bool accumulate, uint32_t a_hi, uint32_t a_lo_off, uint32_t a_grp2) {
     constexpr uint32_t idesc = idesc_bf16(128, 64);
-    int u = 0;
-    uint32_t ph_a = 0;
-    // one 64x64 unit: D[dcol .. dcol+64) (+)= A . W^T with the 3-term split; A hi k-step s at a_hi + a_step * s (8 columns each),
-    // lo at a_hi + a_lo_off + ...; k-steps 2, 3 may sit in a second 32-column group (a_grp2 = offset of k-step 2 from k-step 0)
-    auto unit_mma = [&](uint32_t dcol, bool accumulate, uint32_t a_hi, uint32_t a_lo_off, uint32_t a_grp2) {
-      const int s = u % SLOTS;
-      mbar_wait(&bars.w_full[s], (u / SLOTS) & 1);
-      if (lane == 0) {
-        const uint32_t w0 = smem_u32(smem + s * UNIT_BYTES);
+    const int s = u_use % SLOTS;
+    mbar_wait(&bars.w_full[s], (u_use / SLOTS) & 1);
+    const uint32_t w0 = smem_u32(smem + s * UNIT_BYTES);
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          const uint32_t ah = tmem + a_hi + (ks >> 1) * a_grp2 + (ks & 1) * 8, al = ah + a_lo_off;
-          const uint64_t wh = smem_desc(w0 + ks * 256, 128, 1024), wl = smem_desc(w0 + UNIT_IMG + ks * 256, 128, 1024);
-          mma_ts(tmem + dcol, al, wh, idesc, (accumulate || ks > 0) ? 1u : 0u);
-          mma_ts(tmem + dcol, ah, wl, idesc, 1);
-          mma_ts(tmem + dcol, ah, wh, idesc, 1);
-        }
-        mma_commit(&bars.w_empty[s]);     // slot free once these MMAs have read it
-      }
-      __syncwarp();
-      ++u;
-    };
-    auto wait_a = [&]() { mbar_wait(&bars.a_ready, ph_a); ph_a ^= 1; tc_fence_after(); };
-    auto done = [&]() { if (lane == 0) mma_commit(&bars.d_ready); __syncwarp(); };
-    // A operand region C_A: hi k-step s at C_A + 8 s, lo 32 columns further
-    auto from_a = [&](uint32_t dcol, bool acc) { unit_mma(dcol, acc, C_A, 32, 16); };
-    // GELU'd fc1 half in C_W: 32-column groups [hi 16 | lo 16]; fc2 quarter qh (0/1 within the half) = groups 2qh, 2qh+1
-    auto from_w = [&](int qh) { unit_mma(C_X, true, C_W + qh * 64, 16, 32); };
-    for (int it = 0; it < n_my; ++it) {
-      if (has_so) { wait_a(); from_a(C_X, true); done(); }             // x += att Wo^T
-      if (final_pass) { wait_a(); from_a(C_W, false); done(); continue; }   // head projection
-      wait_a(); from_a(C_W, false); done();                             // q = LN1(x) Wq^T
-      wait_a(); from_a(C_X, true); done();                              // x += a Wproj^T
-      wait_a(); from_a(C_W, false); from_a(C_W + 64, false); done();    // fc1 quarters 0, 1
-      wait_a(); from_w(0); from_w(1); from_a(C_W, false); from_a(C_W + 64, false); done();   // x += fc2 halves 0; fc1 quarters 2, 3
-      wait_a(); from_w(0); from_w(1); done();                           // x += fc2 half 1
-      wait_a(); from_a(C_X, false); from_a(C_W, false); from_a(C_W + 64, false); done();     // q | k | v into columns [0, 192)
+    for (int ks = 0; ks < 4; ++ks) {
+      const uint32_t ah = tmem + a_hi + (ks >> 1) * a_grp2 + (ks & 1) * 8, al = ah + a_lo_off;
+      const uint64_t wh = smem_desc(w0 + ks * 256, 128, 1024), wl = smem_desc(w0 + UNIT_IMG + ks * 256, 128, 1024);
+      mma_ts(tmem + dcol, al, wh, idesc, (accumulate || ks > 0) ? 1u : 0u);
+      mma_ts(tmem + dcol, ah, wl, idesc, 1);
+      mma_ts(tmem + dcol, ah, wh, idesc, 1);
     }
-  } else {
+    ++u_use;
+  };
+  // A operand region C_A: hi k-step s at C_A + 8 s, lo 32 columns further
+  auto from_a = [&](uint32_t dcol, bool acc) { unit_mma(dcol, acc, C_A, 32, 16); };
+  // GELU'd fc1 half in C_W: 32-column groups [hi 16 | lo 16]; fc2 quarter qh (0/1 within the half) = groups 2qh, 2qh+1
+  auto from_w = [&](int qh) { unit_mma(C_X, true, C_W + qh * 64, 16, 32); };
+  auto issue = [&](int step) {                       // leader only
+    mbar_wait(&bars.a_ready, ph_a);
+    ph_a ^= 1;
+    tc_fence_after();
+    switch (step) {
+      case S_SO: from_a(C_X, true); break;                                                    // x += att Wo^T
+      case S_Q: from_a(C_W, false); break;                                                    // q = LN1(x) Wq^T
+      case S_PROJ: from_a(C_X, true); break;                                                  // x += a Wproj^T
+      case S_FC1A: from_a(C_W, false); from_a(C_W + 64, false); break;                        // fc1 quarters 0, 1
+      case S_MID: from_w(0); from_w(1); from_a(C_W, false); from_a(C_W + 64, false); break;   // x += fc2 half 0; fc1 quarters 2, 3
+      case S_FC2B: from_w(0); from_w(1); break;                                               // x += fc2 half 1
+      case S_QKV: from_a(C_X, false); from_a(C_W, false); from_a(C_W + 64, false); break;     // q | k | v into columns [0, 192)
+      default: from_a(C_W, false); break;                                                     // S_HEAD
+    }
+    mma_commit(&bars.d_ready);
+  };
+  const bool leader = tid == 0;
+  if (leader) refill();
+  {
     // ===== compute warps: two threads per row (one 32-column half each) =====
     const int ch = warp >> 2;                        // column half = head
     const int row = (warp & 3) * 32 + lane;          // row in tile = tensor-memory lane
@@ -184,13 +185,21 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
     const int pair_id = 2 + (warp & 3);
     uint32_t ph_d = 0;
     int ln_count = 0;
-    auto submit = [&]() {
+    auto submit = [&](int step) {                    // my part of the A operands is written: hand the MMA group over
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars.a_ready);
+      if (leader) issue(step);
+      __syncwarp();
     };
-    auto await = [&]() { mbar_wait(&bars.d_ready, ph_d); ph_d ^= 1; tc_fence_after(); };
+    auto await = [&]() {
+      mbar_wait(&bars.d_ready, ph_d);
+      ph_d ^= 1;
+      tc_fence_after();
+      if (leader) refill();
+      __syncwarp();
+    };
     auto ld32f = [&](uint32_t taddr, float* v) {
       uint32_t r[32];
       tmem_ld32_async(taddr, r);
@@ -266,7 +275,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
           v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
         }
         write_a(v);
-        submit();
+        submit(S_SO);
         await();
         // the bias of a residual GEMM is added when x is next read, and the sum written back before the next accumulation
         ld32f(t_x, x);
@@ -280,7 +289,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
       if (final_pass) {
         // x = x3 + linears[3](att) + b is complete: MDR head projection [motion_linear | bias_linear | scale_linear] (MDR.py:156-162)
         write_a(x);
-        submit();
+        submit(S_HEAD);
         await();
         if (ch == 0) {
           ld32f(tmem + lane_addr + C_W, v);
@@ -307,7 +316,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
           v[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * w.z + bb.z; v[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * w.w + bb.w;
         }
         write_a(v);
-        submit();
+        submit(S_Q);
       }
       cp_async_wait_all();
       named_sync(1, NCOMP * 32);                     // K|V staged (every thread's copies landed)
@@ -317,7 +326,11 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
         float q[DK];
         ld32f(tmem + lane_addr + C_W + c0, q);
         constexpr int JU = JT ? JT : MAXJ;
-        auto cross = [&](const float* kvb, auto ld4) {
+        // rows of the tile's first sample read K|V from shared memory, the others (a tile spans at most two samples) from
+        // global memory through L1 - one code path through a generic pointer (two copies of this unrolled block were
+        // 40 % of the kernel's 170 KB of code, which thrashed the instruction cache)
+        const float* kvb = (b == b_first) ? skv : p.kv + (size_t)b * J * 128;
+        {
           float s[JU];
           float mx = -INFINITY;
 #pragma unroll
@@ -327,7 +340,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
               float a0_ = 0.f, a1_ = 0.f, a2_ = 0.f, a3_ = 0.f;
 #pragma unroll
               for (int d4 = 0; d4 < DK / 4; ++d4) {
-                const float4 kk = ld4(kr + d4);
+                const float4 kk = kr[d4];
                 a0_ = fmaf(q[4 * d4], kk.x, a0_); a1_ = fmaf(q[4 * d4 + 1], kk.y, a1_);
                 a2_ = fmaf(q[4 * d4 + 2], kk.z, a2_); a3_ = fmaf(q[4 * d4 + 3], kk.w, a3_);
               }
@@ -349,17 +362,15 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
               const float4* vr = reinterpret_cast<const float4*>(kvb + j * 128 + E + c0);
 #pragma unroll
               for (int d4 = 0; d4 < DK / 4; ++d4) {
-                const float4 vv = ld4(vr + d4);
+                const float4 vv = vr[d4];
                 v[4 * d4] = fmaf(pj, vv.x, v[4 * d4]); v[4 * d4 + 1] = fmaf(pj, vv.y, v[4 * d4 + 1]);
                 v[4 * d4 + 2] = fmaf(pj, vv.z, v[4 * d4 + 2]); v[4 * d4 + 3] = fmaf(pj, vv.w, v[4 * d4 + 3]);
               }
             }
           }
-        };
-        if (b == b_first) cross(skv, [](const float4* q_) { return *q_; });
-        else cross(p.kv + (size_t)b * J * 128, [](const float4* q_) { return __ldg(q_); });
+        }
         write_a(v);
-        submit();
+        submit(S_PROJ);
       }
       await();
       // ---- LayerNorm2 -> MLP ----
@@ -381,7 +392,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
           v[4 * i + 2] = (x[4 * i + 2] - mean) * rstd * w.z + bb.z; v[4 * i + 3] = (x[4 * i + 3] - mean) * rstd * w.w + bb.w;
         }
         write_a(v);
-        submit();
+        submit(S_FC1A);
       }
 #pragma unroll 1
       for (int half = 0; half < 2; ++half) {
@@ -402,7 +413,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
           tmem_st16(taddr, hi);                       // in place: [hi 16 columns | lo 16 columns]
           tmem_st16(taddr + 16, lo);
         }
-        submit();
+        submit(half == 0 ? S_MID : S_FC2B);
       }
       await();                                        // fc2 half 1 accumulated: x is complete up to the pending biases
       // ---- unbiased-std LayerNorm -> x3 -> q | k | v ----
@@ -423,7 +434,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
           x[4 * i + 2] = w.z * (x[4 * i + 2] - mean) * rden + bb.z; x[4 * i + 3] = w.w * (x[4 * i + 3] - mean) * rden + bb.w;
         }
         write_a(x);
-        submit();
+        submit(S_QKV);
         if (valid) {
           float4* dst = reinterpret_cast<float4*>(p.x3_out + grow * E + c0);
 #pragma unroll

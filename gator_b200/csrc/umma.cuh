@@ -24,16 +24,18 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_init_fence() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+// try_wait with a suspend-time hint: the warp sleeps in hardware until the phase completes (or the hint expires) instead of
+// re-issuing the probe every few hundred cycles - spinning warps were 19 % of all issued instructions in the MDR chain
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
