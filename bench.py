@@ -1,14 +1,23 @@
 #!/usr/bin/env python
-"""Headline benchmark: meshes/sec of the GATOR pose->mesh forward (BASELINE.json configs[3]: full
-GAT+MDR+upsample forward, synthetic COCO poses, J=19, alpha=True, batch 4096 per GPU).
+"""Headline benchmark: meshes/sec of the GATOR pose->mesh forward (J=19, alpha=True, synthetic COCO poses).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--precision fp32|bf16]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--batch B] [--precision fp32|bf16|bf16x3]
 
-One JSON line on stdout (rank 0).  `value` = whole-job meshes/s with inputs resident in HBM;
-`e2e` = the same through the nn.Module API with pinned-host inputs and the mesh copied back to the host
-inside the timed region; `roofline` = the dominant kernel (MDR 431x431 self-attention) timed on its own
-with CUDA events; `cpu_baseline` = the CPU oracle (port of the reference forward, same torch ops) timed
-on the box's host cores on a bounded sample.  --impl reference times that CPU path as the reference arm.
+N = 1: BASELINE configs[3] - batch 4096 on one B200.  N > 1 (torchrun, one rank per GPU): BASELINE configs[4] - a
+batch of 65 536 sharded over the N GPUs (65 536 / N samples per rank), reported without and with the NCCL output gather.
+
+One JSON line on stdout (rank 0):
+  value           whole-job meshes/s, inputs resident in HBM, CUDA events per step, L2 flushed before every step, max over ranks
+  with_gather     (N > 1) the same job ending with the FULL (65 536, 6890, 3) result on every rank: block-cyclic deal,
+                  chunked all_gather_into_tensor on a side stream overlapped with the next chunk's kernels
+  e2e             host -> host through the public API (gator_b200.pipeline.HostPipeline): pinned inputs, H2D, forward, full
+                  mesh + pose3d copied back to pinned host memory, all inside the timed region
+  e2e_eval        host -> device -> host with the evaluation epilogue (row f1) on the device: only per-sample errors return
+  roofline        the dominant kernel timed alone through its C-ABI entry (plus the other hot kernels)
+  other_workloads BASELINE configs[2]: SMPL_Layer alone at batch 16 384, fp32 and tensor-core path, HBM roofline
+  cpu_baseline    (N = 1) the CPU oracle (port of the reference forward, same ATen ops) on the box's host cores
+  gpu_eager_baseline (N = 1, informational) the same oracle ops run eagerly on this GPU (fp32, TF32 off, chunks of 256)
+--impl reference times the CPU oracle as the reference arm (the reference is plain PyTorch and is not installable offline).
 """
 from __future__ import annotations
 
@@ -30,6 +39,9 @@ UNIT = 'meshes/s'
 TAG = 'coco'                      # J=19, alpha=True (3dpw configuration of demo/run.py)
 FLOP_PER_MESH = 418.1e6           # GATOR.forward J=19, dense, 2*MAC
 SA_FLOP_PER_SAMPLE = 2 * 2 * 2 * 431 * 431 * 32   # self-attention core: 2 heads x (QK^T + PV) x 2*MAC
+MESH_BYTES = 6890 * 3 * 4
+GLOBAL_BATCH_MULTI = 65536        # BASELINE configs[4]
+GATHER_BLOCK = 1024               # samples per rank and gather round
 
 
 def measured_peaks():
@@ -40,6 +52,16 @@ def measured_peaks():
                 'bf16_tflops_sustained': float(p.get('bf16_tflops_sustained', p['bf16_tflops'])), 'src': 'measured'}
     except Exception:
         return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0, 'src': 'fallback'}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the hot kernels from the committed `ncu` capture (profiles/r02_traffic.json, written by
+    tools/launch_summary.py --json from the launch list of a 4096-sample forward); None when absent."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r02_traffic.json')) as f:
+            return json.load(f)
+    except Exception:
+        return {}
 
 
 class ClockSampler:
@@ -92,7 +114,6 @@ class ClockSampler:
 
 
 def make_inputs(batch, seed=2):
-    import numpy as np
     from builders import golden, synthetic
     base = golden('fixtures')['demo_pose19']
     return synthetic.coco_poses2d(base, batch, seed=seed)
@@ -120,6 +141,35 @@ def cpu_forward_rate(sample_batch, min_seconds, threads):
     return sample_batch / med, med, n
 
 
+def gpu_eager_rate(dev, batch=4096, chunk=256):
+    """Informational same-GPU baseline: the oracle's ATen op sequence - the reference forward - executed
+    eagerly on this GPU in fp32 (TF32 off), `batch` samples in chunks of `chunk` (the reference materialises the
+    (B,2,431,431) score tensors: 1.5 MB per sample and layer).  Checker code: only bench.py's baseline legs run it."""
+    import torch
+    from helpers import oracle_setup, orc
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    sd, gc, mc, alpha = oracle_setup(TAG)
+    mv = lambda d: {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in d.items()}
+    sd, gc, mc = mv(sd), mv(gc), mv(mc)
+    x = torch.from_numpy(make_inputs(batch)).to(dev)
+
+    def run():
+        for lo in range(0, batch, chunk):
+            orc.gator_forward(sd, gc, mc, x[lo:lo + chunk], alpha)
+    with torch.no_grad():
+        run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run()
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {'value': batch / (ms * 1e-3), 'unit': UNIT, 'ms_per_4096': ms * 4096 / batch, 'batch': batch, 'chunk': chunk,
+            'what': 'oracle port of the reference forward, PyTorch eager (cuBLAS / ATen, fp32, allow_tf32=False) on this GPU; informational'}
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -127,7 +177,7 @@ def run_reference(args):
     import torch
     threads = os.cpu_count() or 1
     sample = 64
-    # one "step" = one forward over a 64-sample slice of the 4096-sample workload (bounded sample)
+    # one "step" = one forward over a 64-sample slice of the workload (bounded sample)
     from helpers import oracle_setup, orc
     torch.set_num_threads(threads)
     sd, gc, mc, alpha = oracle_setup(TAG)
@@ -140,15 +190,30 @@ def run_reference(args):
             orc.gator_forward(sd, gc, mc, x, alpha)
         dt = (time.perf_counter() - t0) / args.steps
     v = sample / dt
+    world = args.gpus
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'strong' if world > 1 else 'weak',
             'vs_baseline': None, 'dtype': 'fp32', 'data': 'synthetic',
-            'config': {'workload': f'GATOR.forward J=19 alpha=True, batch {args.batch}/GPU (BASELINE configs[3])',
-                       'note': 'CPU reference forward (oracle port, same ATen ops); each step = a 64-sample slice'},
+            'config': {'workload': workload_name(world, per_gpu_batch(args, world)),
+                       'note': 'CPU reference forward (oracle port, same ATen ops) on rank 0; each step = a 64-sample slice of the workload'},
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                              'sample': f'{args.steps} forwards of batch {sample}'},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
     print(json.dumps(line), flush=True)
+
+
+def per_gpu_batch(args, world):
+    if args.batch:
+        return args.batch
+    return 4096 if world == 1 else GLOBAL_BATCH_MULTI // world
+
+
+def workload_name(world, B):
+    if world == 1:
+        return (f'GATOR.forward J=19 alpha=True, batch {B} on one GPU (BASELINE configs[3]); random-init weights, synthetic '
+                'SMPL-shaped template/bases')
+    return (f'GATOR.forward J=19 alpha=True, batch {B * world} sharded over {world} GPUs = {B} per GPU (BASELINE configs[4]); '
+            'random-init weights, synthetic SMPL-shaped template/bases')
 
 
 def run_b200(args):
@@ -162,15 +227,17 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     from gator_b200 import _lib
-    from gator_b200.dist import bind_to_gpu_numa_node, shard_range
+    from gator_b200.dist import bind_to_gpu_numa_node, forward_gathered, shard_range
     numa_node = bind_to_gpu_numa_node(local)              # before any pinned buffer is allocated
     from builders import build_b200_gator
     L = _lib.lib()
     model = build_b200_gator(TAG, dev).set_precision(args.precision)
     J = model.num_joint
-    B = args.batch                                         # per GPU (weak scaling)
-    lo, hi = shard_range(B * world, world, rank)
-    x_host = torch.from_numpy(make_inputs(B * world)[lo:hi]).pin_memory()
+    B = per_gpu_batch(args, world)                         # per GPU
+    total = B * world
+    lo, hi = shard_range(total, world, rank)
+    x_all = make_inputs(total)
+    x_host = torch.from_numpy(x_all[lo:hi]).pin_memory()
     x = x_host.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -179,24 +246,30 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(v):
+        t = torch.tensor([v], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
     # ---- device-resident throughput ----
     # nvidia-smi is started well before the timed region: its start-up (NVML initialisation) was seen to stall the GPU for
-    # tens of milliseconds when it coincided with the first timed steps (one run measured 41 ms per step instead of 20)
+    # tens of milliseconds when it coincided with the first timed steps
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     with torch.no_grad():
         t_ramp = time.perf_counter()                       # untimed: first call packs the weights, then ~0.8 s of
         while True:                                        # forwards so that the SM clock has ramped before the W
-            mesh_w = model(x)                              # warm-up steps the contract asks for
+            model(x)                                       # warm-up steps the contract asks for
             torch.cuda.synchronize()
             if time.perf_counter() - t_ramp > 0.8:
                 break
         mesh = p3 = None
         for _ in range(args.warmup):
             mesh, p3 = model(x)                            # same binding pattern as the timed loop: the previous step's
-        barrier()                                          # outputs are still alive while the next ones are allocated, so
-        L.gator_launch_count(1)                            # the caching allocator's second 340 MB block exists before timing
+        barrier()                                          # outputs are still alive while the next ones are allocated
+        L.gator_launch_count(1)
         sampler.mark(True)
         evs = []
         t_wall = time.perf_counter()
@@ -213,38 +286,107 @@ def run_b200(args):
         launches = L.gator_launch_count(1)
         clocks = sampler.stop() if rank == 0 else None
     per_step = [a.elapsed_time(b) for a, b in evs]
-    step_ms = sum(per_step) / args.steps
-    t = torch.tensor([step_ms], device=dev)
+    step_ms = max_over_ranks(sum(per_step) / args.steps)
+    value = total / (step_ms * 1e-3)
+    del mesh, p3
+
+    # ---- N > 1: the same job ending with the full result on every rank (NCCL gather over NVLink) ----
+    gather = None
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms = t.item()
-    value = B * world / (step_ms * 1e-3)
+        xg = torch.from_numpy(x_all).to(dev)               # every rank holds the (tiny) inputs: 152 B per sample
+        full = torch.empty((total, 6890, 3), dtype=torch.float32, device=dev)
+
+        def fn(a, b):
+            return model(xg[a:b])[0]
+        with torch.no_grad():
+            for _ in range(2):
+                forward_gathered(fn, total, (6890, 3), GATHER_BLOCK, device=dev, out=full)
+            barrier()
+            gevs = []
+            for _ in range(args.steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                forward_gathered(fn, total, (6890, 3), GATHER_BLOCK, device=dev, out=full)
+                e1.record()
+                gevs.append((e0, e1))
+            barrier()
+        g_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in gevs) / args.steps)
+        # check on rank 0: the gathered batch equals a local forward of samples the other ranks computed
+        ok = True
+        if rank == 0:
+            with torch.no_grad():
+                probe = [total - 1, total // 2 + 3, GATHER_BLOCK + 1]
+                ok = all(torch.equal(model(xg[i:i + 1])[0][0], full[i]) for i in probe)
+        recv = (world - 1) / world * total * MESH_BYTES
+        # same slicing without the collective, to separate the cost of the gather from the cost of running in 1024-sample calls
+        with torch.no_grad():
+            for _ in range(2):
+                for a in range(lo, hi, GATHER_BLOCK):
+                    model(xg[a:min(a + GATHER_BLOCK, hi)])
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                for a in range(lo, hi, GATHER_BLOCK):
+                    model(xg[a:min(a + GATHER_BLOCK, hi)])
+            e1.record()
+            barrier()
+        s_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+        gather = {'value': total / (g_ms * 1e-3), 'unit': UNIT, 'ms_per_step': g_ms, 'efficiency_vs_no_gather': step_ms / g_ms,
+                  'ms_per_step_same_slicing_no_gather': s_ms,
+                  'bytes_received_per_gpu': int(recv), 'nvlink_gbs_in_per_gpu_over_step': recv / (g_ms * 1e-3) / 1e9,
+                  'block_samples': GATHER_BLOCK, 'rounds': -(-total // (world * GATHER_BLOCK)), 'verified': bool(ok),
+                  'how': 'block-cyclic deal, all_gather_into_tensor of round k on a side stream while round k+1 computes; '
+                         'output (65536, 6890, 3) fp32 written in place, no pad / cat copies'}
+        del full, xg
 
     # ---- end to end: pinned host input -> H2D -> forward -> mesh + pose3d D2H ----
     from gator_b200.pipeline import HostPipeline
     pipe = HostPipeline(model, B)                    # public host-to-host API: sliced decoder, D2H overlapped
     mesh_host, p3_host = pipe.mesh_host, pipe.pose3d_host
     with torch.no_grad():
-        def e2e_step():
-            pipe.forward(x_host)
         for _ in range(max(args.warmup, 1)):
-            e2e_step()
+            pipe.forward(x_host)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.steps):
-            e2e_step()
+            pipe.forward(x_host)
         e1.record()
         barrier()
-    e2e_ms = e0.elapsed_time(e1) / args.steps
-    t = torch.tensor([e2e_ms], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_ms = t.item()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+
+    # ---- end to end with the evaluation epilogue on the device: only per-sample errors come back ----
+    from gator_b200.evaluate import EvalEpilogue
+    from builders import regressor as _reg
+    ep = EvalEpilogue(_reg('h36m'), device=dev)
+    gt_mesh = torch.randn(B, 6890, 3, device=dev) * 0.3
+    gt_pose = torch.randn(B, 17, 3, device=dev) * 300
+    err_host = torch.empty((2, B), dtype=torch.float32).pin_memory()
+    with torch.no_grad():
+        def eval_step():
+            xd = x_host.to(dev, non_blocking=True)
+            m_, _ = model(xd)
+            r = ep(m_, gt_mesh, gt_pose)
+            err_host[0].copy_(r.joint_err, non_blocking=True)
+            err_host[1].copy_(r.surface_err, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        for _ in range(max(args.warmup, 1)):
+            eval_step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            eval_step()
+        e1.record()
+        barrier()
+    ev_ms = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    del gt_mesh, gt_pose
 
     # ---- batch-1 latency (BASELINE metric: p50 batch-1 latency), eager and under a CUDA graph ----
     latency = None
-    if rank == 0:
+    if rank == 0 and world == 1:
         x1 = x[:1].clone()
         with torch.no_grad():
             for _ in range(5):
@@ -282,121 +424,167 @@ def run_b200(args):
     line = None
     if rank == 0:
         peaks = measured_peaks()
-        # ---- dominant kernels alone (C-ABI entry points, CUDA events on the launching stream) ----
-        nb = 1184                                               # 8 x 148 samples: 3987 chain tiles, 2368 attention CTAs
-        pcode = _lib.PRECISIONS[args.precision]
-        s = _lib.stream_ptr()
-
-        def time_launch(fn, reps=20):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            for _ in range(reps):
-                fn()
-            e1.record()
-            torch.cuda.synchronize()
-            return e0.elapsed_time(e1) / reps
-
-        qkv = torch.randn(nb * 431, 192, device=dev)
-        out = torch.empty(nb * 431, 64, device=dev)
-        sa_ms = time_launch(lambda: _lib.check(L.gator_mdr_self_attention(qkv.data_ptr(), out.data_ptr(), nb, pcode, s), 'self_attention'))
-        sa_tf = SA_FLOP_PER_SAMPLE * nb / (sa_ms * 1e-3) / 1e12
-        sa_name = 'mdr_self_attn_kernel (fp32 FFMA)' if pcode == 0 else f'mdr_self_attn_umma_kernel<{"true" if pcode == 2 else "false"}> (tcgen05)'
-        kernels = [{'kernel': sa_name, 'bound': 'tensor', 'achieved': sa_tf, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
-                    'frac': sa_tf / peaks['bf16_tflops'], 'launch_ms': sa_ms,
-                    'flops_per_launch': SA_FLOP_PER_SAMPLE * nb}]
-        if pcode != 0:
-            model(x[:2])                                            # make sure the MDR weights are packed
-            (_, _, _, _), table, _ = model.pose2mesh._packed
-            xin = torch.randn(nb * 431, 64, device=dev)
-            att = torch.randn(nb * 431, 64, device=dev)
-            kvb = torch.randn(nb * J, 128, device=dev)
-            x3o = torch.empty(nb * 431, 64, device=dev)
-            qko = torch.empty(nb * 431, 192, device=dev)
-            ch_ms = time_launch(lambda: _lib.check(L.gator_mdr_layer_chain(table, 1, J, pcode, xin.data_ptr(), att.data_ptr(), kvb.data_ptr(),
-                                                                            x3o.data_ptr(), qko.data_ptr(), nb, s), 'layer_chain'))
-            ch_flop = nb * 431 * (14 * 64 * 64 * 2 + 2 * J * 32 * 2 * 2)
-            ch_tf = ch_flop / (ch_ms * 1e-3) / 1e12
-            kernels.insert(0, {'kernel': 'mdr_chain_kernel<1,J> (tcgen05 fused layer chain)', 'bound': 'tensor', 'achieved': ch_tf,
-                               'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s', 'frac': ch_tf / peaks['bf16_tflops'],
-                               'launch_ms': ch_ms, 'flops_per_launch': ch_flop})
-        if pcode == 2:
-            # upsample_conv's product on the wide tcgen05 + TMA kernel (bias-only epilogue instead of the conv3 scatter)
-            from gator_b200.packing import pack_umma_wide
-            Mw, Nw, Kw = 3 * 4096, 6890, 1296
-            Aw = torch.randn(Mw, Kw, device=dev)
-            Ww = pack_umma_wide(torch.randn(Nw, Kw, device=dev) / Kw ** 0.5)
-            Cw = torch.empty(Mw, 6892, device=dev)
-            wsw = torch.empty(L.gator_umma_wide_a_bytes(Mw, Kw), dtype=torch.uint8, device=dev)
-            ga = _lib.GemmArgs(M=Mw, N=Nw, K=Kw, lda=Kw, ldw=Kw, ldc=6892, precision=2, A=_lib.ptr(Aw), W_wide=_lib.ptr(Ww),
-                               a_image=_lib.ptr(wsw), a_image_bytes=wsw.numel(), C=_lib.ptr(Cw))
-            wg_ms = time_launch(lambda: _lib.check(L.gator_gemm(ga, s), 'gator_gemm wide'))
-            wg_flop = 2.0 * Mw * Nw * Kw
-            kernels.append({'kernel': 'umma_gemm_wide_kernel (upsample_conv shape, 4096 samples; incl. the A-image pre-pass)',
-                            'bound': 'tensor', 'achieved': wg_flop / (wg_ms * 1e-3) / 1e12, 'peak': peaks['bf16_tflops'],
-                            'unit': 'TFLOP/s', 'frac': wg_flop / (wg_ms * 1e-3) / 1e12 / peaks['bf16_tflops'], 'launch_ms': wg_ms,
-                            'flops_per_launch': wg_flop, 'tensor_flops_issued': 3 * wg_flop,
-                            'frac_issued': 3 * wg_flop / (wg_ms * 1e-3) / 1e12 / peaks['bf16_tflops']})
-            del Aw, Ww, Cw, wsw
-            # evaluation epilogue (row f1): HBM-bound, 2 x 82 680 B read per sample
-            from gator_b200.evaluate import EvalEpilogue
-            from builders import regressor as _reg
-            ep = EvalEpilogue(_reg('h36m'), device=dev)
-            pm = torch.randn(4096, 6890, 3, device=dev) * 0.3
-            gm = pm + 0.02 * torch.randn_like(pm)
-            gj = torch.randn(4096, 17, 3, device=dev) * 300
-            ev_ms = time_launch(lambda: ep(pm, gm, gj))
-            ev_bytes = 4096 * 2 * 82680
-            kernels.append({'kernel': 'eval_sample_kernel (+ eval_mean_kernel)', 'bound': 'hbm', 'achieved': ev_bytes / (ev_ms * 1e-3) / 1e9,
-                            'peak': peaks.get('hbm_gbs'), 'unit': 'GB/s',
-                            'frac': (ev_bytes / (ev_ms * 1e-3) / 1e9 / peaks['hbm_gbs']) if peaks.get('hbm_gbs') else None,
-                            'launch_ms': ev_ms, 'bytes_per_launch': ev_bytes, 'traffic': 686.8e6})
-            del pm, gm, gj
-        roofline = dict(kernels[0])
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu launch list of a 4096-sample forward
-        # (profiles/r01_launches_bf16x3_b4096_flat.csv, layers 1-2: 944.5 MB read + 1750 MB written per 4096 samples), scaled to
-        # this launch's 1184 samples; ncu flushes caches between kernels, so this is an upper bound of a warm launch
-        roofline.update({'traffic': 779e6 if pcode != 0 else None, 'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)',
-                         'note': 'algorithmic flops (2*MAC of the layer\'s 14 64x64 products + cross-attention, or of QK^T + PV) per launch of '
-                                 '1184 samples; the 3-term split issues 3x that many tensor-core MACs, which are not counted; both kernels are '
-                                 'bound by CUDA-core softmax/GELU/LayerNorm/operand-conversion work and MMA round-trip latency, not by the tensor pipe',
-                         'other_kernels': kernels[1:]})
-        # parity of this very configuration against the CPU oracle (64 samples)
-        from helpers import oracle_setup, orc, regressor
-        sd, gc, mc, alpha = oracle_setup(TAG)
-        xs = torch.from_numpy(make_inputs(64, seed=7))
-        with torch.no_grad():
-            ref_mesh, _ = orc.gator_forward(sd, gc, mc, xs, alpha)
-            got, _ = model(xs.to(dev))
-        mp, pa = orc.mpjpe_pa(got.cpu().numpy(), ref_mesh.numpy(), regressor('h36m'))
-        parity = {'max_abs_vertex_err_m': (got.cpu() - ref_mesh).abs().max().item(), 'mpjpe_drift_mm': mp,
-                  'pa_mpjpe_drift_mm': pa, 'samples': 64, 'tolerance_m': 1e-4}
-        threads = os.cpu_count() or 1
-        cpu_v, cpu_med, cpu_n = cpu_forward_rate(64, 12.0, threads)
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
-                'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'strong' if world > 1 else 'weak', 'vs_baseline': None,
                 'dtype': args.precision, 'data': 'synthetic',
-                'config': {'workload': f'GATOR.forward J=19 alpha=True, batch {B}/GPU (BASELINE configs[3]); '
-                                       'random-init weights, synthetic SMPL-shaped template/bases',
-                           'global_batch': B * world, 'l2': 'flushed (256 MiB memset) before every timed step',
-                           'parallelism': f'batch-sharded x{world}, no collective on the data path'},
+                'config': {'workload': workload_name(world, B), 'global_batch': total, 'per_gpu_batch': B,
+                           'l2': 'flushed (256 MiB memset) before every timed step',
+                           'precision': 'bf16x3 = 3-term bf16 split GEMMs (fp32-level accuracy on tcgen05), fp16 self-attention core',
+                           'parallelism': f'batch-sharded x{world}, no collective on the data path' + (' (strong scaling: the 65 536-sample job of configs[4] at every N > 1; N = 1 runs configs[3])' if world > 1 else '')},
                 'clocks': clocks,
-                'e2e': {'value': B * world / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
+                'e2e': {'value': total / (e2e_ms * 1e-3), 'unit': UNIT, 'ms_per_step': e2e_ms,
                         'h2d_bytes_per_step': int(x_host.numel() * 4), 'd2h_bytes_per_step': int((mesh_host.numel() + p3_host.numel()) * 4)},
+                'e2e_eval': {'value': total / (ev_ms * 1e-3), 'unit': UNIT, 'ms_per_step': ev_ms, 'h2d_bytes_per_step': int(x_host.numel() * 4),
+                             'd2h_bytes_per_step': int(err_host.numel() * 4),
+                             'what': 'pinned host poses -> forward -> device-side evaluation epilogue (sparse J-regression, root alignment, '
+                                     'MPJPE / MPVPE per sample, csrc/eval.cu) -> per-sample errors to pinned host memory; the mesh never leaves the GPU'},
                 'gpu_launches': int(launches),
                 'tflops_effective': FLOP_PER_MESH * value / 1e12,
                 'numa_node': numa_node, 'wall_s_timed_region': t_wall, 'step_ms': [round(t_, 3) for t_ in per_step],
-                'latency_b1': latency,
-                'roofline': roofline, 'parity': parity,
-                'cpu_baseline': {'value': cpu_v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                 'sample': f'{cpu_n} forwards of batch 64 (median {cpu_med * 1e3:.0f} ms), oracle port of the reference forward'}}
+                'whole_step_fraction_of_tensor_peak': FLOP_PER_MESH * value / world / 1e12 / peaks['bf16_tflops_sustained']}
+        if gather is not None:
+            line['with_gather'] = gather
+            line['value_with_gather'] = gather['value']
+        if latency is not None:
+            line['latency_b1'] = latency
+        if world == 1:
+            line.update(single_gpu_extras(args, model, x, dev, peaks))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line), flush=True)
+
+
+def single_gpu_extras(args, model, x, dev, peaks):
+    """Rank 0, N = 1: kernel rooflines, configs[2] (SMPL), parity against the oracle, CPU and eager-GPU baselines."""
+    import torch
+    from gator_b200 import _lib
+    L = _lib.lib()
+    J = model.num_joint
+    out = {}
+    traffic = ncu_traffic()
+    nb = 4096                                               # launches of the step's own size
+    pcode = _lib.PRECISIONS[args.precision]
+    s = _lib.stream_ptr()
+
+    def time_launch(fn, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def tensor_entry(name, ms, flop, key, note=None):
+        tf = flop / (ms * 1e-3) / 1e12
+        d = {'kernel': name, 'bound': 'tensor', 'achieved': tf, 'peak': peaks['bf16_tflops'], 'unit': 'TFLOP/s',
+             'frac': tf / peaks['bf16_tflops'], 'launch_ms': ms, 'flops_per_launch': flop, 'traffic': traffic.get(key)}
+        if note:
+            d['note'] = note
+        return d
+
+    kernels = []
+    qkv = torch.randn(nb * 431, 192, device=dev)
+    att = torch.empty(nb * 431, 64, device=dev)
+    if pcode == 0:
+        ms = time_launch(lambda: _lib.check(L.gator_mdr_self_attention(qkv.data_ptr(), att.data_ptr(), nb, 0, s), 'self_attention'))
+        kernels.append(tensor_entry('mdr_self_attn_kernel (fp32 FFMA)', ms, SA_FLOP_PER_SAMPLE * nb, 'mdr_self_attn_kernel'))
+    else:
+        model(x[:2])                                            # make sure the MDR weights are packed
+        (_, _, _, _), table, _ = model.pose2mesh._packed
+        img = torch.empty(L.gator_mdr_self_attention_image_bytes(nb), dtype=torch.uint8, device=dev)
+        xin = torch.randn(nb * 431, 64, device=dev)
+        kvb = torch.randn(nb * J, 128, device=dev)
+        x3o = torch.empty(nb * 431, 64, device=dev)
+        ch_ms = time_launch(lambda: _lib.check(L.gator_mdr_layer_chain(table, 1, J, pcode, xin.data_ptr(), att.data_ptr(), kvb.data_ptr(),
+                                                                        x3o.data_ptr(), None, img.data_ptr(), nb, s), 'layer_chain'))
+        ch_flop = nb * 431 * (14 * 64 * 64 * 2 + 2 * J * 32 * 2 * 2)
+        kernels.append(tensor_entry('mdr_chain2_kernel<J> (tcgen05 fused layer chain, operands in tensor memory)', ch_ms, ch_flop, 'mdr_chain2_kernel',
+                                    'algorithmic 2*MAC of the layer\'s 14 64x64 products + cross-attention; the 3-term bf16 split issues 3x the MMAs'))
+        _lib.check(L.gator_mdr_self_attention_f16(qkv.data_ptr(), img.data_ptr(), att.data_ptr(), nb, s), 'qkv image')
+        sa_ms = time_launch(lambda: _lib.check(L.gator_mdr_self_attention_core(img.data_ptr(), att.data_ptr(), nb, s), 'self_attention_core'))
+        kernels.append(tensor_entry('mdr_self_attn2_kernel (tcgen05 fp16, P in tensor memory, TMA-fed)', sa_ms, SA_FLOP_PER_SAMPLE * nb, 'mdr_self_attn2_kernel',
+                                    'bound by the exponentials: 2 x 431 x 431 ex2 per sample = 0.76 G per launch against 16 MUFU results per clock and SM'))
+        del img, xin, kvb, x3o
+    del qkv, att
+    if pcode == 2:
+        # upsample_conv's product on the wide tcgen05 + TMA kernel (bias-only epilogue instead of the conv3 scatter)
+        from gator_b200.packing import pack_umma_wide
+        Mw, Nw, Kw = 3 * 4096, 6890, 1296
+        Aw = torch.randn(Mw, Kw, device=dev)
+        Ww = pack_umma_wide(torch.randn(Nw, Kw, device=dev) / Kw ** 0.5)
+        Cw = torch.empty(Mw, 6892, device=dev)
+        wsw = torch.empty(L.gator_umma_wide_a_bytes(Mw, Kw), dtype=torch.uint8, device=dev)
+        ga = _lib.GemmArgs(M=Mw, N=Nw, K=Kw, lda=Kw, ldw=Kw, ldc=6892, precision=2, A=_lib.ptr(Aw), W_wide=_lib.ptr(Ww),
+                           a_image=_lib.ptr(wsw), a_image_bytes=wsw.numel(), C=_lib.ptr(Cw))
+        wg_ms = time_launch(lambda: _lib.check(L.gator_gemm(ga, s), 'gator_gemm wide'))
+        wg_flop = 2.0 * Mw * Nw * Kw
+        e = tensor_entry('umma_gemm_wide_kernel (upsample_conv shape, 4096 samples; incl. the A-image pre-pass)', wg_ms, wg_flop, 'umma_gemm_wide_kernel')
+        e.update({'tensor_flops_issued': 3 * wg_flop, 'frac_issued': 3 * wg_flop / (wg_ms * 1e-3) / 1e12 / peaks['bf16_tflops']})
+        kernels.append(e)
+        del Aw, Ww, Cw, wsw
+        # evaluation epilogue (row f1): HBM-bound, 2 x 82 680 B read per sample
+        from gator_b200.evaluate import EvalEpilogue
+        from builders import regressor as _reg
+        ep = EvalEpilogue(_reg('h36m'), device=dev)
+        pm = torch.randn(4096, 6890, 3, device=dev) * 0.3
+        gm = pm + 0.02 * torch.randn_like(pm)
+        gj = torch.randn(4096, 17, 3, device=dev) * 300
+        ev_ms = time_launch(lambda: ep(pm, gm, gj))
+        ev_bytes = 4096 * 2 * MESH_BYTES
+        kernels.append({'kernel': 'eval_sample_kernel (+ eval_mean_kernel)', 'bound': 'hbm', 'achieved': ev_bytes / (ev_ms * 1e-3) / 1e9,
+                        'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ev_bytes / (ev_ms * 1e-3) / 1e9 / peaks['hbm_gbs'],
+                        'launch_ms': ev_ms, 'bytes_per_launch': ev_bytes, 'traffic': traffic.get('eval_sample_kernel')})
+        del pm, gm, gj
+    roofline = dict(kernels[0])
+    roofline.update({'peak_source': peaks['src'] + ' (cuBLAS bf16 burst)',
+                     'traffic_source': 'dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu launch list of a '
+                                       '4096-sample forward (profiles/r02_traffic.json); null if not captured',
+                     'other_kernels': kernels[1:]})
+    out['roofline'] = roofline
+
+    # ---- BASELINE configs[2]: SMPL LBS layer alone, batch 16384 ----
+    from builders import build_b200_smpl, synthetic
+    Bs = 16384
+    pose, betas, trans = [torch.from_numpy(a).to(dev) for a in synthetic.smpl_inputs(Bs)]
+    smpl = {}
+    layer = build_b200_smpl(device=dev)
+    for prec in ('fp32', 'bf16x3'):
+        layer.set_precision(prec)
+        with torch.no_grad():
+            ms = time_launch(lambda: layer(pose, betas, trans), reps=10)
+        by = Bs * (MESH_BYTES + 24 * 12 + 72 * 4 + 10 * 4 + 12)
+        smpl[prec] = {'value': Bs / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'bound': 'hbm', 'bytes_per_mesh': by // Bs,
+                      'achieved': by / (ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'frac': by / (ms * 1e-3) / 1e9 / peaks['hbm_gbs']}
+    out['other_workloads'] = {'smpl_layer_b16384': {'workload': 'SMPL_Layer.forward(pose, betas, trans), batch 16384 (BASELINE configs[2]), synthetic '
+                                                                'SMPL-shaped buffers; device-resident inputs, CUDA events over 10 calls',
+                                                    'roofline': 'HBM: 83.3 KB of mandatory traffic per mesh (SURVEY 8(d))', **smpl}}
+    del pose, betas, trans
+
+    # ---- parity of this very configuration against the CPU oracle (64 samples) ----
+    from helpers import oracle_setup, orc, regressor
+    sd, gc, mc, alpha = oracle_setup(TAG)
+    xs = torch.from_numpy(make_inputs(64, seed=7))
+    with torch.no_grad():
+        ref_mesh, _ = orc.gator_forward(sd, gc, mc, xs, alpha)
+        got, _ = model(xs.to(dev))
+    mp, pa = orc.mpjpe_pa(got.cpu().numpy(), ref_mesh.numpy(), regressor('h36m'))
+    out['parity'] = {'max_abs_vertex_err_m': (got.cpu() - ref_mesh).abs().max().item(), 'mpjpe_drift_mm': mp,
+                     'pa_mpjpe_drift_mm': pa, 'samples': 64, 'tolerance_m': 1e-4}
+    try:
+        out['gpu_eager_baseline'] = gpu_eager_rate(dev)
+    except Exception as e:      # informational leg: report, do not fail the bench
+        out['gpu_eager_baseline'] = {'error': f'{type(e).__name__}: {e}'}
+    threads = os.cpu_count() or 1
+    cpu_v, cpu_med, cpu_n = cpu_forward_rate(64, 12.0, threads)
+    out['cpu_baseline'] = {'value': cpu_v, 'unit': UNIT, 'cores': threads, 'kind': 'port',
+                           'sample': f'{cpu_n} forwards of batch 64 (median {cpu_med * 1e3:.0f} ms), oracle port of the reference forward'}
+    return out
 
 
 def main():
@@ -405,7 +593,7 @@ def main():
     ap.add_argument('--steps', type=int, default=10)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--batch', type=int, default=4096, help='samples per GPU')
+    ap.add_argument('--batch', type=int, default=0, help='samples per GPU (default: 4096 on one GPU, 65536 / N on N)')
     ap.add_argument('--precision', default='bf16x3', choices=['fp32', 'bf16', 'bf16x3'])
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup

@@ -94,7 +94,7 @@ class SmplCamArgs(C.Structure):
 
 _STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs, EvalArgs, Pose2dArgs, SmplCamArgs]
 EXPORTS = ['gator_abi_version', 'gator_last_error', 'gator_abi_sizeof', 'gator_launch_count',
-           'gator_mdr_self_attention', 'gator_mdr_self_attention_image_bytes', 'gator_mdr_self_attention_f16', 'gator_mdr_layer_chain', 'gator_umma_weight_layout',
+           'gator_mdr_self_attention', 'gator_mdr_self_attention_image_bytes', 'gator_mdr_self_attention_f16', 'gator_mdr_self_attention_core', 'gator_mdr_layer_chain', 'gator_umma_weight_layout',
            'gator_gat_slot_name', 'gator_gat_workspace_bytes', 'gator_gat_forward',
            'gator_mdr_slot_name', 'gator_mdr_workspace_bytes', 'gator_mdr_forward',
            'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_gemm',
@@ -146,7 +146,9 @@ def lib():
         L.gator_mdr_self_attention_f16.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.gator_mdr_layer_chain.restype = C.c_int
         L.gator_mdr_layer_chain.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
-                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+                                            C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+        L.gator_mdr_self_attention_core.restype = C.c_int
+        L.gator_mdr_self_attention_core.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.gator_umma_wide_layout.restype = C.c_int
         L.gator_umma_wide_layout.argtypes = [C.c_int32, C.c_int32, c_int_p, c_int_p]
         L.gator_umma_wide_a_bytes.restype = C.c_size_t

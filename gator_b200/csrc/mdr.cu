@@ -413,11 +413,19 @@ extern "C" int gator_mdr_self_attention_f16(const float* qkv, void* image, float
   return launch_self_attn2(image, out, batch, (cudaStream_t)stream);
 }
 
+extern "C" int gator_mdr_self_attention_core(const void* image, float* out, int32_t batch, void* stream) {
+  using namespace gator;
+  GATOR_REQUIRE(image && out && batch >= 0, "gator_mdr_self_attention_core: bad argument");
+  if (batch == 0) return GATOR_OK;
+  return launch_self_attn2(image, out, batch, (cudaStream_t)stream);
+}
+
 extern "C" int gator_mdr_layer_chain(const void* const* weights, int32_t layer, int32_t num_joint, int32_t precision,
                                      const float* x_in, const float* att_in, const float* kv, float* x3_out,
-                                     float* qkv_out, int32_t batch, void* stream) {
+                                     float* qkv_out, void* image_out, int32_t batch, void* stream) {
   using namespace gator;
-  GATOR_REQUIRE(weights && x_in && kv && x3_out && qkv_out, "gator_mdr_layer_chain: null buffer");
+  GATOR_REQUIRE(weights && x_in && kv && x3_out && (qkv_out || image_out), "gator_mdr_layer_chain: null buffer");
+  GATOR_REQUIRE(!image_out || precision == GATOR_PREC_BF16X3, "gator_mdr_layer_chain: operand images need GATOR_PREC_BF16X3");
   GATOR_REQUIRE(layer >= 0 && layer < GATOR_MDR_LAYERS && num_joint >= 2 && num_joint <= MAXJ && batch >= 0,
                 "gator_mdr_layer_chain: bad argument");
   GATOR_REQUIRE(precision == GATOR_PREC_BF16 || precision == GATOR_PREC_BF16X3, "gator_mdr_layer_chain: tensor-core precisions only");
@@ -428,8 +436,11 @@ extern "C" int gator_mdr_layer_chain(const void* const* weights, int32_t layer, 
   GATOR_REQUIRE(weights[base + MDRL_CHAIN], "gator_mdr_layer_chain: CHAIN blob missing");
   const float* prm[11] = {static_cast<const float*>(weights[pbase + MDRL_SO_B]), W(MDRL_N1_W), W(MDRL_N1_B), W(MDRL_PROJ_B),
                           W(MDRL_N2_W), W(MDRL_N2_B), W(MDRL_FC1_B), W(MDRL_FC2_B), W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
-  return launch_mdr_chain(x_in, att_in, kv, weights[base + MDRL_CHAIN], prm, x3_out, qkv_out, nullptr, batch, num_joint,
-                          precision == GATOR_PREC_BF16X3, (cudaStream_t)stream);
+  if (precision == GATOR_PREC_BF16X3)
+    return launch_mdr_chain2(x_in, att_in, kv, weights[base + MDRL_CHAIN], prm, x3_out, qkv_out, image_out, nullptr, batch, num_joint,
+                             (cudaStream_t)stream);
+  return launch_mdr_chain(x_in, att_in, kv, weights[base + MDRL_CHAIN], prm, x3_out, qkv_out, nullptr, batch, num_joint, false,
+                          (cudaStream_t)stream);
 }
 
 extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {

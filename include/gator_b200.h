@@ -209,14 +209,18 @@ int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_
  * layer-chain kernel writes these images itself). */
 size_t gator_mdr_self_attention_image_bytes(int32_t batch);
 int gator_mdr_self_attention_f16(const float* qkv, void* image, float* out, int32_t batch, void* stream);
-/* The fused row-wise chain of MDR layer `layer` (0..2) on its own (csrc/mdr_chain_umma.cu; tensor-core precisions
- * only): everything of MDR.py:140-153 between two self-attention cores.  `weights` is the gator_mdr_args table;
- * x_in (B*431,64) = embedded vertices (layer 0) or the previous layer's x3; att_in (B*431,64) = previous
- * self-attention output (NULL for layer 0); kv (B*J,128) = this layer's cross-attention K|V;
- * outputs x3_out (B*431,64), qkv_out (B*431,192). */
+/* The core alone on already packed operand images (what gator_mdr_forward runs; roofline measurement). */
+int gator_mdr_self_attention_core(const void* image, float* out, int32_t batch, void* stream);
+/* The fused row-wise chain of MDR layer `layer` (0..2) on its own (tensor-core precisions only; GATOR_PREC_BF16X3:
+ * csrc/mdr_chain2_umma.cu, GATOR_PREC_BF16: csrc/mdr_chain_umma.cu): everything of MDR.py:140-153 between two
+ * self-attention cores.  `weights` is the gator_mdr_args table; x_in (B*431,64) = embedded vertices (layer 0) or the
+ * previous layer's x3; att_in (B*431,64) = previous self-attention output (NULL for layer 0); kv (B*J,128) = this
+ * layer's cross-attention K|V; outputs x3_out (B*431,64) and q|k|v as fp32 rows qkv_out (B*431,192) and / or as the
+ * fp16 operand images image_out (gator_mdr_self_attention_image_bytes(B) bytes; GATOR_PREC_BF16X3 only); either of
+ * the two q|k|v outputs may be NULL, not both. */
 int gator_mdr_layer_chain(const void* const* weights, int32_t layer, int32_t num_joint, int32_t precision,
                           const float* x_in, const float* att_in, const float* kv, float* x3_out, float* qkv_out,
-                          int32_t batch, void* stream);
+                          void* image_out, int32_t batch, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * SMPL linear blend skinning - replaces SMPL_Layer.forward

@@ -1,7 +1,8 @@
 """Summarise an `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,
 sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active --csv` launch list: per kernel name the launch count,
 total / average duration, share of the total, DRAM bytes per launch and tensor-pipe activity.
-    python tools/launch_summary.py launches.csv [skip_first_n_launches]"""
+    python tools/launch_summary.py launches.csv [skip_first_n_launches] [traffic.json]
+With a third argument, dram bytes (read + write) per launch and kernel are also written as JSON (bench.py: roofline.traffic)."""
 import collections
 import csv
 import sys
@@ -42,3 +43,11 @@ print(f'sum of kernel times: {tot / 1e3:.2f} ms over {sum(a["n"] for a in agg.va
 for name, a in sorted(agg.items(), key=lambda kv: -kv[1]['us']):
     print(f'{name:44s} n={a["n"]:4d} {a["us"] / 1e3:8.3f} ms {100 * a["us"] / tot:5.1f}%  avg {a["us"] / a["n"]:8.1f} us  '
           f'dram rd {a["rd"] / a["n"] / 1e6:7.1f} wr {a["wr"] / a["n"] / 1e6:7.1f} MB/launch  tensor pipe {a["tc"] / max(a["us"], 1e-9):4.1f}%')
+
+if len(sys.argv) > 3:
+    import json
+    js = {}
+    for name, a in agg.items():
+        short = name.split('::')[-1].split('<')[0].strip()
+        js[short] = (a['rd'] + a['wr']) / a['n']
+    json.dump(js, open(sys.argv[3], 'w'), indent=1, sort_keys=True)
