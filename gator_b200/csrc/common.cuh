@@ -128,11 +128,11 @@ int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, co
 int launch_mdr_chain2(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
                       float* x3_out, float* qkv_out, void* img_out, float* hd_out, int nb, int J, cudaStream_t stream);
 
-// All GATBlocks of the lifter in one kernel (csrc/gat_chain_umma.cu).  blobs_dev / prm_dev are DEVICE arrays of
-// pointers: [depth] weight-piece blobs and [depth * 14] fp32 parameter arrays.
+// All GATBlocks of the lifter in one kernel (csrc/gat_chain2_umma.cu; always the 3-term bf16 split).  blobs_dev / prm_dev
+// are DEVICE arrays of pointers: [depth] weight-piece blobs (34 x 32 KB) and [depth * 14] fp32 parameter arrays.
 bool gat_chain_supported(int J);
 int launch_gat_chain(float* x, int rows, int J, int depth, const void* const* blobs_dev, const float* const* prm_dev,
-                     const float* attn_bias, const float* mask1, const float* mask2, bool split, cudaStream_t stream);
+                     const float* attn_bias, const float* mask1, const float* mask2, cudaStream_t stream);
 
 // LayerNorm over the last dim (C = 64 or 128).  mode 0: nn.LayerNorm (eps 1e-5, biased var);
 // mode 1: a*(x-mean)/(std_unbiased+1e-6)+b (vanilla_transformer_encoder.py:31-34).  gelu: apply after.

@@ -267,7 +267,7 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
     if (fused)
       GATOR_TRY(launch_gat_chain(x, M, J, a->depth, static_cast<const void* const*>(a->weights[GAT_CHAIN_BLOBS]),
                                  static_cast<const float* const*>(a->weights[GAT_CHAIN_PRM]), G(GAT_ATTN_BIAS),
-                                 G(GAT_HOP_MASK1), G(GAT_HOP_MASK2), a->precision == GATOR_PREC_BF16X3, stream));
+                                 G(GAT_HOP_MASK1), G(GAT_HOP_MASK2), stream));
     for (int l = 0; !fused && l < a->depth; ++l) {
       const int base = GAT_NUM_GLOBAL + l * GATB_NUM;
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };

@@ -246,21 +246,20 @@ class GAT(nn.Module):
         # fused-blocks kernel (csrc/gat_chain_umma.cu): 36 weight pieces + 14 parameter arrays per block
         keep = []
         blobs, prms = [], []
-        zeros16 = torch.zeros(16, 128, device=dev)
         for b in block_dicts:
             qkv, proj, gcn = b['QKV_W'], b['PROJ_W'], b['GCN_W01']
             w01 = torch.zeros(192, 128, device=dev)
             w01[:144] = b['XF_W01']
             wb = torch.zeros(128, 192, device=dev)
             wb[:, :144] = b['XF_WB']
-            pieces = [torch.cat([qkv[16 * h:16 * h + 16], qkv[128 + 16 * h:128 + 16 * h + 16],
-                                 qkv[256 + 16 * h:256 + 16 * h + 16], zeros16], 0) for h in range(8)]
+            # 34 pieces in the order csrc/gat_chain2_umma.cu consumes them
+            pieces = [qkv[0:64], qkv[64:128], qkv[128:192], qkv[256:320], qkv[192:256], qkv[320:384]]
             pieces += [proj[:, 0:64], proj[:, 64:128]]
             pieces += [gcn[0:128, 0:64], gcn[0:128, 64:128], gcn[128:256, 0:64], gcn[128:256, 64:128]]
-            for u in range(3):
-                pieces += [w01[64 * u:64 * u + 64], wb[:, 64 * u:64 * u + 64]]
-            for u in range(8):
-                pieces += [b['FC1_W'][64 * u:64 * u + 64], b['FC2_W'][:, 64 * u:64 * u + 64]]
+            pieces += [w01[64 * u:64 * u + 64] for u in range(3)] + [wb[:, 64 * u:64 * u + 64] for u in range(3)]
+            fc1, fc2 = b['FC1_W'], b['FC2_W']
+            pieces += [fc1[64 * u:64 * u + 64] for u in range(4)] + [fc2[:, 64 * u:64 * u + 64] for u in range(4)]
+            pieces += [fc1[64 * u:64 * u + 64] for u in range(4, 8)] + [fc2[:, 64 * u:64 * u + 64] for u in range(4, 8)]
             blob = pack_umma_blob(pieces)
             assert blob.numel() == len(pieces) * 2 * 64 * 128
             xfb = torch.zeros(192, device=dev)

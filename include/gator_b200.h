@@ -76,10 +76,11 @@ typedef enum {
   GAT_NORM_B,         /* (128)                                                    */
   GAT_LIFT_W,         /* (3J,128J) lifter.weight                                 */
   GAT_LIFT_B,         /* (3J)                                                     */
-  GAT_CHAIN_BLOBS,    /* fused-blocks kernel (csrc/gat_chain_umma.cu), may be NULL: DEVICE array [depth] of pointers to
-                         36 x 32 KB bf16 hi|lo tcgen05 weight pieces per block: qkv per head [q_h;k_h;v_h;0] (64x128) x8,
-                         proj K-halves (128x64) x2, gcn W0 / W1 K-halves x4, {x_feat.linears rows 64u.. (64x128),
-                         linearback[:, 64u..] (128x64)} x3, {fc1 rows 64u.. , fc2[:, 64u..]} x8 */
+  GAT_CHAIN_BLOBS,    /* fused-blocks kernel (csrc/gat_chain2_umma.cu), may be NULL: DEVICE array [depth] of pointers to
+                         34 x 32 KB bf16 hi|lo tcgen05 weight pieces per block, in the order the kernel consumes them:
+                         q rows 0-63, 64-127, k heads 0-3, v heads 0-3, k heads 4-7, v heads 4-7 (64x128 each);
+                         proj K-halves (128x64) x2; gcn W0 K-halves x2, W1 K-halves x2; [L0;L1] rows 64u.. (64x128) x3;
+                         linearback[:, 64u..] (128x64) x3; fc1 rows 64u.. u=0..3; fc2[:, 64u..] u=0..3; fc1 u=4..7; fc2 u=4..7 */
   GAT_CHAIN_PRM,      /* DEVICE array [depth*14] of fp32 arrays: LN1_W, LN1_B, QKV_B, PROJ_B, GCN_M, GCN_ADIAG, GCN_AOFF,
                          GCN_BIAS, XF_B01 (zero-padded to 192), XF_BB, LN2_W, LN2_B, FC1_B, FC2_B; may be NULL */
   GAT_NUM_GLOBAL
