@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(NT, 1) gat_chain2_kernel(GatChain2Params p) {
   __shared__ uint32_t tmem_slot;
   __shared__ float2 xch_ln[2][128][4];              // LayerNorm partials [parity][row][column quarter]
   __shared__ uint32_t hopbits[2][MAXJ];             // hop masks as bit sets per query joint
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const int J = JT ? JT : p.J;
   constexpr int JU = JT ? JT : MAXJ;
   const int S = p.S;
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(NT, 1) gat_chain2_kernel(GatChain2Params p) {
   const int srow0 = samp * J;                       // first row of this row's sample
   float* xch = reinterpret_cast<float*>(smem + OFF_XCH);
   float* sbias = reinterpret_cast<float*>(smem + OFF_BIAS);
-  const bool leader = tid == 0;
+  const bool leader = warp == 0;                    // warp 0 (all lanes, one elected to issue) is also TMA producer and MMA issuer
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 32) {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(NT, 1) gat_chain2_kernel(GatChain2Params p) {
   const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
   const uint32_t t_lane = tmem + lane_addr;
 
-  // ---- leader (warp 0, lane 0): TMA producer + MMA issuer ----
+  // ---- leader warp: TMA producer + MMA issuer (executed by the whole warp, instructions issued by one elected lane) ----
   const int total_units = p.depth * PIECES;
   int u_use = 0, u_load = 0;
   uint32_t ph_a = 0;
@@ -144,8 +144,10 @@ __global__ void __launch_bounds__(NT, 1) gat_chain2_kernel(GatChain2Params p) {
         }
       }
       const uint8_t* src = p.blobs[u_load / PIECES] + (size_t)(u_load % PIECES) * PIECE_BYTES;
-      mbar_arrive_expect_tx(&bars.w_full[s], PIECE_BYTES);
-      bulk_copy_g2s(smem + OFF_RING + s * PIECE_BYTES, src, PIECE_BYTES, &bars.w_full[s]);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bars.w_full[s], PIECE_BYTES);
+        bulk_copy_g2s(smem + OFF_RING + s * PIECE_BYTES, src, PIECE_BYTES, &bars.w_full[s]);
+      }
       ++u_load;
     }
   };
@@ -159,14 +161,17 @@ __global__ void __launch_bounds__(NT, 1) gat_chain2_kernel(GatChain2Params p) {
     const uint32_t idesc = wide ? idesc_bf16(128, 128) : idesc_bf16(128, 64);
     const uint32_t w_sbo = wide ? 1024u : 2048u;
     const int ksteps = wide ? 4 : 8;
-    for (int ks = 0; ks < ksteps; ++ks) {
-      const uint32_t ah = tmem + a_hi + (ks >> 1) * a_grp2 + (ks & 1) * 8, al = ah + a_lo_off;
-      const uint64_t wh = smem_desc(w0 + ks * 256, 128, w_sbo), wl = smem_desc(w0 + PIECE_IMG + ks * 256, 128, w_sbo);
-      mma_ts(tmem + dcol, al, wh, idesc, (accumulate || ks > 0) ? 1u : 0u);
-      mma_ts(tmem + dcol, ah, wl, idesc, 1);
-      mma_ts(tmem + dcol, ah, wh, idesc, 1);
+    if (elect_one()) {
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const uint32_t ah = tmem + a_hi + (ks >> 1) * a_grp2 + (ks & 1) * 8, al = ah + a_lo_off;
+        const uint64_t wh = smem_desc(w0 + ks * 256, 128, w_sbo), wl = smem_desc(w0 + PIECE_IMG + ks * 256, 128, w_sbo);
+        mma_ts(tmem + dcol, al, wh, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        mma_ts(tmem + dcol, ah, wl, idesc, 1);
+        mma_ts(tmem + dcol, ah, wh, idesc, 1);
+      }
+      mma_commit(&bars.w_empty[s]);
     }
-    mma_commit(&bars.w_empty[s]);
+    __syncwarp();
     ++u_use;
     refill();
   };
@@ -193,7 +198,8 @@ __global__ void __launch_bounds__(NT, 1) gat_chain2_kernel(GatChain2Params p) {
                   for (int u = 0; u < 4; ++u) narrow_from_a(C_W + 64 * u); break;            // fc1 units 4-7
       default: for (int q4 = 0; q4 < 4; ++q4) wide_from_w(q4); break;                        // S_FC2B: x += fc2 half 1
     }
-    mma_commit(&bars.d_ready);
+    if (elect_one()) mma_commit(&bars.d_ready);
+    __syncwarp();
   };
   if (leader) refill();
 

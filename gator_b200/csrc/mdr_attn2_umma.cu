@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
 
   if (warp == 0) tmem_alloc(&tmem_slot, 512);
   if (tid == 32) {
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __
 
   if (warp == W_TMA) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       for (int i = 0; i < n_my; ++i) {
         const int s = i % STAGES;
         if (i >= STAGES) mbar_wait(&bars.kv_empty[s], ((i / STAGES) - 1) & 1);
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __
       const uint32_t sb = smem_u32(smem + s * ITEM);
       if (i == 0) {
         mbar_wait(&bars.kv_full[s], 0);
-        if (lane == 0) {
+        if (elect_one()) {
           for (int t = 0; t < 4; ++t) { issue_qk(sb, t, 0); mma_commit(&bars.s_full[t]); }
         }
         __syncwarp();
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __
         for (int t = 0; t < 4; ++t) {
           mbar_wait(&bars.p_full[t], ph_p);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             issue_pv(sb, t, j);
             if (!last) {
               issue_qk(sb, t, j + 1);

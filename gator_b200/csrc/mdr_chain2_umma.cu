@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
   __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
   __shared__ float2 xch_buf[2][128][2];               // LayerNorm partial statistics, [parity][row][column half]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = uniform_warp_idx(), lane = tid & 31;
   const bool final_pass = p.hd_out != nullptr;
   const bool has_so = p.att_in != nullptr;
   const int J = JT ? JT : p.J;
@@ -122,7 +122,8 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
   const int first_unit = final_pass ? 0 : (has_so ? 0 : 1);
   const int units_per_tile = final_pass ? 2 : 14 - first_unit;
 
-  // ---- leader (warp 0, lane 0): TMA producer + MMA issuer ----
+  // ---- leader warp 0: TMA producer + MMA issuer (executed by the whole warp, instructions issued by one elected lane, so
+  //      that descriptors and addresses stay in uniform registers) ----
   const int total_units = n_my * units_per_tile;
   int u_use = 0, u_load = 0;                         // weight units consumed by issued MMAs / requested from L2
   uint32_t ph_a = 0;
@@ -130,8 +131,10 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
     while (u_load < total_units && u_load - u_use < SLOTS) {
       const int s = u_load % SLOTS, k = u_load % units_per_tile;
       const int unit = final_pass ? k : kUnitOrder[first_unit + k];
-      mbar_arrive_expect_tx(&bars.w_full[s], UNIT_BYTES);
-      bulk_copy_g2s(smem + s * UNIT_BYTES, p.blob + (size_t)unit * UNIT_BYTES, UNIT_BYTES, &bars.w_full[s]);
+      if (elect_one()) {
+        mbar_arrive_expect_tx(&bars.w_full[s], UNIT_BYTES);
+        bulk_copy_g2s(smem + s * UNIT_BYTES, p.blob + (size_t)unit * UNIT_BYTES, UNIT_BYTES, &bars.w_full[s]);
+      }
       ++u_load;
     }
   };
@@ -142,14 +145,17 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
     const int s = u_use % SLOTS;
     mbar_wait(&bars.w_full[s], (u_use / SLOTS) & 1);
     const uint32_t w0 = smem_u32(smem + s * UNIT_BYTES);
+    if (elect_one()) {
 #pragma unroll
-    for (int ks = 0; ks < 4; ++ks) {
-      const uint32_t ah = tmem + a_hi + (ks >> 1) * a_grp2 + (ks & 1) * 8, al = ah + a_lo_off;
-      const uint64_t wh = smem_desc(w0 + ks * 256, 128, 1024), wl = smem_desc(w0 + UNIT_IMG + ks * 256, 128, 1024);
-      mma_ts(tmem + dcol, al, wh, idesc, (accumulate || ks > 0) ? 1u : 0u);
-      mma_ts(tmem + dcol, ah, wl, idesc, 1);
-      mma_ts(tmem + dcol, ah, wh, idesc, 1);
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint32_t ah = tmem + a_hi + (ks >> 1) * a_grp2 + (ks & 1) * 8, al = ah + a_lo_off;
+        const uint64_t wh = smem_desc(w0 + ks * 256, 128, 1024), wl = smem_desc(w0 + UNIT_IMG + ks * 256, 128, 1024);
+        mma_ts(tmem + dcol, al, wh, idesc, (accumulate || ks > 0) ? 1u : 0u);
+        mma_ts(tmem + dcol, ah, wl, idesc, 1);
+        mma_ts(tmem + dcol, ah, wh, idesc, 1);
+      }
     }
+    __syncwarp();
     ++u_use;
   };
   // A operand region C_A: hi k-step s at C_A + 8 s, lo 32 columns further
@@ -170,9 +176,10 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
       case S_QKV: from_a(C_X, false); from_a(C_W, false); from_a(C_W + 64, false); break;     // q | k | v into columns [0, 192)
       default: from_a(C_W, false); break;                                                     // S_HEAD
     }
-    mma_commit(&bars.d_ready);
+    if (elect_one()) mma_commit(&bars.d_ready);
+    __syncwarp();
   };
-  const bool leader = tid == 0;
+  const bool leader = warp == 0;
   if (leader) refill();
   {
     // ===== compute warps: two threads per row (one 32-column half each) =====
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
         write_a(v);
         submit(S_Q);
       }
-      if (leader && it + 1 < n_my) {
+      if (tid == 0 && it + 1 < n_my) {
         // the next tile's rows of x (and att) are 128 consecutive 256-byte rows: two bulk prefetches bring them from HBM
         // into L2 while this tile computes, so the loads at the top of the next iteration do not pay the DRAM latency
         const long long r0 = (long long)(tile + gridDim.x) * 128;

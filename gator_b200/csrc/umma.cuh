@@ -38,6 +38,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u)
       : "memory");
 }
+// One lane of a fully converged warp.  MMA / TMA / commit instructions are issued as  if (elect_one()) ...  from code the
+// whole warp executes: their operands then stay in uniform registers.  Issued from a divergent  if (tid == 0)  branch,
+// every operand of every tcgen05.mma goes through an ELECT + R2UR.BROADCAST sequence (~20 instructions per MMA, measured
+// as the limiter of the round-2 GAT kernel: one lane issues 612 MMAs per GATBlock and tile).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+// warp index as a value the compiler knows to be warp-uniform
+__device__ __forceinline__ int uniform_warp_idx() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 // non-blocking probe: has the phase with this parity completed?
 __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
