@@ -83,6 +83,8 @@ int gemm_f32(const float* A, int lda, const float* W, int ldw, float* C, int ldc
 // Wpacked_lo != null selects the 3-term split (a_hi w_hi + a_lo w_hi + a_hi w_lo): ~2^-17 relative error.
 int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, const void* Wpacked_lo, float* C, int ldc, int M,
                    int N, int K, const Epilogue& epi, cudaStream_t stream);
+int gemm_bf16_umma_splitk(const float* A, int lda, const void* Wpacked, const void* Wpacked_lo, float* C, int ldc, int M,
+                          int N, int K, const Epilogue& epi, float* ws, size_t ws_floats, cudaStream_t stream);
 void umma_weight_layout(int N, int K, int* BN, int* n_tiles, int* K_pad);
 
 // Wide-N variant for GATOR_PREC_BF16X3 (csrc/umma_gemm_wide.cu): persistent, warp-specialised, TMA-fed.  Wimg is the
@@ -109,24 +111,25 @@ inline int gemm(int precision, const float* A, int lda, const float* W, int ldw,
   return gemm_f32(A, lda, W, ldw, C, ldc, M, N, K, epi, stream);
 }
 
-// tcgen05 version of the MDR self-attention core: qkv (nb*431, 192) -> out (nb*431, 64)
-int launch_self_attn_umma(const float* qkv, float* out, int nb, bool split, cudaStream_t stream);
-
 // round-2 self-attention core (csrc/mdr_attn2_umma.cu): fp16 [Q | K | V] operand images per (sample, head) -> out (nb*431, 64)
 size_t self_attn2_image_bytes(int nb);
 int launch_qkv_image(const float* qkv, void* img, int nb, cudaStream_t stream);
 int launch_self_attn2(const void* img, float* out, int nb, cudaStream_t stream);
 
-// Fused row-wise chain of one MDR layer (csrc/mdr_chain_umma.cu): x3_prev/att_prev -> x3, qkv
-// hd_out != null selects the final pass (x3 + linears[3](att) -> MDR head projection -> hd (rows, 28))
-int launch_mdr_chain(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
-                     float* x3_out, float* qkv_out, float* hd_out, int nb, int J, bool split, cudaStream_t stream);
-
-// Round-2 version of the same chain (csrc/mdr_chain2_umma.cu): A operands and the residual stream in tensor memory,
-// warp-specialised, TMA-fed weight ring.  q|k|v leave as fp32 rows (qkv_out) and / or as the fp16 operand images of
+// Fused row-wise chain of one MDR layer (csrc/mdr_chain2_umma.cu): x3_prev / att_prev -> x3, q|k|v.  A operands and the
+// residual stream in tensor memory, TMA-fed weight ring, always the 3-term bf16 split.  hd_out != null selects the final pass
+// (x3 + linears[3](att) -> MDR head projection -> hd (rows, 28)).  q|k|v leave as fp32 rows (qkv_out) and / or as the fp16 operand images of
 // launch_self_attn2 (img_out); either may be null.
+struct ChainEmbed {                  // operands of the vertex embedding, for layer 0 with x_in == null
+  const float* vconst = nullptr;     // (431, 64) VF_CONST
+  const float* w3 = nullptr;         // (64, 3)   VF_W3
+  const int* vj = nullptr;           // (431)     nearest joint of each coarse vertex
+  const float* pose3d = nullptr;     // (nb, J, 3)
+  int metres = 0;
+};
 int launch_mdr_chain2(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
-                      float* x3_out, float* qkv_out, void* img_out, float* hd_out, int nb, int J, cudaStream_t stream);
+                      float* x3_out, float* qkv_out, void* img_out, float* hd_out, int nb, int J, cudaStream_t stream,
+                      const ChainEmbed* embed = nullptr);
 
 // All GATBlocks of the lifter in one kernel (csrc/gat_chain2_umma.cu; always the 3-term bf16 split).  blobs_dev / prm_dev
 // are DEVICE arrays of pointers: [depth] weight-piece blobs (34 x 32 KB) and [depth * 14] fp32 parameter arrays.

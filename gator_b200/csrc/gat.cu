@@ -21,7 +21,7 @@ gat_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ w1,
                  const float* __restrict__ gnw, const float* __restrict__ gnb, const float* __restrict__ w2t,
                  const float* __restrict__ b2, const float* __restrict__ posc, float* __restrict__ x, int J) {
   __shared__ float p[MAXJ * 2];
-  __shared__ float g[64][MAXJ + 1];
+  __shared__ __align__(16) float g[64][MAXJ];        // GELU(GroupNorm(.)) [channel][joint]; read as float4 over the joints (broadcast)
   const int b = blockIdx.x, tid = threadIdx.x;
   if (tid < 2 * J) p[tid] = pose2d[(size_t)b * J * 2 + tid];
   __syncthreads();
@@ -59,11 +59,19 @@ gat_embed_kernel(const float* __restrict__ pose2d, const float* __restrict__ w1,
     const float bb = b2[c];
 #pragma unroll
     for (int j = 0; j < MAXJ; ++j) acc[j] = 0.f;
+    const int j4n = (J + 3) >> 2;
+#pragma unroll 4
     for (int k = 0; k < 64; ++k) {
       const float w = __ldg(w2t + k * C + c);
+      const float4* gk = reinterpret_cast<const float4*>(g[k]);
 #pragma unroll
-      for (int j = 0; j < MAXJ; ++j)
-        if (j < J) acc[j] = fmaf(w, g[k][j], acc[j]);
+      for (int j4 = 0; j4 < MAXJ / 4; ++j4) {
+        if (j4 < j4n) {                     // (entries j >= J of a row are never written; their products are never stored)
+          const float4 t = gk[j4];
+          acc[4 * j4] = fmaf(w, t.x, acc[4 * j4]); acc[4 * j4 + 1] = fmaf(w, t.y, acc[4 * j4 + 1]);
+          acc[4 * j4 + 2] = fmaf(w, t.z, acc[4 * j4 + 2]); acc[4 * j4 + 3] = fmaf(w, t.w, acc[4 * j4 + 3]);
+        }
+      }
     }
     float* xo = x + (size_t)b * J * C;
 #pragma unroll
@@ -240,7 +248,8 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
   const int prec = a->precision;
   int cb = resolve_chunk(B, a->chunk, J);
   if (fused && a->chunk <= 0) {   // the fused kernel only needs x (128 floats / row): run the whole batch in one pass
-    const size_t cap = a->workspace_bytes / ((size_t)J * 128 * sizeof(float));
+    // (x plus the split-K partial sums of the lifter: at most 16 x 3J floats per sample)
+    const size_t cap = a->workspace_bytes / ((size_t)J * (128 + 16 * 3) * sizeof(float));
     cb = (size_t)B < cap ? B : (int)cap;
   }
   const size_t rows_max = (size_t)cb * J;
@@ -316,7 +325,14 @@ extern "C" int gator_gat_forward(const gator_gat_args* a, void* stream_) {
     GATOR_TRY(layernorm_rows(x, feat, G(GAT_NORM_W), G(GAT_NORM_B), M, C, 0, 1, stream));
     Epilogue e;
     e.bias = G(GAT_LIFT_B);
-    GATOR_TRY(gemm(prec, feat, J * C, G(GAT_LIFT_W), J * C, GB(GAT_LIFT_W), a->pose3d + (size_t)b0 * 3 * J, 3 * J, nb, 3 * J, J * C, e, stream));
+    // lifter: nb x 3J outputs over K = 128 J - a handful of 128-row tiles, so the K loop is split over blockIdx.z
+    // (partials in the `n` workspace region, which is idle here)
+    const PackedW lw = GB(GAT_LIFT_W);
+    if (prec != GATOR_PREC_FP32 && lw.hi && (prec == GATOR_PREC_BF16 || lw.lo))
+      GATOR_TRY(gemm_bf16_umma_splitk(feat, J * C, lw.hi, prec == GATOR_PREC_BF16X3 ? lw.lo : nullptr, a->pose3d + (size_t)b0 * 3 * J, 3 * J, nb,
+                                      3 * J, J * C, e, n, a->workspace_bytes / sizeof(float) - rows_max * 128, stream));
+    else
+      GATOR_TRY(gemm(prec, feat, J * C, G(GAT_LIFT_W), J * C, GB(GAT_LIFT_W), a->pose3d + (size_t)b0 * 3 * J, 3 * J, nb, 3 * J, J * C, e, stream));
   }
   return GATOR_OK;
 }

@@ -335,7 +335,7 @@ int resolve_chunk(int batch, int chunk) {
 }
 
 struct Ws {
-  float *x, *y, *q, *hid, *jf, *yj, *kv, *hd, *coarse, *a3, *a3img;
+  float *x, *y, *q, *hid, *img, *jf, *yj, *kv, *hd, *coarse, *a3, *a3img;
   size_t a3img_bytes, bytes;
 };
 
@@ -350,6 +350,7 @@ Ws carve(float* base, int nb, int J, int nsuper) {
   w.y = take(mv * E);
   w.q = take(mv * E);
   w.hid = take(mv * 256);
+  w.img = take(self_attn2_image_bytes(nb) / sizeof(float));   // fp16 [Q | K | V] operand images of the self-attention core
   const size_t msj = (size_t)nsuper * J;   // joint rows of a super-chunk: K|V of all 3 layers are computed once for it
   w.jf = take(msj * E);
   w.yj = take(msj * E);
@@ -397,9 +398,8 @@ int launch_self_attn(const float* qkv, float* out, int nb, cudaStream_t stream) 
 extern "C" int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_t precision, void* stream) {
   using namespace gator;
   GATOR_REQUIRE(qkv && out && batch >= 0, "gator_mdr_self_attention: bad argument");
-  GATOR_REQUIRE(precision >= GATOR_PREC_FP32 && precision <= GATOR_PREC_BF16X3, "gator_mdr_self_attention: bad precision %d", precision);
+  GATOR_REQUIRE(precision == GATOR_PREC_FP32, "gator_mdr_self_attention: fp32 FFMA core only; the tensor-core core is gator_mdr_self_attention_f16");
   if (batch == 0) return GATOR_OK;
-  if (precision != GATOR_PREC_FP32) return launch_self_attn_umma(qkv, out, batch, precision == GATOR_PREC_BF16X3, (cudaStream_t)stream);
   return launch_self_attn(qkv, out, batch, (cudaStream_t)stream);
 }
 
@@ -425,7 +425,6 @@ extern "C" int gator_mdr_layer_chain(const void* const* weights, int32_t layer, 
                                      float* qkv_out, void* image_out, int32_t batch, void* stream) {
   using namespace gator;
   GATOR_REQUIRE(weights && x_in && kv && x3_out && (qkv_out || image_out), "gator_mdr_layer_chain: null buffer");
-  GATOR_REQUIRE(!image_out || precision == GATOR_PREC_BF16X3, "gator_mdr_layer_chain: operand images need GATOR_PREC_BF16X3");
   GATOR_REQUIRE(layer >= 0 && layer < GATOR_MDR_LAYERS && num_joint >= 2 && num_joint <= MAXJ && batch >= 0,
                 "gator_mdr_layer_chain: bad argument");
   GATOR_REQUIRE(precision == GATOR_PREC_BF16 || precision == GATOR_PREC_BF16X3, "gator_mdr_layer_chain: tensor-core precisions only");
@@ -436,11 +435,8 @@ extern "C" int gator_mdr_layer_chain(const void* const* weights, int32_t layer, 
   GATOR_REQUIRE(weights[base + MDRL_CHAIN], "gator_mdr_layer_chain: CHAIN blob missing");
   const float* prm[11] = {static_cast<const float*>(weights[pbase + MDRL_SO_B]), W(MDRL_N1_W), W(MDRL_N1_B), W(MDRL_PROJ_B),
                           W(MDRL_N2_W), W(MDRL_N2_B), W(MDRL_FC1_B), W(MDRL_FC2_B), W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
-  if (precision == GATOR_PREC_BF16X3)
-    return launch_mdr_chain2(x_in, att_in, kv, weights[base + MDRL_CHAIN], prm, x3_out, qkv_out, image_out, nullptr, batch, num_joint,
-                             (cudaStream_t)stream);
-  return launch_mdr_chain(x_in, att_in, kv, weights[base + MDRL_CHAIN], prm, x3_out, qkv_out, nullptr, batch, num_joint, false,
-                          (cudaStream_t)stream);
+  return launch_mdr_chain2(x_in, att_in, kv, weights[base + MDRL_CHAIN], prm, x3_out, qkv_out, image_out, nullptr, batch, num_joint,
+                           (cudaStream_t)stream);
 }
 
 extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
@@ -471,7 +467,7 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   auto GB = [&](int s) { PackedW w; w.hi = a->weights_bf16 ? a->weights_bf16[s] : nullptr; w.lo = a->weights_bf16_lo ? a->weights_bf16_lo[s] : nullptr; return w; };
   // debug/ablation: `reserved` is a bit mask of the groups that take the bf16 kernels (0 = all):
   //   2 layer GEMMs, 4 self-attention, 8 head GEMM, 16 upsample_conv, 32 joint-feature GEMM
-  const int mask = (a->reserved & ~128) ? (a->reserved & ~128) : ~0;
+  const int mask = a->reserved ? a->reserved : ~0;
   auto P = [&](int bit) { return (a->precision != GATOR_PREC_FP32 && (mask & bit)) ? a->precision : (int)GATOR_PREC_FP32; };
   const int prec = P(2);
   const int cb = resolve_chunk(B, a->chunk);
@@ -505,17 +501,20 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
   for (int b0 = s0; b0 < s0 + ns; b0 += cb) {
     const int nb = (s0 + ns - b0 < cb) ? s0 + ns - b0 : cb;
     const int Mv = nb * V;
-    mdr_embed_kernel<<<nb, 256, 0, stream>>>(a->pose2d + (size_t)b0 * J * 2, a->pose3d + (size_t)b0 * J * 3,
-                                             G(MDR_JF_WPOSE), G(MDR_VF_CONST), G(MDR_VF_W3),
-                                             static_cast<const int*>(a->weights[MDR_VJ]), nullptr, w.x, J, a->pose3d_metres);
-    GATOR_TRY(check_launch("mdr_embed"));
     Epilogue e;
     auto KV = [&](int l) { return w.kv + ((size_t)l * ns + (b0 - s0)) * J * 2 * E; };   // this chunk's K|V rows of layer l
 
-    // bit 64 of the ablation mask disables the fused layer kernel
-    // bit 128 (development A/B switch): the round-1 fused kernels instead of the round-2 ones
-    const bool round1 = (a->reserved & 128) != 0;
-    const bool fused = a->precision != GATOR_PREC_FP32 && have_chain && (a->reserved & ~128) == 0;
+    // any bit of the ablation mask disables the fused layer kernel
+    const bool fused = a->precision != GATOR_PREC_FP32 && have_chain && a->reserved == 0;
+    ChainEmbed emb;                  // fused path: the vertex embedding is computed inside the layer-0 chain kernel
+    emb.vconst = G(MDR_VF_CONST); emb.w3 = G(MDR_VF_W3); emb.vj = static_cast<const int*>(a->weights[MDR_VJ]);
+    emb.pose3d = a->pose3d + (size_t)b0 * J * 3; emb.metres = a->pose3d_metres;
+    if (!fused) {
+      mdr_embed_kernel<<<nb, 256, 0, stream>>>(a->pose2d + (size_t)b0 * J * 2, a->pose3d + (size_t)b0 * J * 3,
+                                               G(MDR_JF_WPOSE), G(MDR_VF_CONST), G(MDR_VF_W3),
+                                               static_cast<const int*>(a->weights[MDR_VJ]), nullptr, w.x, J, a->pose3d_metres);
+      GATOR_TRY(check_launch("mdr_embed"));
+    }
     for (int l = 0; fused && l < GATOR_MDR_LAYERS; ++l) {
       const int base = MDR_NUM_GLOBAL + l * MDRL_NUM;
       auto W = [&](int s) { return static_cast<const float*>(a->weights[base + s]); };
@@ -526,23 +525,12 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
                               W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
       const float* prm2[11] = {W(MDRL_SO_B), G(MDR_HEAD_B), W(MDRL_N1_B), W(MDRL_PROJ_B), W(MDRL_N2_W), W(MDRL_N2_B),
                                W(MDRL_FC1_B), W(MDRL_FC2_B), W(MDRL_CLN_A), W(MDRL_CLN_B), W(MDRL_SQKV_B)};
-      if (a->precision == GATOR_PREC_BF16X3 && !round1) {
-        // round-2 kernels: chain (3-term bf16 split, operands in tensor memory) -> fp16 operand images (in w.hid) ->
-        // fp16 self-attention core
-        GATOR_TRY(launch_mdr_chain2(l == 0 ? w.x : w.q, l == 0 ? nullptr : w.y, KV(l), a->weights[base + MDRL_CHAIN], prm,
-                                    w.q, nullptr, w.hid, nullptr, nb, J, stream));
-        GATOR_TRY(launch_self_attn2(w.hid, w.y, nb, stream));
-        if (l == GATOR_MDR_LAYERS - 1)   // last layer: x = x3 + linears.3(att) + b and the head projection, fused
-          GATOR_TRY(launch_mdr_chain2(w.q, w.y, KV(l), a->weights[MDR_CHAIN_FINAL], prm2, nullptr, nullptr, nullptr, w.hd, nb, J, stream));
-        continue;
-      }
-      GATOR_TRY(launch_mdr_chain(l == 0 ? w.x : w.q, l == 0 ? nullptr : w.y, KV(l), a->weights[base + MDRL_CHAIN], prm,
-                                 w.q, w.hid, nullptr, nb, J, a->precision == GATOR_PREC_BF16X3, stream));
-      GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, a->precision == GATOR_PREC_BF16X3, stream));
-      if (l == GATOR_MDR_LAYERS - 1) {   // last layer: x = x3 + linears.3(att) + b and the head projection, fused
-        GATOR_TRY(launch_mdr_chain(w.q, w.y, KV(l), a->weights[MDR_CHAIN_FINAL], prm2, nullptr, nullptr, w.hd, nb, J,
-                                   a->precision == GATOR_PREC_BF16X3, stream));
-      }
+      // layer chain (3-term bf16 split GEMMs, operands in tensor memory) -> fp16 operand images -> fp16 self-attention core
+      GATOR_TRY(launch_mdr_chain2(l == 0 ? nullptr : w.q, l == 0 ? nullptr : w.y, KV(l), a->weights[base + MDRL_CHAIN], prm,
+                                  w.q, nullptr, w.img, nullptr, nb, J, stream, l == 0 ? &emb : nullptr));
+      GATOR_TRY(launch_self_attn2(w.img, w.y, nb, stream));
+      if (l == GATOR_MDR_LAYERS - 1)   // last layer: x = x3 + linears.3(att) + b and the head projection, fused
+        GATOR_TRY(launch_mdr_chain2(w.q, w.y, KV(l), a->weights[MDR_CHAIN_FINAL], prm2, nullptr, nullptr, nullptr, w.hd, nb, J, stream));
     }
     for (int l = 0; !fused && l < GATOR_MDR_LAYERS; ++l) {
       const int base = MDR_NUM_GLOBAL + l * MDRL_NUM;
@@ -573,8 +561,12 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
       e = Epilogue();
       e.bias = W(MDRL_SQKV_B);
       GATOR_TRY(gemm(prec, w.q, E, W(MDRL_SQKV_W), E, WB(MDRL_SQKV_W), w.hid, 3 * E, Mv, 3 * E, E, e, stream));
-      if (P(4) != GATOR_PREC_FP32) GATOR_TRY(launch_self_attn_umma(w.hid, w.y, nb, P(4) == GATOR_PREC_BF16X3, stream));
-      else GATOR_TRY(launch_self_attn(w.hid, w.y, nb, stream));
+      if (P(4) != GATOR_PREC_FP32) {
+        GATOR_TRY(launch_qkv_image(w.hid, w.img, nb, stream));
+        GATOR_TRY(launch_self_attn2(w.img, w.y, nb, stream));
+      } else {
+        GATOR_TRY(launch_self_attn(w.hid, w.y, nb, stream));
+      }
       e = Epilogue();
       e.bias = W(MDRL_SO_B);
       e.R = w.q;

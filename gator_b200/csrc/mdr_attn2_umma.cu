@@ -3,7 +3,7 @@
 //
 // Operands arrive PRE-PACKED: per (sample, head) one contiguous 82 944-byte record [Q | K | V], each a 432 x 32 fp16
 // image in the tcgen05 no-swizzle core-matrix layout  offset(row, d) = (row/8)*512 + (d/8)*128 + (row%8)*16 + (d%8)*2
-// (row 431 = zero padding), written by the layer-chain kernel's q|k|v epilogue (csrc/mdr_chain_umma.cu) or by
+// (row 431 = zero padding), written by the layer-chain kernel's q|k|v epilogue (csrc/mdr_chain2_umma.cu) or by
 // `qkv_image_kernel` below.  Q and K are K-major operands; the same image of V is the MN-major B operand of P V, so no
 // transpose of V exists anywhere.
 //

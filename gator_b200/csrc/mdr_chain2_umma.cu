@@ -9,7 +9,8 @@
 //   x3  = a2 (x - mean) / (std_unbiased + 1e-6) + b2                (vanilla_transformer_encoder.py:31-34)
 //   q|k|v = x3 [Wq;Wk;Wv]^T + b                                     (:88-90)   -> x3 (fp32) and fp16 operand images
 //
-// What changed against the round-1 kernel (csrc/mdr_chain_umma.cu), which spent two thirds of its cycles with no eligible warp:
+// What changed against the round-1 kernel (A images in shared memory, 18 block-wide MMA round trips per tile), which spent
+// two thirds of its cycles with no eligible warp:
 //  * every A operand lives in TENSOR MEMORY (tcgen05.mma [d], [a], b-desc): the row owner writes its bf16 hi / lo halves
 //    with tcgen05.st into its own lane - no shared-memory A images, no fence.proxy.async, no bank conflicts;
 //  * the residual stream x lives in tensor memory too and IS the accumulator of the three residual GEMMs
@@ -68,6 +69,9 @@ struct Chain2Params {
   int J;
   long long rows_total;   // nb * 431
   int ntiles;
+  // layer 0 with x_in == null: the vertex embedding (MDR.py:127-134 with the constants folded) is computed on the fly,
+  //   x[b, v, :] = VF_CONST[v, :] + W_v[:, 3:6] . pose3d[b, vj[v]] (/ 1000 when pose3d is in millimetres)
+  ChainEmbed emb;
 };
 
 struct Bars {
@@ -259,12 +263,27 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
         cp_async_commit();
       }
       // ---- x -> tensor memory; layers 1, 2 / final: A = att, x += att Wo^T on the tensor core ----
-      {
+      if (p.x_in) {
         const float4* src = reinterpret_cast<const float4*>(p.x_in + grow * E + c0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const float4 t = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
           x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+        }
+      } else {
+        const float* pj = p.emb.pose3d + ((size_t)b * J + __ldg(p.emb.vj + vert)) * 3;
+        float px = __ldg(pj), py = __ldg(pj + 1), pz = __ldg(pj + 2);
+        if (!p.emb.metres) { px = px / 1000.0f; py = py / 1000.0f; pz = pz / 1000.0f; }
+        const float4* vc = reinterpret_cast<const float4*>(p.emb.vconst + (size_t)vert * E + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = __ldg(vc + i);
+          const float r4[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float* w = p.emb.w3 + (c0 + 4 * i + u) * 3;
+            x[4 * i + u] = valid ? r4[u] + fmaf(__ldg(w), px, fmaf(__ldg(w + 1), py, __ldg(w + 2) * pz)) : 0.f;
+          }
         }
       }
       auto store_x = [&]() {                         // x (registers) -> my half of the accumulator columns
@@ -331,7 +350,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
         const long long r0 = (long long)(tile + gridDim.x) * 128;
         const long long nr = (p.rows_total - r0 < 128) ? p.rows_total - r0 : 128;
         if (nr > 0) {
-          bulk_prefetch_l2(p.x_in + r0 * E, (uint32_t)(nr * E * 4));
+          if (p.x_in) bulk_prefetch_l2(p.x_in + r0 * E, (uint32_t)(nr * E * 4));
           if (has_so) bulk_prefetch_l2(p.att_in + r0 * E, (uint32_t)(nr * E * 4));
         }
       }
@@ -500,7 +519,9 @@ constexpr int smem_bytes(int J) { return SLOTS * UNIT_BYTES + J * 128 * 4; }
 
 // x_in / att_in / kv / outputs as in Chain2Params; prm = 11 device pointers (so_b of the PREVIOUS layer first).
 int launch_mdr_chain2(const float* x_in, const float* att_in, const float* kv, const void* blob, const float* const* prm,
-                      float* x3_out, float* qkv_out, void* img_out, float* hd_out, int nb, int J, cudaStream_t stream) {
+                      float* x3_out, float* qkv_out, void* img_out, float* hd_out, int nb, int J, cudaStream_t stream,
+                      const ChainEmbed* embed) {
+  GATOR_REQUIRE(x_in || (embed && !att_in && !hd_out), "mdr_chain2: x_in may only be null for layer 0 with the embedding operands given");
   static DeviceOnce attr_once;
   static int num_sms[64];
   int dev = 0;
@@ -515,6 +536,7 @@ int launch_mdr_chain2(const float* x_in, const float* att_in, const float* kv, c
   p.x_in = x_in; p.att_in = att_in; p.kv = kv; p.blob = static_cast<const uint8_t*>(blob);
   for (int i = 0; i < 11; ++i) p.prm[i] = prm[i];
   p.x3_out = x3_out; p.qkv_out = qkv_out; p.img_out = static_cast<uint8_t*>(img_out); p.hd_out = hd_out; p.J = J;
+  p.emb = embed ? *embed : ChainEmbed{};
   p.rows_total = (long long)nb * V;
   p.ntiles = (int)((p.rows_total + 127) / 128);
   const int sms = num_sms[dev & 63] > 0 ? num_sms[dev & 63] : 148;

@@ -42,6 +42,8 @@ struct UmmaGemmParams {
                                       // several CTAs fit on an SM and overlap each other's staging / epilogue
   Epilogue epi;
   int vec;
+  int ksplit;                         // > 1: blockIdx.z takes a contiguous share of the K blocks and writes raw partial sums
+  size_t part_stride;                 //      to C + z * part_stride (the epilogue is applied by splitk_reduce_kernel)
 };
 
 __global__ void __launch_bounds__(256)
@@ -76,11 +78,15 @@ umma_gemm_kernel(UmmaGemmParams p) {
   const uint32_t tmem = tmem_slot;
   const uint32_t idesc = idesc_bf16(BM, BN);
 
-  const int nk = p.K_pad / BKE;
+  const int nk_all = p.K_pad / BKE;
+  const int kb_begin = p.ksplit > 1 ? (int)((long long)nk_all * blockIdx.z / p.ksplit) : 0;
+  const int kb_end = p.ksplit > 1 ? (int)((long long)nk_all * (blockIdx.z + 1) / p.ksplit) : nk_all;
+  const int nk = kb_end - kb_begin;
   const int kgroups = p.K_pad / 8;             // 16-byte chunks per packed W row-group
-  for (int kb = 0; kb < nk; ++kb) {
-    const int buf = kb % stages;
-    if (kb >= stages) mbar_wait(&mbar[buf], ((kb / stages) - 1) & 1);
+  for (int kbi = 0; kbi < nk; ++kbi) {
+    const int kb = kb_begin + kbi;
+    const int buf = kbi % stages;
+    if (kbi >= stages) mbar_wait(&mbar[buf], ((kbi / stages) - 1) & 1);
     // ---- stage A: 128 rows x 64 k, fp32 -> bf16, chunk c = (rg, kc, r) stored linearly ----
     {
       uint4* dst = reinterpret_cast<uint4*>(sA + buf * a_stride);
@@ -127,11 +133,11 @@ umma_gemm_kernel(UmmaGemmParams p) {
         if (split) {   // a*w ~= a_lo*w_hi + a_hi*w_lo + a_hi*w_hi  (the dropped a_lo*w_lo term is ~2^-18 relative)
           const uint64_t adl = smem_desc(a0 + A_STAGE + ks * 256, 128, BKE * 16);
           const uint64_t bdl = smem_desc(b0 + w_stage + ks * 256, 128, BKE * 16);
-          mma_bf16(tmem, adl, bd, idesc, (kb | ks) != 0);
+          mma_bf16(tmem, adl, bd, idesc, (kbi | ks) != 0);
           mma_bf16(tmem, ad, bdl, idesc, 1);
           mma_bf16(tmem, ad, bd, idesc, 1);
         } else {
-          mma_bf16(tmem, ad, bd, idesc, (kb | ks) != 0);
+          mma_bf16(tmem, ad, bd, idesc, (kbi | ks) != 0);
         }
       }
       mma_commit(&mbar[buf]);
@@ -143,7 +149,8 @@ umma_gemm_kernel(UmmaGemmParams p) {
 
   // ---- epilogue ----
   const int slabs = (BN + 31) / 32;
-  const Epilogue& e = p.epi;
+  const Epilogue e = p.ksplit > 1 ? Epilogue() : p.epi;
+  float* const Cout = p.C + (p.ksplit > 1 ? blockIdx.z * p.part_stride : 0);
   for (int s0 = 0; s0 < slabs; s0 += 2) {
     const int my = s0 + (warp >> 2);
     if (my < slabs) {
@@ -171,7 +178,7 @@ umma_gemm_kernel(UmmaGemmParams p) {
           const int b = m / 3, tt = m - b * 3;
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            if (n + j < p.N) p.C[((size_t)b * p.N + (n + j)) * 3 + tt] = v[j] + __ldg(e.bias_rows + (n + j) * 3 + tt);
+            if (n + j < p.N) Cout[((size_t)b * p.N + (n + j)) * 3 + tt] = v[j] + __ldg(e.bias_rows + (n + j) * 3 + tt);
           continue;
         }
         const float* brow = e.bias_rows ? e.bias_rows + (size_t)(m % e.bias_period) * p.N : nullptr;
@@ -183,7 +190,7 @@ umma_gemm_kernel(UmmaGemmParams p) {
             for (int j = 0; j < 4; ++j) v[j] = gelu_erf(v[j]);
           }
           if (e.R) { const float4 rr = *reinterpret_cast<const float4*>(e.R + (size_t)m * e.ldr + n); v[0] += rr.x; v[1] += rr.y; v[2] += rr.z; v[3] += rr.w; }
-          *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(Cout + (size_t)m * p.ldc + n) = make_float4(v[0], v[1], v[2], v[3]);
         } else {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -193,7 +200,7 @@ umma_gemm_kernel(UmmaGemmParams p) {
             if (brow) x += __ldg(brow + n + j);
             if (e.act == 1) x = gelu_erf(x);
             if (e.R) x += e.R[(size_t)m * e.ldr + n + j];
-            p.C[(size_t)m * p.ldc + n + j] = x;
+            Cout[(size_t)m * p.ldc + n + j] = x;
           }
         }
       }
@@ -207,10 +214,33 @@ umma_gemm_kernel(UmmaGemmParams p) {
 
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) == 0; }
 
+// C[m,n] = epi(sum_z part[z][m][n]) in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ part, size_t part_stride, int ksplit, float* __restrict__ C,
+                                                            int ldc, int M, int N, Epilogue e) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = (int)(i / N), n = (int)(i - (long long)m * N);
+  float x = 0.f;
+  for (int z = 0; z < ksplit; ++z) x += part[z * part_stride + (size_t)m * ldc + n];
+  if (e.bias) x += __ldg(e.bias + n);
+  if (e.bias_rows) x += __ldg(e.bias_rows + (size_t)(m % e.bias_period) * N + n);
+  if (e.act == 1) x = gelu_erf(x);
+  if (e.R) x += e.R[(size_t)m * e.ldr + n];
+  C[(size_t)m * ldc + n] = x;
+}
+
 }  // namespace
 
 int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, const void* Wpacked_lo, float* C, int ldc, int M,
                    int N, int K, const Epilogue& epi, cudaStream_t stream) {
+  return gemm_bf16_umma_splitk(A, lda, Wpacked, Wpacked_lo, C, ldc, M, N, K, epi, nullptr, 0, stream);
+}
+
+// Same product for long K and few output columns (the lifter: K = 128 J, N = 3 J): the K blocks are shared out over
+// blockIdx.z (8 ways) and the partial sums (ws: 8 x M x ldc floats) are added in a fixed order by a second small kernel -
+// a 4096-row batch is only 32 row tiles, which left 116 of the 148 SMs idle for the length of a 38-block K loop.
+int gemm_bf16_umma_splitk(const float* A, int lda, const void* Wpacked, const void* Wpacked_lo, float* C, int ldc, int M,
+                          int N, int K, const Epilogue& epi, float* ws, size_t ws_floats, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return GATOR_OK;
   GATOR_REQUIRE(A && Wpacked && C, "gemm_bf16_umma: null operand");
   GATOR_REQUIRE(K > 0 && K % 4 == 0 && lda % 4 == 0, "gemm_bf16_umma: K=%d lda=%d must be multiples of 4", K, lda);
@@ -234,9 +264,25 @@ int gemm_bf16_umma(const float* A, int lda, const void* Wpacked, const void* Wpa
   GATOR_TRY(attr_once.run("umma_gemm", [&](int) -> cudaError_t {
     return cudaFuncSetAttribute(umma_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * (2 * A_STAGE + 2 * 128 * BKE * 2));
   }));
-  dim3 grid(ceil_div(M, BM), n_tiles);
+  // The split depends on K only - never on M - so that a sample's result does not depend on the batch it is computed in
+  // (the summation order over K is part of the result's last bits).
+  const int nkb = p.K_pad / BKE;
+  int ksplit = 1;
+  if (ws && !epi.conv3 && nkb >= 16) {
+    ksplit = nkb / 4 < 8 ? nkb / 4 : 8;
+    GATOR_REQUIRE((size_t)ksplit * M * ldc <= ws_floats, "gemm_bf16_umma_splitk: workspace %zu < %zu floats", ws_floats, (size_t)ksplit * M * ldc);
+  }
+  p.ksplit = ksplit;
+  p.part_stride = (size_t)M * ldc;
+  if (ksplit > 1) p.C = ws;
+  dim3 grid(ceil_div(M, BM), n_tiles, ksplit);
   umma_gemm_kernel<<<grid, 256, smem, stream>>>(p);
-  return check_launch("umma_gemm");
+  GATOR_TRY(check_launch("umma_gemm"));
+  if (ksplit > 1) {
+    splitk_reduce_kernel<<<(unsigned)(((long long)M * N + 255) / 256), 256, 0, stream>>>(ws, p.part_stride, ksplit, C, ldc, M, N, epi);
+    return check_launch("splitk_reduce");
+  }
+  return GATOR_OK;
 }
 
 }  // namespace gator

@@ -175,7 +175,7 @@ class GAT(nn.Module):
         self._ws = None
         self.precision = _lib.PREC_FP32
         self.chunk = 0
-        self.fused = True       # tensor-core precisions: all GATBlocks in one kernel (csrc/gat_chain_umma.cu)
+        self.fused = True       # tensor-core precisions: all GATBlocks in one kernel (csrc/gat_chain2_umma.cu)
         self.register_load_state_dict_post_hook(_invalidate_hook)
         if pretrained:
             self._load_pretrained_model()
@@ -243,7 +243,7 @@ class GAT(nn.Module):
                 'FC2_W': f(blk.mlp.fc2.weight), 'FC2_B': f(blk.mlp.fc2.bias),
             }
             block_dicts.append(b)
-        # fused-blocks kernel (csrc/gat_chain_umma.cu): 36 weight pieces + 14 parameter arrays per block
+        # fused-blocks kernel (csrc/gat_chain2_umma.cu): 34 weight pieces + 14 parameter arrays per block
         keep = []
         blobs, prms = [], []
         for b in block_dicts:

@@ -205,7 +205,7 @@ class MDR(nn.Module):
                 'SQKV_B': f(torch.cat([sa.linears[i].bias for i in range(3)], 0)),
                 'SO_W': f(sa.linears[3].weight), 'SO_B': f(sa.linears[3].bias),
             }
-            # 64x64 units of the fused layer kernel (csrc/mdr_chain_umma.cu), each as [hi | lo] tcgen05 images
+            # 64x64 units of the fused layer kernel (csrc/mdr_chain2_umma.cu), each as [hi | lo] tcgen05 images
             fc1, fc2 = f(enc.mlp.fc1.weight), f(enc.mlp.fc2.weight)
             units = [prev_so if prev_so is not None else torch.zeros(E, E, device=dev), l['WQ'], l['PROJ_W']]
             units += [fc1[64 * q:64 * q + 64] for q in range(4)] + [fc2[:, 64 * q:64 * q + 64] for q in range(4)]

@@ -201,8 +201,8 @@ typedef struct {
 const char* gator_mdr_slot_name(int slot);
 size_t gator_mdr_workspace_bytes(int32_t batch, int32_t num_joint, int32_t chunk);
 int gator_mdr_forward(const gator_mdr_args* a, void* stream);
-/* The dominant kernel on its own, for roofline measurement: 2-head 431x431 self-attention core
- * (vanilla_transformer_encoder.py:36-46) over qkv (B*431, 192) -> out (B*431, 64). */
+/* The 2-head 431x431 self-attention core (vanilla_transformer_encoder.py:36-46) on its own, fp32 FFMA kernel
+ * (precision must be GATOR_PREC_FP32): qkv (B*431, 192) -> out (B*431, 64). */
 int gator_mdr_self_attention(const float* qkv, float* out, int32_t batch, int32_t precision, void* stream);
 /* Round-2 core of the same op: fp16 operands (fp32 accumulate), persistent warp-specialised tcgen05 kernel fed by TMA
  * bulk copies (csrc/mdr_attn2_umma.cu).  `image` is caller workspace of gator_mdr_self_attention_image_bytes(batch)
@@ -212,13 +212,12 @@ size_t gator_mdr_self_attention_image_bytes(int32_t batch);
 int gator_mdr_self_attention_f16(const float* qkv, void* image, float* out, int32_t batch, void* stream);
 /* The core alone on already packed operand images (what gator_mdr_forward runs; roofline measurement). */
 int gator_mdr_self_attention_core(const void* image, float* out, int32_t batch, void* stream);
-/* The fused row-wise chain of MDR layer `layer` (0..2) on its own (tensor-core precisions only; GATOR_PREC_BF16X3:
- * csrc/mdr_chain2_umma.cu, GATOR_PREC_BF16: csrc/mdr_chain_umma.cu): everything of MDR.py:140-153 between two
- * self-attention cores.  `weights` is the gator_mdr_args table; x_in (B*431,64) = embedded vertices (layer 0) or the
+/* The fused row-wise chain of MDR layer `layer` (0..2) on its own (csrc/mdr_chain2_umma.cu; tensor-core precisions
+ * only, always the 3-term bf16 split): everything of MDR.py:140-153 between two self-attention cores.  `weights` is the gator_mdr_args table; x_in (B*431,64) = embedded vertices (layer 0) or the
  * previous layer's x3; att_in (B*431,64) = previous self-attention output (NULL for layer 0); kv (B*J,128) = this
  * layer's cross-attention K|V; outputs x3_out (B*431,64) and q|k|v as fp32 rows qkv_out (B*431,192) and / or as the
- * fp16 operand images image_out (gator_mdr_self_attention_image_bytes(B) bytes; GATOR_PREC_BF16X3 only); either of
- * the two q|k|v outputs may be NULL, not both. */
+ * fp16 operand images image_out (gator_mdr_self_attention_image_bytes(B) bytes); either of the two q|k|v outputs may
+ * be NULL, not both. */
 int gator_mdr_layer_chain(const void* const* weights, int32_t layer, int32_t num_joint, int32_t precision,
                           const float* x_in, const float* att_in, const float* kv, float* x3_out, float* qkv_out,
                           void* image_out, int32_t batch, void* stream);

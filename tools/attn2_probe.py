@@ -1,5 +1,4 @@
-"""GPU probe: round-2 fp16 self-attention core (gator_mdr_self_attention_f16) against fp64, and its timing beside the
-round-1 kernels."""
+"""GPU probe: fp16 self-attention core (gator_mdr_self_attention_f16) against fp64, and its timing with / without the image pack."""
 import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -45,8 +44,7 @@ for nbt in (296, 4096):
         for _ in range(n): fn()
         e1.record(); torch.cuda.synchronize()
         return e0.elapsed_time(e1) / n * 1e3
-    for prec in (1, 2):
-        us = t(lambda: L.gator_mdr_self_attention(qkv.data_ptr(), o.data_ptr(), nbt, prec, _lib.stream_ptr()))
-        print(f'  nb={nbt} round-1 kernel prec={prec}: {us:.1f} us')
+    us = t(lambda: L.gator_mdr_self_attention_core(img.data_ptr(), o.data_ptr(), nbt, _lib.stream_ptr()))
+    print(f'  nb={nbt} f16 core alone: {us:.1f} us  ({nbt*47.6e6/us/1e6:.1f} TFLOP/s algorithmic)')
     us = t(lambda: L.gator_mdr_self_attention_f16(qkv.data_ptr(), img.data_ptr(), o.data_ptr(), nbt, _lib.stream_ptr()))
     print(f'  nb={nbt} f16 kernel incl. image pack: {us:.1f} us  ({nbt*47.6e6/us/1e6:.1f} TFLOP/s algorithmic)')
