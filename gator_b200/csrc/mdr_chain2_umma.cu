@@ -17,7 +17,7 @@
 //    (linears[3], proj, fc2 accumulate straight into it; their biases are added when x is next read);
 //  * GELU(fc1) is converted IN PLACE (32 fp32 columns -> 16 hi + 16 lo columns) and read back as the A operand of fc2;
 //  * 7 MMA round trips per tile instead of 18 (fc1 / fc2 in halves of 128 columns, q|k|v as one group);
-//  * the 14 weight units (16 KB each) stream through a 6-slot ring with cp.async.bulk + mbarriers, issued a whole compute
+//  * the 14 weight units (16 KB each) stream through a 5-slot ring with cp.async.bulk + mbarriers, issued a whole compute
 //    phase ahead; 8 warps own the rows (two threads per row) and lane 0 of warp 0 doubles as MMA issuer and TMA producer
 //    (256 threads x 128 registers x 2 CTAs = the whole register file; a 9th warp would be allocated as four); the only
 //    block-wide synchronisation in the tile loop is the mbarrier pair around each MMA group; persistent CTAs, two per SM
@@ -40,7 +40,7 @@ constexpr int DK = 32;
 constexpr int MAXJ = 32;
 constexpr int UNIT_IMG = 64 * 64 * 2;          // 8 KB: one 64x64 bf16 image
 constexpr int UNIT_BYTES = 2 * UNIT_IMG;       // hi | lo
-constexpr int SLOTS = 6;
+constexpr int SLOTS = 5;
 constexpr int NCOMP = 8;                       // warps: all of them own rows
 constexpr int NT = NCOMP * 32;
 constexpr int QKV_IMG = VP * DK * 2;           // one fp16 operand image of the self-attention kernel
@@ -100,7 +100,7 @@ __device__ __forceinline__ void split32(const float* v, uint32_t* hi, uint32_t* 
 
 template <int JT>
 __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
-  extern __shared__ __align__(1024) uint8_t smem[];   // [SLOTS][UNIT_BYTES] weight ring | K|V [J][128] fp32
+  extern __shared__ __align__(1024) uint8_t smem[];   // [SLOTS][UNIT_BYTES] weight ring | K|V [2 samples][J][128] fp32
   __shared__ Bars bars;
   __shared__ uint32_t tmem_slot;
   __shared__ float2 xch_buf[2][128][2];               // LayerNorm partial statistics, [parity][row][column half]
@@ -249,17 +249,19 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
       const int tile = blockIdx.x + it * gridDim.x;
       const long long flat = (long long)tile * 128 + row;
       const bool valid = flat < p.rows_total;
-      const size_t grow = valid ? (size_t)flat : 0;
+      const int b_first = (int)(((long long)tile * 128) / V);
+      const size_t grow = valid ? (size_t)flat : (size_t)tile * 128;   // rows past the end behave like the tile's first row (never stored)
       const int b = (int)(grow / V);
       const int vert = (int)(grow - (size_t)b * V);
-      const int b_first = (int)(((long long)tile * 128) / V);
       float x[32], v[32];
-      // ---- K|V of the tile's first sample -> shared memory (rows of the next sample read theirs through L1) ----
+      // ---- K|V of the (at most two) samples the tile's rows belong to -> shared memory ----
       if (!final_pass) {
         named_sync(1, NCOMP * 32);                   // everyone is done with the previous tile's K|V
+        const long long nb_total = p.rows_total / V;
+        const int ns = (b_first + 1 < nb_total) ? 2 : 1;
         const float* src = p.kv + (size_t)b_first * J * 128;
         const uint32_t dst = smem_u32(skv);
-        for (int i = tid; i < J * 32; i += NCOMP * 32) cp_async16(dst + i * 16, src + i * 4);
+        for (int i = tid; i < ns * J * 32; i += NCOMP * 32) cp_async16(dst + i * 16, src + i * 4);
         cp_async_commit();
       }
       // ---- x -> tensor memory; layers 1, 2 / final: A = att, x += att Wo^T on the tensor core ----
@@ -362,10 +364,8 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
         float q[DK];
         ld32f(tmem + lane_addr + C_W + c0, q);
         constexpr int JU = JT ? JT : MAXJ;
-        // rows of the tile's first sample read K|V from shared memory, the others (a tile spans at most two samples) from
-        // global memory through L1 - one code path through a generic pointer (two copies of this unrolled block were
-        // 40 % of the kernel's 170 KB of code, which thrashed the instruction cache)
-        const float* kvb = (b == b_first) ? skv : p.kv + (size_t)b * J * 128;
+        // a tile of 128 consecutive rows spans at most two samples (431 rows each): both K|V blocks are in shared memory
+        const float* kvb = skv + (b - b_first) * J * 128;
         {
           float s[JU];
           float mx = -INFINITY;
@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-constexpr int smem_bytes(int J) { return SLOTS * UNIT_BYTES + J * 128 * 4; }
+constexpr int smem_bytes(int J) { return SLOTS * UNIT_BYTES + 2 * J * 128 * 4; }
 
 }  // namespace
 
