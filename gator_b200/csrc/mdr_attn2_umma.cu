@@ -14,10 +14,11 @@
 //                [96,128).  Tile 3 holds rows 384..430 only, so its warps 14 and 15 have no row at all; they are
 //   warp 14      the MMA issuer (one lane), and
 //   warp 15      the TMA producer: one bulk copy per image into a 2-stage ring (the next (sample, head) loads while this one runs).
-// Per key block j (96, 96, 96, 96, 48 keys) and tile t:   S = Q_t K_j^T  ->  warpgroup t: block max, P = exp2(S c - m) as
-// fp16 written IN PLACE over S with tcgen05.st (P is the tensor-memory A operand of the next MMA - it never touches shared
-// memory)  ->  O_t += P V_j, S_t = Q_t K_{j+1}^T.   The four tiles are at different points of this loop, so the MMA
-// latency of one tile is covered by the exp work of the other three; there is no block-wide barrier in the loop.
+// Per key block j (9 blocks of 48 keys) and tile t:   S = Q_t K_j^T  ->  warpgroup t: block max, P = exp2(S c - m) as fp16
+// written IN PLACE over S with tcgen05.st (P is the tensor-memory A operand of the next MMA - it never touches shared
+// memory)  ->  O_t += P V_j.   S is double-buffered per tile (S0 48 | S1 48 | O 32 columns): Q_t K_{j+1}^T is computed
+// while the warpgroup works on block j, and P V_j is issued asynchronously behind it, so a softmax warp only ever waits for
+// an MMA that was issued a whole block earlier; there is no block-wide barrier in the loop.
 // Softmax is the online form with a lazily updated running maximum: the row maximum only moves (and O is rescaled, in
 // tensor memory) when a block exceeds it by more than 2^8 - fp16 holds P <= 2^8 exactly as well as P <= 1.
 // fp16 (11-bit significand) instead of the round-1 3-term bf16 split: 2.2e-5 m end-to-end vertex error (CPU emulation,
@@ -40,65 +41,44 @@ constexpr int E = 64;
 constexpr int IMG = VP * DK * 2;          // 27 648 B per image
 constexpr int ITEM = 3 * IMG;             // 82 944 B per (sample, head)
 constexpr int STAGES = 2;
-constexpr int KB = 96;                    // keys per block
-constexpr int NBLK = 5;                   // 4 x 96 + 48
+constexpr int KB = 48;                    // keys per block
+constexpr int NBLK = 9;                   // 9 x 48 = 432
 constexpr int NT = 512;                   // 16 warps
 constexpr int W_MMA = 14, W_TMA = 15;     // the two row-less warps of query tile 3
-constexpr int SMEM = STAGES * ITEM;       // 165 888 B dynamic
+constexpr int OST_WARP = 32 * DK * 4;      // 4 KB per softmax warp: O rows staged for coalesced stores
+constexpr int SMEM = STAGES * ITEM + 14 * OST_WARP;   // 165 888 + 57 344 B dynamic
 constexpr float kScaleLog2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32)
 constexpr float kLazy = 8.0f;             // the running maximum moves only when exceeded by 2^8
 
 struct Bars {
   uint64_t kv_full[STAGES], kv_empty[STAGES];
-  uint64_t s_full[4], p_full[4], o_full[4];
+  uint64_t s_full[4][2], p_full[4][2], pv_done[4], o_full[4];
 };
 
-// One key block of one query row.  NK = 96 (full block) or 48 (last block: 47 keys + the zero pad row of K).
-// s_addr: this thread's lane + first column of the S block; o_addr: lane + first column of O.
-template <int NK>
-__device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t o_addr, bool first, bool valid, float& m, float& l) {
-  constexpr int NVAL = NK == KB ? KB : NK - 1;   // the last column of the last block is the pad key
-  uint32_t a[32], b[32];
-  // ---- pass A: block maximum (software-pipelined tensor-memory loads) ----
-  float mb;
+// One key block (48 keys) of one query row, single pass over the scores (48 registers).  LAST: the block's last column is
+// the zero pad row of K.  s_addr: this thread's lane + first column of the S buffer; o_addr: lane + first column of O.
+template <bool LAST>
+__device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t o_addr, bool first, bool valid, float& m, float& l,
+                                              uint64_t* pv_done, uint32_t pv_parity) {
+  uint32_t a[32], b[16];
   tmem_ld32_async(s_addr, a);
+  tmem_ld16_async(s_addr + 32, b);
   tmem_ld_wait_dep32(a);
-  if (NK == KB) {
-    tmem_ld32_async(s_addr + 32, b);
-    float m0 = -INFINITY, m1 = -INFINITY;
+  float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      m0 = fmax3(m0, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
-      m1 = fmax3(m1, __uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
-    }
-    tmem_ld_wait_dep32(b);
-    tmem_ld32_async(s_addr + 64, a);
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      m0 = fmax3(m0, __uint_as_float(b[i]), __uint_as_float(b[i + 1]));
-      m1 = fmax3(m1, __uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
-    }
-    tmem_ld_wait_dep32(a);
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      m0 = fmax3(m0, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
-      m1 = fmax3(m1, __uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
-    }
-    mb = fmaxf(m0, m1);
-  } else {
-    tmem_ld16_async(s_addr + 32, b);
-    float m0 = -INFINITY, m1 = -INFINITY;
-#pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      m0 = fmax3(m0, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
-      m1 = fmax3(m1, __uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
-    }
-    tmem_ld_wait_dep16(b);
-#pragma unroll
-    for (int i = 0; i < 15; i += 3) m0 = fmax3(m0, __uint_as_float(b[i]), __uint_as_float(b[i + 1])), m1 = fmaxf(m1, __uint_as_float(b[i + 2]));
-    mb = fmaxf(m0, m1);
+  for (int i = 0; i < 32; i += 4) {
+    m0 = fmax3(m0, __uint_as_float(a[i]), __uint_as_float(a[i + 1]));
+    m1 = fmax3(m1, __uint_as_float(a[i + 2]), __uint_as_float(a[i + 3]));
   }
-  mb *= kScaleLog2;
+  tmem_ld_wait_dep16(b);
+#pragma unroll
+  for (int i = 0; i < 12; i += 4) {
+    m0 = fmax3(m0, __uint_as_float(b[i]), __uint_as_float(b[i + 1]));
+    m1 = fmax3(m1, __uint_as_float(b[i + 2]), __uint_as_float(b[i + 3]));
+  }
+  m0 = fmax3(m0, __uint_as_float(b[12]), __uint_as_float(b[13]));
+  m1 = LAST ? fmaxf(m1, __uint_as_float(b[14])) : fmax3(m1, __uint_as_float(b[14]), __uint_as_float(b[15]));
+  const float mb = fmaxf(m0, m1) * kScaleLog2;
   // ---- running maximum (lazy) and, rarely, the rescale of O in tensor memory ----
   if (first) {
     m = mb;
@@ -107,52 +87,35 @@ __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t o_addr, 
     if (__ballot_sync(0xffffffffu, need)) {   // warp-uniform: tcgen05.ld / st are warp-collective
       const float f = need ? ex2_approx(m - mb) : 1.0f;
       if (need) { l *= f; m = mb; }
-      // O_t is quiescent here: S of this block was committed after the previous block's P V, which has therefore completed
-      tmem_ld32_async(o_addr, a);
-      tmem_ld_wait_dep32(a);
+      mbar_wait(pv_done, pv_parity);          // the previous block's P V (issued asynchronously) has finished accumulating into O
+      tc_fence_after();
+      uint32_t o[32];
+      tmem_ld32_async(o_addr, o);
+      tmem_ld_wait_dep32(o);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) a[i] = __float_as_uint(__uint_as_float(a[i]) * f);
-      tmem_st32(o_addr, a);
-      tmem_st_wait();
+      for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * f);
+      tmem_st32(o_addr, o);
     }
   }
-  // ---- pass B: P = exp2(s c - m) -> fp16, in place; row sum in fp32 ----
+  // ---- P = exp2(s c - m) -> fp16, written over the first 24 columns of the S buffer; row sum in fp32 ----
   const float nm = -m;
   float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-  auto chunk = [&](const uint32_t* s, uint32_t* p, int n, int nvalid) {   // n columns (32 or 16) -> n/2 packed registers
+  uint32_t pk[24];
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (i < n) {
-        const float p0 = (i < nvalid) ? ex2_approx(fmaf(__uint_as_float(s[i]), kScaleLog2, nm)) : 0.f;
-        const float p1 = (i + 1 < nvalid) ? ex2_approx(fmaf(__uint_as_float(s[i + 1]), kScaleLog2, nm)) : 0.f;
-        const float p2 = (i + 2 < nvalid) ? ex2_approx(fmaf(__uint_as_float(s[i + 2]), kScaleLog2, nm)) : 0.f;
-        const float p3 = (i + 3 < nvalid) ? ex2_approx(fmaf(__uint_as_float(s[i + 3]), kScaleLog2, nm)) : 0.f;
-        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
-        p[i / 2] = pack_f16(p0, p1);
-        p[i / 2 + 1] = pack_f16(p2, p3);
-      }
-    }
-  };
-  uint32_t pk[16];
-  tmem_ld32_async(s_addr, a);
-  tmem_ld_wait_dep32(a);
-  tmem_ld32_async(s_addr + 32, b);          // (for NK = 48 only the first 16 of these columns are used)
-  chunk(a, pk, 32, 32);
-  tmem_ld_wait_dep32(b);
-  tmem_st16(s_addr, pk);                    // P columns [0,16) over S columns [0,16): S chunk 0 is in registers
-  if (NK == KB) {
-    tmem_ld32_async(s_addr + 64, a);
-    chunk(b, pk, 32, 32);
-    tmem_ld_wait_dep32(a);
-    tmem_st16(s_addr + 16, pk);
-    chunk(a, pk, 32, 32);
-    tmem_st16(s_addr + 32, pk);
-  } else {
-    chunk(b, pk, 16, NVAL - 32);
-    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(s_addr + 16), "r"(pk[0]), "r"(pk[1]),
-                 "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                 : "memory");
+  for (int i = 0; i < 48; i += 4) {
+    const uint32_t* s = i < 32 ? a + i : b + (i - 32);
+    const float p0 = ex2_approx(fmaf(__uint_as_float(s[0]), kScaleLog2, nm));
+    const float p1 = ex2_approx(fmaf(__uint_as_float(s[1]), kScaleLog2, nm));
+    const float p2 = ex2_approx(fmaf(__uint_as_float(s[2]), kScaleLog2, nm));
+    const float p3 = (LAST && i == 44) ? 0.f : ex2_approx(fmaf(__uint_as_float(s[3]), kScaleLog2, nm));
+    l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+    pk[i / 2] = pack_f16(p0, p1);
+    pk[i / 2 + 1] = pack_f16(p2, p3);
   }
+  tmem_st16(s_addr, pk);
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(s_addr + 16), "r"(pk[16]), "r"(pk[17]),
+               "r"(pk[18]), "r"(pk[19]), "r"(pk[20]), "r"(pk[21]), "r"(pk[22]), "r"(pk[23])
+               : "memory");
   l += (l0 + l1) + (l2 + l3);
   tmem_st_wait();
 }
@@ -168,8 +131,13 @@ __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __
     for (int s = 0; s < STAGES; ++s) { mbar_init(&bars.kv_full[s], 1); mbar_init(&bars.kv_empty[s], 1); }
     for (int t = 0; t < 4; ++t) {
       // warpgroup 3 holds rows 384..511 of which 384..430 exist: warps 2, 3 of it have no row at all and take no part
-      mbar_init(&bars.s_full[t], 1);
-      mbar_init(&bars.p_full[t], t < 3 ? 4 : 2);
+      mbar_init(&bars.s_full[t][0], 1);
+      mbar_init(&bars.s_full[t][1], 1);
+      // (a warp may run one block ahead of its warpgroup - S of the next block is ready early - so the "P written"
+      //  barrier is per S buffer: arrivals of block g and block g + 1 never mix)
+      mbar_init(&bars.p_full[t][0], t < 3 ? 4 : 2);
+      mbar_init(&bars.p_full[t][1], t < 3 ? 4 : 2);
+      mbar_init(&bars.pv_done[t], 1);
       mbar_init(&bars.o_full[t], 1);
     }
     mbar_init_fence();
@@ -195,58 +163,66 @@ __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __
     }
   } else if (warp == W_MMA) {
     // ===== MMA issuer =====
-    constexpr uint32_t id_s96 = idesc_f16(128, KB), id_s48 = idesc_f16(128, 48), id_pv = idesc_f16(128, DK, 1);
-    auto issue_qk = [&](uint32_t stage_base, int t, int j) {   // S_t = Q_t K_j^T (2 k-steps of 16)
+    constexpr uint32_t id_s = idesc_f16(128, KB), id_pv = idesc_f16(128, DK, 1);
+    // Blocks are numbered globally, g = item * NBLK + j; block g uses S buffer g & 1 of its tile (NBLK is odd, so the buffer of a
+    // (sample, head)'s first block alternates from one item to the next).
+    auto issue_qk = [&](uint32_t stage_base, int t, int j, int buf) {   // S_t[buf] = Q_t K_j^T (2 k-steps of 16)
       const uint32_t q0 = stage_base + t * (16 * 512), k0 = stage_base + IMG + j * (KB / 8) * 512;
 #pragma unroll
       for (int ks = 0; ks < 2; ++ks)
-        mma_bf16(tmem + t * 128, smem_desc(q0 + ks * 256, 128, 512), smem_desc(k0 + ks * 256, 128, 512), j < NBLK - 1 ? id_s96 : id_s48, ks);
+        mma_bf16(tmem + t * 128 + buf * KB, smem_desc(q0 + ks * 256, 128, 512), smem_desc(k0 + ks * 256, 128, 512), id_s, ks);
     };
-    auto issue_pv = [&](uint32_t stage_base, int t, int j) {   // O_t (+)= P V_j: A = P in tensor memory, B = V MN-major
+    auto issue_pv = [&](uint32_t stage_base, int t, int j, int buf) {   // O_t (+)= P V_j: A = P in tensor memory (first 24 columns of S_t[buf]), B = V MN-major
       const uint32_t v0 = stage_base + 2 * IMG + j * (KB / 8) * 512;
-      const int ksteps = j < NBLK - 1 ? KB / 16 : 3;
-      for (int ks = 0; ks < ksteps; ++ks)
-        mma_ts(tmem + t * 128 + KB, tmem + t * 128 + ks * 8, smem_desc(v0 + ks * 1024, 512, 128), id_pv, (j | ks) != 0);
+#pragma unroll
+      for (int ks = 0; ks < KB / 16; ++ks)
+        mma_ts(tmem + t * 128 + 2 * KB, tmem + t * 128 + buf * KB + ks * 8, smem_desc(v0 + ks * 1024, 512, 128), id_pv, (j | ks) != 0);
     };
-    uint32_t ph_p = 0;   // parity of the next p_full completion (same for all four tiles: they advance in lockstep here)
+    uint32_t ph_p[2] = {0, 0};   // parity of the next p_full completion per S buffer (the four tiles are served in turn; serving
+                                 // them out of order by polling the barriers was measured 7 % slower: the polling warp takes issue slots)
     for (int i = 0; i < n_my; ++i) {
       const int s = i % STAGES;
       const uint32_t sb = smem_u32(smem + s * ITEM);
       if (i == 0) {
         mbar_wait(&bars.kv_full[s], 0);
         if (elect_one()) {
-          for (int t = 0; t < 4; ++t) { issue_qk(sb, t, 0); mma_commit(&bars.s_full[t]); }
+          for (int t = 0; t < 4; ++t) {
+            issue_qk(sb, t, 0, 0); mma_commit(&bars.s_full[t][0]);
+            issue_qk(sb, t, 1, 1); mma_commit(&bars.s_full[t][1]);
+          }
         }
         __syncwarp();
       }
       for (int j = 0; j < NBLK; ++j) {
-        const bool last = j == NBLK - 1;
+        const int buf = (i * NBLK + j) & 1;
         uint32_t sb_next = 0;
-        if (last && i + 1 < n_my) {
+        if (j >= NBLK - 2 && i + 1 < n_my) {          // the last two blocks are followed by the first two of the next (sample, head)
           const int s1 = (i + 1) % STAGES;
           mbar_wait(&bars.kv_full[s1], ((i + 1) / STAGES) & 1);
           sb_next = smem_u32(smem + s1 * ITEM);
         }
         for (int t = 0; t < 4; ++t) {
-          mbar_wait(&bars.p_full[t], ph_p);
+          mbar_wait(&bars.p_full[t][buf], ph_p[buf]);
           tc_fence_after();
           if (elect_one()) {
-            issue_pv(sb, t, j);
-            if (!last) {
-              issue_qk(sb, t, j + 1);
-              mma_commit(&bars.s_full[t]);
-            } else {
+            issue_pv(sb, t, j, buf);
+            mma_commit(&bars.pv_done[t]);
+            if (j == NBLK - 1) {
               mma_commit(&bars.o_full[t]);
               if (t == 3) mma_commit(&bars.kv_empty[s]);   // every MMA that reads this stage has been issued
-              if (sb_next) {                                // first block of the next (sample, head) right behind it
-                issue_qk(sb_next, t, 0);
-                mma_commit(&bars.s_full[t]);
-              }
+            }
+            // the S buffer just consumed takes the block after next (in-order tensor pipe: P V has read P before it is overwritten)
+            if (j + 2 < NBLK) {
+              issue_qk(sb, t, j + 2, buf);
+              mma_commit(&bars.s_full[t][buf]);
+            } else if (sb_next) {
+              issue_qk(sb_next, t, j + 2 - NBLK, buf);
+              mma_commit(&bars.s_full[t][buf]);
             }
           }
           __syncwarp();
         }
-        ph_p ^= 1;
+        ph_p[buf] ^= 1;
       }
     }
   } else {
@@ -257,21 +233,25 @@ __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __
     const bool valid = q < V;
     {
       const uint32_t lane_addr = (uint32_t)((warp & 3) * 32) << 16;
-      const uint32_t s_addr = tmem + lane_addr + t * 128, o_addr = s_addr + KB;
-      uint32_t ph_s = 0, ph_o = 0;
+      const uint32_t s_base = tmem + lane_addr + t * 128, o_addr = s_base + 2 * KB;
+      uint32_t ph_s = 0, ph_o = 0, n_pv = 0;          // ph_s bit buf: parity of the next s_full[t][buf] completion; n_pv: P V groups so far
       for (int i = 0; i < n_my; ++i) {
         const int item = blockIdx.x + i * gridDim.x;
         float m = 0.f, l = 0.f;
 #pragma unroll 1
         for (int j = 0; j < NBLK; ++j) {
-          mbar_wait(&bars.s_full[t], ph_s);
-          ph_s ^= 1;
+          // buffer of block j of item i: blocks alternate buffers ACROSS items too (NBLK is odd)
+          const int buf = (i * NBLK + j) & 1;
+          mbar_wait(&bars.s_full[t][buf], (ph_s >> buf) & 1);
+          ph_s ^= 1u << buf;
           tc_fence_after();
-          if (j < NBLK - 1) softmax_block<KB>(s_addr, o_addr, j == 0, valid, m, l);
-          else softmax_block<48>(s_addr, o_addr, false, valid, m, l);
+          const uint32_t s_addr = s_base + buf * KB;
+          if (j < NBLK - 1) softmax_block<false>(s_addr, o_addr, j == 0, valid, m, l, &bars.pv_done[t], (n_pv - 1) & 1);
+          else softmax_block<true>(s_addr, o_addr, false, valid, m, l, &bars.pv_done[t], (n_pv - 1) & 1);
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&bars.p_full[t]);
+          if (lane == 0) mbar_arrive(&bars.p_full[t][buf]);
+          ++n_pv;
         }
         // ---- O out: thread = row, 32 fp32 = one 128-byte line of out[b, q, h*32 .. h*32+31] ----
         mbar_wait(&bars.o_full[t], ph_o);
@@ -280,13 +260,27 @@ __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __
         uint32_t o[32];
         tmem_ld32_async(o_addr, o);
         tmem_ld_wait_dep32(o);
-        if (valid) {
+        {
+          // row-per-lane -> (4 rows x 128 contiguous bytes) per store instruction, through a warp-private XOR-swizzled
+          // shared-memory tile (a lane-per-row store touches 32 half-used sectors per instruction)
           const float inv = 1.0f / l;
-          float4* dst = reinterpret_cast<float4*>(out + ((size_t)(item >> 1) * V + q) * E + (item & 1) * DK);
+          uint8_t* st = smem + STAGES * ITEM + warp * OST_WARP;
 #pragma unroll
           for (int c = 0; c < 8; ++c)
-            dst[c] = make_float4(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv, __uint_as_float(o[4 * c + 2]) * inv,
-                                 __uint_as_float(o[4 * c + 3]) * inv);
+            *reinterpret_cast<float4*>(st + lane * 128 + ((c ^ (lane & 7)) * 16)) =
+                make_float4(__uint_as_float(o[4 * c]) * inv, __uint_as_float(o[4 * c + 1]) * inv, __uint_as_float(o[4 * c + 2]) * inv,
+                            __uint_as_float(o[4 * c + 3]) * inv);
+          __syncwarp();
+          const int c = lane & 7;
+          const int q0 = t * 128 + (warp & 3) * 32;         // first query row of this warp
+          float* obase = out + ((size_t)(item >> 1) * V) * E + (item & 1) * DK + c * 4;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int r = k * 4 + (lane >> 3);
+            const float4 val = *reinterpret_cast<const float4*>(st + r * 128 + ((c ^ (r & 7)) * 16));
+            if (q0 + r < V) *reinterpret_cast<float4*>(obase + (size_t)(q0 + r) * E) = val;
+          }
+          __syncwarp();
         }
         // the next item's first P V (accumulate = 0) overwrites O only after this thread's p_full arrival for its block 0
       }
