@@ -58,6 +58,13 @@ class CsrArgs(C.Structure):
                 ('x', C.c_void_p), ('y', C.c_void_p)]
 
 
+class Upsample2Args(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('cols', C.c_int32), ('rows1', C.c_int32), ('rows2', C.c_int32),
+                ('width1', C.c_int32), ('width2', C.c_int32), ('scale', C.c_float), ('reserved', C.c_int32),
+                ('col1', C.c_void_p), ('val1', C.c_void_p), ('col2', C.c_void_p), ('val2', C.c_void_p),
+                ('x', C.c_void_p), ('y', C.c_void_p)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32),
                 ('lda', C.c_int32), ('ldw', C.c_int32), ('ldc', C.c_int32), ('ldr', C.c_int32),
@@ -92,12 +99,12 @@ class SmplCamArgs(C.Structure):
                 ('cam_t', C.c_void_p), ('pose_out', C.c_void_p), ('betas_out', C.c_void_p), ('trans_out', C.c_void_p)]
 
 
-_STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs, EvalArgs, Pose2dArgs, SmplCamArgs]
+_STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs, EvalArgs, Pose2dArgs, SmplCamArgs, Upsample2Args]
 EXPORTS = ['gator_abi_version', 'gator_last_error', 'gator_abi_sizeof', 'gator_launch_count',
            'gator_mdr_self_attention', 'gator_mdr_self_attention_image_bytes', 'gator_mdr_self_attention_f16', 'gator_mdr_self_attention_core', 'gator_mdr_layer_chain', 'gator_umma_weight_layout',
            'gator_gat_slot_name', 'gator_gat_workspace_bytes', 'gator_gat_forward',
            'gator_mdr_slot_name', 'gator_mdr_workspace_bytes', 'gator_mdr_forward',
-           'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_gemm',
+           'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_mesh_upsample2', 'gator_gemm',
            'gator_eval_epilogue', 'gator_pose2d_preprocess', 'gator_smpl_cam_fixup',
            'gator_umma_wide_layout', 'gator_umma_wide_a_bytes']
 
@@ -133,7 +140,7 @@ def lib():
         for name, st in (('gator_gat_forward', GatArgs), ('gator_mdr_forward', MdrArgs),
                          ('gator_smpl_forward', SmplArgs), ('gator_csr_spmm', CsrArgs), ('gator_gemm', GemmArgs),
                          ('gator_eval_epilogue', EvalArgs), ('gator_pose2d_preprocess', Pose2dArgs),
-                         ('gator_smpl_cam_fixup', SmplCamArgs)):
+                         ('gator_smpl_cam_fixup', SmplCamArgs), ('gator_mesh_upsample2', Upsample2Args)):
             getattr(L, name).restype = C.c_int
             getattr(L, name).argtypes = [C.POINTER(st), C.c_void_p]
         L.gator_launch_count.restype = C.c_longlong

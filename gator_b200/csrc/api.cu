@@ -43,6 +43,7 @@ extern "C" size_t gator_abi_sizeof(int which) {
     case 5: return sizeof(gator_eval_args);
     case 6: return sizeof(gator_pose2d_args);
     case 7: return sizeof(gator_smpl_cam_args);
+    case 8: return sizeof(gator_upsample2_args);
     default: return 0;
   }
 }

@@ -260,7 +260,11 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
 // 8192 -> 1.64: the persistent blend-shape GEMM needs many tiles per CTA to fill its waves, and keeping v_posed
 // L2-resident with small chunks does not pay.  (Numbers taken with the CUDA-core skinning kernel and 4 epilogue warps
 // in the GEMM; with the tensor-core skinning kernel of smpl_skin_umma.cu and 8-16 epilogue warps the same batch takes 1.05 ms.)
-constexpr int kChunk = 8192;
+static int chunk_samples() {
+  static const int v = [] { const char* e = getenv("GATOR_SMPL_CHUNK"); const int c = e ? atoi(e) : 0; return c >= 20 && c <= 65536 ? c : 8192; }();
+  return v;
+}
+#define kChunk chunk_samples()
 
 struct Ws {
   float *aop, *amat, *offset, *vposed;

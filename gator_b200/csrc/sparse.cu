@@ -206,6 +206,114 @@ csr_spmm3_rows_kernel(const int* __restrict__ rowptr, const int* __restrict__ co
   }
 }
 
+
+// Mesh.upsample through two operators in one launch (mesh.py:110-123 with n1=2, n2=0: 431 -> 1723 -> 6890).
+// CTA = 4 consecutive samples, two CTAs per SM (one streams outputs while the other stages / runs level 1): the
+// inputs (cols x 3 floats per sample) and the intermediate level (rows1 x 3) live in shared memory, so HBM sees the
+// 5 KB input and the 83 KB output of a sample once.
+//  * lane = one output FLOAT position (row r = f / 3, component c = f % 3), not one row: a warp's stores are 128
+//    contiguous bytes per sample straight from registers (no staging pass through shared memory);
+//  * the four samples of the group are interleaved in shared memory (float4 per float position), so ONE 16-byte
+//    shared-memory load per non-zero serves all four samples: 3 LDS + 12 FMA + 4 STG per position;
+//  * operators are ELL records of four (col, val) per row - two 16-byte loads per position and group, L2-resident.
+// The first version of this kernel (scalar ELL loads, per-sample 4-byte gathers) was issue-bound: 87 instructions per
+// warp-level output, 289 us at B = 4096 (profiles/r02_ncu_mesh_upsample2.txt); this one issues ~11.
+constexpr int UP_NS = 4;
+template <int W1, int W2>
+__global__ void __launch_bounds__(512, 2)
+mesh_upsample2_kernel(const int4* __restrict__ col1, const float4* __restrict__ val1, const int4* __restrict__ col2,
+                      const float4* __restrict__ val2, const float* __restrict__ x, float* __restrict__ y, int cols,
+                      int rows1, int rows2, float scale, int batch, int groups) {
+  extern __shared__ __align__(16) float4 sm4[];
+  const int xs0 = cols * 3, xs1 = rows1 * 3, xs2 = rows2 * 3;
+  float4* sx0 = sm4;                  // [xs0] x 4 samples
+  float4* sx1 = sm4 + xs0;            // [xs1] x 4 samples
+  const int tid = threadIdx.x;
+  auto gather = [](const float4* __restrict__ src, const int4 cc, const float4 ww, int c, int W) -> float4 {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int id[4] = {cc.x * 3 + c, cc.y * 3 + c, cc.z * 3 + c, cc.w * 3 + c};
+    const float w[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < W) {
+        const float4 v = src[id[k]];
+        a.x = fmaf(w[k], v.x, a.x); a.y = fmaf(w[k], v.y, a.y); a.z = fmaf(w[k], v.z, a.z); a.w = fmaf(w[k], v.w, a.w);
+      }
+    }
+    return a;
+  };
+  for (int g = blockIdx.x; g < groups; g += gridDim.x) {
+    const int b0 = g * UP_NS;
+    const int ns = min(UP_NS, batch - b0);
+    __syncthreads();                  // the previous group's level 2 has finished reading sx1
+    {
+      // all of a thread's loads are issued before the first store (12 in flight per thread)
+      const float* src = x + (size_t)b0 * xs0;
+      float* dst = reinterpret_cast<float*>(sx0);
+      for (int i0 = 0; i0 < xs0; i0 += 3 * 512) {
+        float v[UP_NS][3];
+#pragma unroll
+        for (int s = 0; s < UP_NS; ++s)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            const int i = i0 + j * 512 + tid;
+            v[s][j] = (s < ns && i < xs0) ? __ldg(src + s * xs0 + i) : 0.f;
+          }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int i = i0 + j * 512 + tid;
+          if (i < xs0) sx0[i] = make_float4(v[0][j], v[1][j], v[2][j], v[3][j]);
+        }
+      }
+    }
+    __syncthreads();
+    for (int f = tid; f < xs1; f += 512) {
+      const int r = f / 3, c = f - r * 3;
+      sx1[f] = gather(sx0, __ldg(col1 + r), __ldg(val1 + r), c, W1);
+    }
+    __syncthreads();
+    float* y0 = y + (size_t)b0 * xs2;
+    if (ns == UP_NS) {
+      // the operator record of the next position is requested before the current one is processed
+      int4 cc = make_int4(0, 0, 0, 0);
+      float4 ww = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tid < xs2) { cc = __ldg(col2 + tid / 3); ww = __ldg(val2 + tid / 3); }
+      for (int f = tid; f < xs2; f += 512) {
+        const int r = f / 3, c = f - r * 3;
+        const int4 cc0 = cc;
+        const float4 ww0 = ww;
+        if (f + 512 < xs2) { cc = __ldg(col2 + (f + 512) / 3); ww = __ldg(val2 + (f + 512) / 3); }
+        const float4 a = gather(sx1, cc0, ww0, c, W2);
+        float* yo = y0 + f;
+        yo[0] = a.x * scale; yo[xs2] = a.y * scale; yo[2 * (size_t)xs2] = a.z * scale; yo[3 * (size_t)xs2] = a.w * scale;
+      }
+    } else {
+      for (int f = tid; f < xs2; f += 512) {
+        const int r = f / 3, c = f - r * 3;
+        const float4 a = gather(sx1, __ldg(col2 + r), __ldg(val2 + r), c, W2);
+        float* yo = y0 + f;
+        yo[0] = a.x * scale;
+        if (ns > 1) yo[xs2] = a.y * scale;
+        if (ns > 2) yo[2 * (size_t)xs2] = a.z * scale;
+      }
+    }
+  }
+}
+
+template <int W1, int W2>
+int launch_upsample2(const gator_upsample2_args* a, int slots, cudaStream_t stream) {
+  static DeviceOnce attr_once;
+  GATOR_TRY(attr_once.run("mesh_upsample2", [&](int) -> cudaError_t {
+    return cudaFuncSetAttribute(mesh_upsample2_kernel<W1, W2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  }));
+  const int groups = ceil_div(a->batch, UP_NS);
+  const size_t smem = (size_t)UP_NS * (a->cols + a->rows1) * 12;
+  mesh_upsample2_kernel<W1, W2><<<groups < slots ? groups : slots, 512, smem, stream>>>(
+      reinterpret_cast<const int4*>(a->col1), reinterpret_cast<const float4*>(a->val1), reinterpret_cast<const int4*>(a->col2),
+      reinterpret_cast<const float4*>(a->val2), a->x, a->y, a->cols, a->rows1, a->rows2, a->scale, a->batch, groups);
+  return check_launch("mesh_upsample2");
+}
+
 }  // namespace
 }  // namespace gator
 
@@ -247,4 +355,30 @@ extern "C" int gator_csr_spmm(const gator_csr_args* a, void* stream) {
   csr_spmm_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
       a->rowptr, a->colidx, a->values, a->x, a->y, a->rows, a->cols, a->feat, a->scale, total, vec);
   return check_launch("csr_spmm");
+}
+
+extern "C" int gator_mesh_upsample2(const gator_upsample2_args* a, void* stream_) {
+  using namespace gator;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GATOR_REQUIRE(a, "gator_mesh_upsample2: null args");
+  GATOR_REQUIRE(a->batch >= 0 && a->cols > 0 && a->rows1 > 0 && a->rows2 > 0, "gator_mesh_upsample2: bad shape");
+  GATOR_REQUIRE(a->width1 >= 1 && a->width1 <= 4 && a->width2 >= 1 && a->width2 <= 4, "gator_mesh_upsample2: ELL width must be 1..4");
+  if (a->batch == 0) return GATOR_OK;
+  GATOR_REQUIRE(a->col1 && a->val1 && a->col2 && a->val2 && a->x && a->y, "gator_mesh_upsample2: null buffer");
+  GATOR_REQUIRE(((reinterpret_cast<uintptr_t>(a->col1) | reinterpret_cast<uintptr_t>(a->val1) | reinterpret_cast<uintptr_t>(a->col2) |
+                  reinterpret_cast<uintptr_t>(a->val2)) & 15u) == 0, "gator_mesh_upsample2: ELL arrays must be 16-byte aligned");
+  GATOR_REQUIRE((size_t)(a->cols + a->rows1) * 12 * UP_NS <= 112 * 1024,
+                "gator_mesh_upsample2: levels do not fit shared memory (use gator_csr_spmm twice)");
+  static int sm_count[64];
+  static DeviceOnce sm_once;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  GATOR_TRY(sm_once.run("mesh_upsample2 (SM count)", [&](int d) -> cudaError_t {
+    return cudaDeviceGetAttribute(&sm_count[d & 63], cudaDevAttrMultiProcessorCount, d);
+  }));
+  const int slots = 2 * (sm_count[dev & 63] > 0 ? sm_count[dev & 63] : 148);
+  // the records always hold four entries; widths <= 3 skip the fourth (its weight is 0)
+  const bool w1 = a->width1 > 3, w2 = a->width2 > 3;
+  if (w1) return w2 ? launch_upsample2<4, 4>(a, slots, stream) : launch_upsample2<4, 3>(a, slots, stream);
+  return w2 ? launch_upsample2<3, 4>(a, slots, stream) : launch_upsample2<3, 3>(a, slots, stream);
 }

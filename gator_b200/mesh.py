@@ -28,6 +28,17 @@ class _Csr:
         self.colidx = torch.from_numpy(ci).to(device)
         self.values = torch.from_numpy(va).to(device)
         self.device = torch.device(device)
+        # ELL copy (records of four (col, val) per row) for the fused two-level upsampling kernel; rows with fewer
+        # non-zeros are padded with weight 0 on a column the row already uses
+        nnz = np.diff(rp)
+        self.ell_width = int(nnz.max()) if len(nnz) else 0
+        self.ell_col = self.ell_val = None
+        if 1 <= self.ell_width <= 4 and nnz.min() >= 1:
+            k = np.arange(4)[None, :]
+            valid = k < nnz[:, None]
+            pos = rp[:-1][:, None] + np.where(valid, k, 0)
+            self.ell_col = torch.from_numpy(np.ascontiguousarray(ci[pos]).astype(np.int32)).to(device)
+            self.ell_val = torch.from_numpy(np.where(valid, va[pos], 0).astype(np.float32)).to(device)
 
     def apply(self, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
         """y[..., r, :] = scale * sum_k val_k x[..., col_k, :] for x of shape (N,F) or (B,N,F)."""
@@ -50,6 +61,37 @@ class _Csr:
         with torch.cuda.device(x.device):
             _lib.check(_lib.lib().gator_csr_spmm(a, _lib.stream_ptr()), 'gator_csr_spmm')
         return y[0] if squeeze else y
+
+
+def _fusable(first: _Csr, second: _Csr, x) -> bool:
+    """Two consecutive operators the fused kernel (gator_mesh_upsample2) takes: xyz features, ELL width <= 4, both
+    coarse levels of four samples in 112 KB of shared memory."""
+    return (x.dim() in (2, 3) and x.shape[-1] == 3 and first.ell_col is not None and second.ell_col is not None
+            and second.shape[1] == first.shape[0] and (first.shape[1] + first.shape[0]) * 48 <= 112 * 1024)
+
+
+def _apply2(first: _Csr, second: _Csr, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
+    """second(first(x)) in one launch; same checks and bit-identical results as two _Csr.apply calls."""
+    if not x.is_cuda:
+        raise RuntimeError('gator_b200.Mesh: CUDA tensors only (no CPU fallback)')
+    if x.device != first.rowptr.device:
+        raise RuntimeError(f'gator_b200.Mesh: input on {x.device} but the operator is on {first.rowptr.device}')
+    if x.dtype != torch.float32:
+        raise TypeError('gator_b200.Mesh: float32 only')
+    squeeze = x.dim() == 2
+    xb = x.unsqueeze(0) if squeeze else x
+    if xb.shape[1] != first.shape[1]:
+        raise ValueError(f'expected (*, {first.shape[1]}, 3), got {tuple(x.shape)}')
+    xb = xb.contiguous()
+    B = xb.shape[0]
+    y = torch.empty((B, second.shape[0], 3), dtype=torch.float32, device=x.device)
+    a = _lib.Upsample2Args(batch=B, cols=first.shape[1], rows1=first.shape[0], rows2=second.shape[0],
+                           width1=first.ell_width, width2=second.ell_width, scale=scale, reserved=0,
+                           col1=_lib.ptr(first.ell_col), val1=_lib.ptr(first.ell_val),
+                           col2=_lib.ptr(second.ell_col), val2=_lib.ptr(second.ell_val), x=_lib.ptr(xb), y=_lib.ptr(y))
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().gator_mesh_upsample2(a, _lib.stream_ptr()), 'gator_mesh_upsample2')
+    return y[0] if squeeze else y
 
 
 def adjmat_sparse(adjmat, nsize=1):
@@ -105,8 +147,15 @@ class Mesh(object):
 
     def upsample(self, x, n1=1, n2=0):
         """Upsample mesh: x (N,3) or (B,N,3) through U[n1-1..n2] (coarse to fine)."""
-        for i in reversed(range(n2, n1)):
-            x = self._ops('U')[i].apply(x)
+        ops = [self._ops('U')[i] for i in reversed(range(n2, n1))]
+        i = 0
+        while i < len(ops):
+            if i + 1 < len(ops) and _fusable(ops[i], ops[i + 1], x):
+                x = _apply2(ops[i], ops[i + 1], x)       # intermediate level stays in shared memory
+                i += 2
+            else:
+                x = ops[i].apply(x)
+                i += 1
         return x
 
     # init-time helper used by MDR.__init__ (MDR.py:79-81): same product as the reference's

@@ -49,7 +49,7 @@ typedef enum {
 int gator_abi_version(void);
 const char* gator_last_error(void);
 /* sizeof() of the ABI structs as compiled, so the ctypes mirror can be verified at load time:
- * which = 0 gat, 1 mdr, 2 smpl, 3 csr, 4 gemm, 5 eval, 6 pose2d, 7 smpl_cam */
+ * which = 0 gat, 1 mdr, 2 smpl, 3 csr, 4 gemm, 5 eval, 6 pose2d, 7 smpl_cam, 8 upsample2 */
 size_t gator_abi_sizeof(int which);
 /* number of kernels this library has launched (process-wide); reset != 0 zeroes it after reading.
  * bench.py reports it as `gpu_launches`. */
@@ -314,6 +314,36 @@ typedef struct {
 } gator_csr_args;
 
 int gator_csr_spmm(const gator_csr_args* a, void* stream);
+
+/* Two consecutive upsampling operators in one launch - Mesh.upsample(x, n1=2, n2=0) of
+ * lib/models/backbones/mesh.py:110-123 (431 -> 1723 -> 6890 vertices): the intermediate level stays in shared
+ * memory, so a sample costs its 5 KB input and its 83 KB output of HBM traffic and nothing else.
+ * Operators are passed in ELL form as records of FOUR entries per row: col[r * 4 + k], val[r * 4 + k], k < 4
+ * (16-byte aligned arrays); a row with fewer non-zeros is padded with val = 0 and a column the row already uses;
+ * `width` = the largest number of non-zeros of a row (<= 4).  Arithmetic per output element is the same fmaf chain,
+ * in the same order, as gator_csr_spmm applied twice.
+ *   mid[b, r, :] = sum_k val1[r, k] * x[b, col1[r, k], :]            r < rows1
+ *   y[b, r, :]   = scale * sum_k val2[r, k] * mid[b, col2[r, k], :]  r < rows2
+ * Requires (cols + rows1) * 12 * 4 bytes <= 112 KB of shared memory (four samples per CTA, two CTAs per SM);
+ * larger levels go through gator_csr_spmm twice. */
+typedef struct {
+  int32_t batch;               /* B                                                       */
+  int32_t cols;                /* input vertices per sample (431)                         */
+  int32_t rows1;               /* intermediate vertices (1723)                            */
+  int32_t rows2;               /* output vertices (6890)                                  */
+  int32_t width1;              /* ELL width of the first operator (1..4)                  */
+  int32_t width2;              /* ELL width of the second operator (1..4)                 */
+  float scale;
+  int32_t reserved;
+  const int32_t* col1;         /* (rows1, 4)                                              */
+  const float* val1;           /* (rows1, 4)                                              */
+  const int32_t* col2;         /* (rows2, 4)                                              */
+  const float* val2;           /* (rows2, 4)                                              */
+  const float* x;              /* (B, cols, 3)                                            */
+  float* y;                    /* (B, rows2, 3)                                           */
+} gator_upsample2_args;
+
+int gator_mesh_upsample2(const gator_upsample2_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Fused evaluation epilogue - replaces, per batch, lib/core/base.py:219-223

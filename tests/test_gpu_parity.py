@@ -382,6 +382,27 @@ def test_mesh_resampling_matches_reference_golden():
     assert torch.allclose(b, 2.0 * a, atol=1e-5)
 
 
+def test_mesh_upsample_fused_two_levels():
+    """Mesh.upsample(x, 2, 0) runs both operators in one launch (gator_mesh_upsample2): bit-identical to the two
+    single-level launches (same fmaf chains), for every samples-per-CTA choice the launcher makes and for ragged
+    last groups; and equal to the golden chain of the reference."""
+    import os
+    from gator_b200.mesh import Mesh
+    from helpers import base_data_root
+    mesh = Mesh(os.path.join(base_data_root(), 'data', 'base_data', 'mesh_downsampling.npz'), device=torch.device(DEV))
+    m = golden('mesh')
+    d2 = torch.from_numpy(m['down2']).to(DEV)
+    assert np.abs(mesh.upsample(d2, n1=2, n2=0).cpu().numpy() - m['up0']).max() <= 1e-6
+    gen = torch.Generator(device=DEV).manual_seed(5)
+    for B in (1, 2, 3, 5, 7, 296 * 3 + 1, 4096, 4099):
+        x = torch.randn(B, 431, 3, device=DEV, generator=gen)
+        fused = mesh.upsample(x, n1=2, n2=0)
+        two = mesh.upsample(mesh.upsample(x, n1=2, n2=1), n1=1, n2=0)
+        assert torch.equal(fused, two), B
+    x1 = torch.randn(431, 3, device=DEV, generator=gen)
+    assert torch.equal(mesh.upsample(x1, n1=2, n2=0), mesh.upsample(x1[None], n1=2, n2=0)[0])
+
+
 def test_joint_regression_post_step(models):
     from gator_b200.ops import JointRegressor
     g = golden('gator')
