@@ -97,18 +97,19 @@ def test_gather_world2_gloo(total):
 
 
 def test_host_pipeline_slice_plan():
-    """gator_b200.pipeline.plan_slices: geometric slices that cover the batch exactly, never below one CTA per SM."""
+    """gator_b200.pipeline.plan_slices: geometric slices that cover the batch exactly, never below two CTAs per SM."""
     from gator_b200.pipeline import HostPipeline, plan_slices
     for B in (1, 37, 296, 297, 700, 4096, 8192, 65536):
         b = plan_slices(B, HostPipeline.RATIO)
         sizes = [hi - lo for lo, hi in zip(b[:-1], b[1:])]
         assert b[0] == 0 and b[-1] == B and all(s > 0 for s in sizes)
         assert all(x >= y for x, y in zip(sizes[:-2], sizes[1:-1]))           # shrinking (the last one absorbs the remainder)
-        if B > 296:
-            assert min(sizes) >= 148
-        if B >= 700:
+        if B > 592:
+            assert min(sizes) >= 296
+        if B >= 1500:
             assert len(sizes) >= 2 and sizes[-1] <= 0.4 * B                    # only a short copy is left exposed
-    assert plan_slices(4096, 0.35) == [0, 2662, 3593, 3919, 4096]
+    assert plan_slices(4096, 0.35, 148) == [0, 2662, 3593, 3919, 4096]
+    assert plan_slices(4096, 0.8)[:3] == [0, 819, 1474] and len(plan_slices(4096, 0.8)) == 10
 
 
 def test_numa_binding_is_best_effort():

@@ -432,6 +432,23 @@ def test_host_pipeline_matches_plain_forward(models):
     assert torch.equal(hm, mesh.cpu()) and torch.equal(hp, p3.cpu())
     hm, hp = HostPipeline(m, 0).forward(x[:0])
     assert hm.shape == (0, 6890, 3) and hp.shape == (0, 17, 3)
+    # throughput mode: tickets, two alternating pinned output sets, results equal to the plain forward
+    pipe = HostPipeline(m, 700)
+    xs = [torch.from_numpy(synthetic.poses2d(700, 17, seed=20 + i)).pin_memory() for i in range(4)]
+    want = [tuple(t.cpu() for t in m(xi.to(DEV))) for xi in xs]
+    t0 = pipe.submit(xs[0])
+    t1 = pipe.submit(xs[1])
+    with pytest.raises(RuntimeError):
+        pipe.submit(xs[2])                         # ticket 0 not collected yet: its buffers would be overwritten
+    for i, t in ((0, t0), (1, t1)):
+        hm, hp = pipe.result(t)
+        assert torch.equal(hm, want[i][0]) and torch.equal(hp, want[i][1].reshape(700, 17, 3)), i
+    t2 = pipe.submit(xs[2]); t3 = pipe.submit(xs[3])
+    hm3, hp3 = pipe.result(t3)
+    hm2, hp2 = pipe.result(t2)
+    assert torch.equal(hm2, want[2][0]) and torch.equal(hm3, want[3][0]) and torch.equal(hp3, want[3][1].reshape(700, 17, 3))
+    with pytest.raises(ValueError):
+        pipe.result(t0)
 
 
 def test_config5_shard_size_tensor_path(models):
