@@ -9,10 +9,14 @@
 // (the CUDA-core kernel is bound by those gathers: 48 conflict-free wavefronts per warp and sample).
 //
 // Same skeleton as csrc/umma_gemm_wide.cu: persistent CTAs, warp 0 = TMA producer (one 16 KB weight tile + one 32 KB
-// transform tile per stage - K fits one block), warp 1 = MMA issue into one of two 256-column TMEM accumulators,
-// warps 2-17 = epilogue (four warps per TMEM lane quarter, 5 samples each): lane = vertex; v_posed segments
-// (96 contiguous floats per warp and sample) are requested one tile ahead and go through a warp-private shared-memory
-// transpose; the skinned vertices leave as 128-byte coalesced stores.
+// transform tile per stage - K fits one block - and, in a ring of its own, the tile's v_posed block: one 1536-byte bulk
+// copy per sample row, 20 x 128 vertices), warp 1 = MMA issue into one of two 256-column TMEM accumulators,
+// warps 2-17 = epilogue (four warps per TMEM lane quarter, 5 samples each): lane = vertex, its rest position read from
+// the v_posed block with a stride of 3 words (conflict free), the skinned vertices staged in warp-private shared memory
+// and stored as 256-byte coalesced rows of 8-byte accesses (a sample row is 8 mod 16 bytes).
+// Round 1 loaded v_posed with per-lane global loads and transposed it through shared memory in the epilogue warps: 103
+// instructions per (vertex, sample), issue slots 67 % busy, 286 us per 8192 samples = 70 % of the HBM roofline of its
+// own traffic (profiles/r02_ncu_smpl_kernels.txt).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -31,12 +35,17 @@ constexpr int A_HALF = TM * 32 * 2;     // 8 KB: hi or lo of a weight tile (128 
 constexpr int B_HALF = 256 * 32 * 2;    // 16 KB: hi or lo of a transform tile (256 rows, 240 used)
 constexpr int A_TILE = 2 * A_HALF, B_TILE = 2 * B_HALF;
 constexpr int STAGE = A_TILE + B_TILE;  // 48 KB
-constexpr int STAGES = 3;
+constexpr int STAGES = 2;
+constexpr int P_ROW = TM * 3 * 4;       // 1536 B: the v_posed floats of a tile's 128 vertices, one sample
+constexpr int P_STAGE = TS * P_ROW;     // 30 KB
+constexpr int P_STAGES = 2;
 constexpr int GROUPS = 4;               // epilogue warps per TMEM lane quarter (5 measured no faster)
 constexpr int HS = TS / GROUPS;         // samples per epilogue warp and tile (5)
 constexpr int EPI_WARPS = 4 * GROUPS;
 constexpr int NTHREADS = (2 + EPI_WARPS) * 32;
-constexpr int SMEM = STAGES * STAGE + EPI_WARPS * HS * 96 * 4;   // + [warp][sample][96] transpose regions (30 KB)
+constexpr int OFF_P = STAGES * STAGE;
+constexpr int OFF_ST = OFF_P + P_STAGES * P_STAGE;
+constexpr int SMEM = OFF_ST + EPI_WARPS * HS * 96 * 4;            // + [warp][sample][96] output staging (30 KB)
 
 struct SkinParams {
   const uint8_t* Wimg;     // [m_tiles][hi|lo][16][4][8][8]
@@ -74,13 +83,14 @@ skin_t_image_kernel(const float* __restrict__ amat, int S, long long chunks, uin
 __global__ void __launch_bounds__(NTHREADS, 1)
 smpl_skin_umma_kernel(SkinParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint64_t full[STAGES], empty[STAGES], acc_full[2], acc_empty[2], p_full[P_STAGES], p_empty[P_STAGES];
   __shared__ uint32_t tmem_slot;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (warp == 1) tmem_alloc(&tmem_slot, 512);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < P_STAGES; ++s) { mbar_init(&p_full[s], 1); mbar_init(&p_empty[s], EPI_WARPS); }
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_empty[0], EPI_WARPS * 32); mbar_init(&acc_empty[1], EPI_WARPS * 32);
     mbar_init_fence();
@@ -101,6 +111,15 @@ smpl_skin_umma_kernel(SkinParams p) {
         mbar_arrive_expect_tx(&full[s], STAGE);
         bulk_copy_g2s(smem + s * STAGE, p.Wimg + (size_t)mt * A_TILE, A_TILE, &full[s]);
         bulk_copy_g2s(smem + s * STAGE + A_TILE, p.Timg + (size_t)nt * B_TILE, B_TILE, &full[s]);
+        // the tile's v_posed block: rows of 128 vertices (the last vertex tile stops at the padded end of the row)
+        const int ps = it % P_STAGES;
+        if (it >= P_STAGES) mbar_wait(&p_empty[ps], ((it / P_STAGES) - 1) & 1);
+        const int ns = min(TS, p.S - nt * TS);
+        const int row_bytes = min(P_ROW, p.ld * 4 - mt * P_ROW);
+        mbar_arrive_expect_tx(&p_full[ps], (uint32_t)(ns * row_bytes));
+        const float* src = p.vposed + (size_t)nt * TS * p.ld + (size_t)mt * (P_ROW / 4);
+        uint8_t* dst = smem + OFF_P + ps * P_STAGE;
+        for (int i = 0; i < ns; ++i) bulk_copy_g2s(dst + i * P_ROW, src + (size_t)i * p.ld, (uint32_t)row_bytes, &p_full[ps]);
       }
     }
   } else if (warp == 1) {
@@ -130,52 +149,40 @@ smpl_skin_umma_kernel(SkinParams p) {
     const int ew = warp - 2;
     const int q = warp & 3;                        // TMEM lane quarter = which 32 vertices of the tile
     const int grp = ew >> 2;                       // which HS of the tile's samples
-    float* st = reinterpret_cast<float*>(smem + STAGES * STAGE) + ew * HS * 96;
-    // v_posed segments (and the per-sample offsets, one element per lane) of a tile are requested one tile ahead, so
-    // their L2 / HBM latency is covered by the previous tile's work
-    float seg[HS][3];
+    float* st = reinterpret_cast<float*>(smem + OFF_ST) + ew * HS * 96;
+    // per-sample offsets of a tile (one element per lane) are requested one tile ahead
     float ofs = 0.f;
     auto request = [&](int t) {
-      const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
-      const int vbase = mt * TM + q * 32;
-      const int nf = max(0, min(32, NV - vbase)) * 3;
+      const int nt = t / p.m_tiles;
       const int s_lo = nt * TS + grp * HS;
       const int ns = max(0, min(HS, p.S - s_lo));
-      const float* vp = p.vposed + (size_t)s_lo * p.ld + (size_t)vbase * 3;
-#pragma unroll
-      for (int i = 0; i < HS; ++i) {
-        const float* vn = vp + (size_t)i * p.ld;
-        seg[i][0] = (i < ns && lane < nf) ? vn[lane] : 0.f;
-        seg[i][1] = (i < ns && lane + 32 < nf) ? vn[lane + 32] : 0.f;
-        seg[i][2] = (i < ns && lane + 64 < nf) ? vn[lane + 64] : 0.f;
-      }
       ofs = lane < ns * 3 ? p.offset[(size_t)s_lo * 3 + lane] : 0.f;
     };
     if ((int)blockIdx.x < total) request(blockIdx.x);
     int it = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
       const int nt = t / p.m_tiles, mt = t - nt * p.m_tiles;
-      const int buf = it & 1;
+      const int buf = it & 1, ps = it % P_STAGES;
       const int vbase = mt * TM + q * 32;
       const int nf = max(0, min(32, NV - vbase)) * 3;            // floats of this warp's vertex segment
       const int s_lo = nt * TS + grp * HS;
       const int ns = max(0, min(HS, p.S - s_lo));
-      // transpose through the warp's shared-memory region: [sample][96 floats] -> lane = vertex
-#pragma unroll
-      for (int i = 0; i < HS; ++i) { st[i * 96 + lane] = seg[i][0]; st[i * 96 + lane + 32] = seg[i][1]; st[i * 96 + lane + 64] = seg[i][2]; }
-      __syncwarp();
+      // rest positions: lane = vertex, stride of 3 words (rows past the batch / vertices past the mesh hold stale data
+      // that is computed on but never stored)
+      mbar_wait(&p_full[ps], (it / P_STAGES) & 1);
+      const float* pt = reinterpret_cast<const float*>(smem + OFF_P + ps * P_STAGE) + (grp * HS) * (P_ROW / 4) + q * 96 + lane * 3;
       float pv[HS][3];
 #pragma unroll
-      for (int i = 0; i < HS; ++i) { pv[i][0] = st[i * 96 + lane * 3]; pv[i][1] = st[i * 96 + lane * 3 + 1]; pv[i][2] = st[i * 96 + lane * 3 + 2]; }
-      const float ofs_cur = ofs;
+      for (int i = 0; i < HS; ++i) { pv[i][0] = pt[i * (P_ROW / 4)]; pv[i][1] = pt[i * (P_ROW / 4) + 1]; pv[i][2] = pt[i * (P_ROW / 4) + 2]; }
       __syncwarp();
+      if (lane == 0) mbar_arrive(&p_empty[ps]);
+      const float ofs_cur = ofs;
       if (t + (int)gridDim.x < total) request(t + gridDim.x);
       mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc_fence_after();
       if (nf > 0 && ns > 0) {
         const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + grp * HS * 12;
-        // one sample at a time (16 registers of accumulator columns): a batched read of all HS samples needs 80 and
-        // made the compiler spill the prefetched v_posed values, which turned the prefetch into a blocking load
+        // one sample at a time (16 registers of accumulator columns)
 #pragma unroll
         for (int i = 0; i < HS; ++i) {
           if (i < ns) {
@@ -191,13 +198,16 @@ smpl_skin_umma_kernel(SkinParams p) {
           }
         }
         __syncwarp();
+        // 8-byte accesses: a sample row is 82 680 B = 8 mod 16, a segment starts a multiple of 384 B into it
+        const int nf2 = nf >> 1;
+        float2* dst0 = reinterpret_cast<float2*>(p.verts + (size_t)s_lo * NV3 + (size_t)vbase * 3);
+        const float2* st2 = reinterpret_cast<const float2*>(st);
 #pragma unroll
         for (int i = 0; i < HS; ++i) {
           if (i < ns) {
-            float* dst = p.verts + (size_t)(s_lo + i) * NV3 + (size_t)vbase * 3;
-            if (lane < nf) dst[lane] = st[i * 96 + lane];
-            if (lane + 32 < nf) dst[lane + 32] = st[i * 96 + lane + 32];
-            if (lane + 64 < nf) dst[lane + 64] = st[i * 96 + lane + 64];
+            float2* dst = dst0 + (size_t)i * (NV3 / 2);
+            if (lane < nf2) dst[lane] = st2[i * 48 + lane];
+            if (lane + 32 < nf2) dst[lane + 32] = st2[i * 48 + lane + 32];
           }
         }
         __syncwarp();
@@ -220,6 +230,8 @@ size_t skin_t_image_bytes(int S) { return (size_t)((S + TS - 1) / TS) * B_TILE; 
 int launch_smpl_skin_umma(const float* vposed, int ld, const float* amat, const float* offset, const void* Wimg, void* timg,
                           float* verts, int S, float scale, cudaStream_t stream) {
   if (S <= 0) return GATOR_OK;
+  GATOR_REQUIRE(ld % 4 == 0 && ld >= NV3 && (reinterpret_cast<uintptr_t>(vposed) & 15u) == 0,
+                "smpl_skin_umma: v_posed rows must be 16-byte aligned (bulk copies) and hold 20670 floats");
   SkinParams p;
   p.Wimg = static_cast<const uint8_t*>(Wimg);
   p.Timg = static_cast<const uint8_t*>(timg);
