@@ -48,6 +48,7 @@ constexpr int W_MMA = 14, W_TMA = 15;     // the two row-less warps of query til
 constexpr int OST_WARP = 32 * DK * 4;      // 4 KB per softmax warp: O rows staged for coalesced stores
 constexpr int SMEM = STAGES * ITEM + 14 * OST_WARP;   // 165 888 + 57 344 B dynamic
 constexpr float kScaleLog2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e) / sqrt(32)
+constexpr int kEmu = 1;                   // exponentials per group of four evaluated by ex2_poly (see there)
 constexpr float kLazy = 8.0f;             // the running maximum moves only when exceeded by 2^8
 
 struct Bars {
@@ -57,7 +58,23 @@ struct Bars {
 
 // One key block (48 keys) of one query row, single pass over the scores (48 registers).  LAST: the block's last column is
 // the zero pad row of K.  s_addr: this thread's lane + first column of the S buffer; o_addr: lane + first column of O.
-template <bool LAST>
+// 2^x on the FMA / ALU pipes (no MUFU): round-to-nearest split x = n + f, f in [-0.5, 0.5], cubic minimax polynomial for
+// 2^f (relative error 7.5e-5, a sixth of the fp16 rounding P gets anyway), n added into the exponent field.  The MUFU
+// unit delivers 16 results per clock and SM and the 2 x 431 x 432 exponentials per sample are this kernel's floor
+// (0.33 ms per 4096-sample launch at 100 % MUFU utilisation), so EMU of every four exponentials take this path.
+// Measured per 4096-sample launch: EMU = 0 524 us, EMU = 1 512 us, EMU = 2 583 us (the issue slots, not the MUFU unit,
+// bind beyond one in four); same error against fp64 in all three (tools/attn2_probe.py).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -100.0f);
+  const float fi = x + 12582912.0f;                 // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const float f = x - (fi - 12582912.0f);
+  float p = fmaf(0.055171459913253784f, f, 0.2426108568906784f);
+  p = fmaf(p, f, 0.6932609677314758f);
+  p = fmaf(p, f, 0.9999281167984009f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(fi) << 23));
+}
+
+template <bool LAST, int EMU>
 __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t o_addr, bool first, bool valid, float& m, float& l,
                                               uint64_t* pv_done, uint32_t pv_parity) {
   uint32_t a[32], b[16];
@@ -105,8 +122,9 @@ __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t o_addr, 
   for (int i = 0; i < 48; i += 4) {
     const uint32_t* s = i < 32 ? a + i : b + (i - 32);
     const float p0 = ex2_approx(fmaf(__uint_as_float(s[0]), kScaleLog2, nm));
-    const float p1 = ex2_approx(fmaf(__uint_as_float(s[1]), kScaleLog2, nm));
-    const float p2 = ex2_approx(fmaf(__uint_as_float(s[2]), kScaleLog2, nm));
+    const float x1 = fmaf(__uint_as_float(s[1]), kScaleLog2, nm), x2 = fmaf(__uint_as_float(s[2]), kScaleLog2, nm);
+    const float p1 = EMU >= 2 ? ex2_poly(x1) : ex2_approx(x1);
+    const float p2 = EMU >= 1 ? ex2_poly(x2) : ex2_approx(x2);
     const float p3 = (LAST && i == 44) ? 0.f : ex2_approx(fmaf(__uint_as_float(s[3]), kScaleLog2, nm));
     l0 += p0; l1 += p1; l2 += p2; l3 += p3;
     pk[i / 2] = pack_f16(p0, p1);
@@ -120,6 +138,7 @@ __device__ __forceinline__ void softmax_block(uint32_t s_addr, uint32_t o_addr, 
   tmem_st_wait();
 }
 
+template <int EMU>
 __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __restrict__ img, float* __restrict__ out, int items) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ Bars bars;
@@ -246,8 +265,8 @@ __global__ void __launch_bounds__(NT, 1) mdr_self_attn2_kernel(const uint8_t* __
           ph_s ^= 1u << buf;
           tc_fence_after();
           const uint32_t s_addr = s_base + buf * KB;
-          if (j < NBLK - 1) softmax_block<false>(s_addr, o_addr, j == 0, valid, m, l, &bars.pv_done[t], (n_pv - 1) & 1);
-          else softmax_block<true>(s_addr, o_addr, false, valid, m, l, &bars.pv_done[t], (n_pv - 1) & 1);
+          if (j < NBLK - 1) softmax_block<false, EMU>(s_addr, o_addr, j == 0, valid, m, l, &bars.pv_done[t], (n_pv - 1) & 1);
+          else softmax_block<true, EMU>(s_addr, o_addr, false, valid, m, l, &bars.pv_done[t], (n_pv - 1) & 1);
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars.p_full[t][buf]);
@@ -332,13 +351,13 @@ int launch_self_attn2(const void* img, float* out, int nb, cudaStream_t stream) 
   int dev = 0;
   cudaGetDevice(&dev);
   GATOR_TRY(attr_once.run("mdr_self_attn2", [&](int d) -> cudaError_t {
-    GATOR_CUDA_OK(cudaFuncSetAttribute(mdr_self_attn2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    GATOR_CUDA_OK(cudaFuncSetAttribute(mdr_self_attn2_kernel<kEmu>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     return cudaDeviceGetAttribute(&num_sms[d & 63], cudaDevAttrMultiProcessorCount, d);
   }));
   const int items = nb * 2;
   const int sms = num_sms[dev & 63] > 0 ? num_sms[dev & 63] : 148;
   const int grid = items < sms ? items : sms;
-  mdr_self_attn2_kernel<<<grid, NT, SMEM, stream>>>(static_cast<const uint8_t*>(img), out, items);
+  mdr_self_attn2_kernel<kEmu><<<grid, NT, SMEM, stream>>>(static_cast<const uint8_t*>(img), out, items);
   return check_launch("mdr_self_attn2");
 }
 
