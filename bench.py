@@ -617,6 +617,30 @@ def single_gpu_extras(args, model, x, dev, peaks):
                                                                 'SMPL-shaped buffers; device-resident inputs, CUDA events over 10 calls',
                                                     'roofline': 'HBM: 83.3 KB of mandatory traffic per mesh (SURVEY 8(d))', **smpl}}
     del pose, betas, trans
+    # Mesh.upsample 431 -> 1723 -> 6890 (row a21) in one launch, batch 4096; MANO layer (row f4) at batch 16384, fp32 kernels
+    try:
+        from builders import base_data_root
+        from gator_b200.mesh import Mesh
+        mesh_op = Mesh(os.path.join(base_data_root(), 'data', 'base_data', 'mesh_downsampling.npz'), device=dev)
+        xc = torch.randn(4096, 431, 3, device=dev)
+        ms = time_launch(lambda: mesh_op.upsample(xc, n1=2, n2=0), reps=10)
+        by = 4096 * (431 + 6890) * 12
+        out['other_workloads']['mesh_upsample_b4096'] = {
+            'workload': 'Mesh.upsample(x, n1=2, n2=0): 431 -> 1723 -> 6890 vertices, batch 4096, one launch (gator_mesh_upsample2)',
+            'ms_per_step': ms, 'value': 4096 / (ms * 1e-3), 'unit': UNIT, 'bound': 'hbm', 'bytes_per_mesh': by // 4096,
+            'achieved': by / (ms * 1e-3) / 1e9, 'peak': peaks['hbm_gbs'], 'frac': by / (ms * 1e-3) / 1e9 / peaks['hbm_gbs']}
+        del xc
+        from gator_b200.mano_layer import ManoLayer
+        hand = ManoLayer(mano_data=synthetic.mano_data(), ncomps=6).to(dev)
+        hp, hb, ht = [torch.from_numpy(a).to(dev) for a in synthetic.mano_inputs(Bs, ncomps=6)]
+        with torch.no_grad():
+            ms = time_launch(lambda: hand(hp, hb, ht), reps=10)
+        out['other_workloads']['mano_layer_b16384'] = {
+            'workload': 'ManoLayer.forward(pose_coeffs (B,9), betas, trans), batch 16384, synthetic MANO-shaped buffers (778 vertices, '
+                        '16 joints), fp32 kernels', 'ms_per_step': ms, 'value': Bs / (ms * 1e-3), 'unit': 'hands/s'}
+        del hp, hb, ht
+    except Exception as e:      # secondary workloads: report, do not fail the bench
+        out['other_workloads']['error'] = f'{type(e).__name__}: {e}'
 
     # ---- parity of this very configuration against the CPU oracle (64 samples) ----
     from helpers import oracle_setup, orc, regressor

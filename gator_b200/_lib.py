@@ -65,6 +65,23 @@ class Upsample2Args(C.Structure):
                 ('x', C.c_void_p), ('y', C.c_void_p)]
 
 
+class LbsArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('n_verts', C.c_int32), ('n_joints', C.c_int32), ('k_blend', C.c_int32),
+                ('center_idx', C.c_int32), ('has_betas', C.c_int32), ('has_trans', C.c_int32), ('check_zero_norm', C.c_int32),
+                ('weights_per_vertex', C.c_int32), ('out_scale', C.c_float),
+                ('parents', C.c_void_p), ('j_template', C.c_void_p), ('j_shapedirs', C.c_void_p), ('default_betas', C.c_void_p),
+                ('blend_w', C.c_void_p), ('v_template', C.c_void_p), ('skin_idx', C.c_void_p), ('skin_w', C.c_void_p),
+                ('pose', C.c_void_p), ('betas', C.c_void_p), ('trans', C.c_void_p), ('verts', C.c_void_p), ('jtr', C.c_void_p),
+                ('workspace', C.c_void_p), ('workspace_bytes', C.c_size_t)]
+
+
+class ManoPostArgs(C.Structure):
+    _fields_ = [('batch', C.c_int32), ('n_verts', C.c_int32), ('center_idx', C.c_int32), ('has_trans', C.c_int32),
+                ('check_zero_norm', C.c_int32), ('root_palm', C.c_int32), ('tip_verts', C.c_int32 * 5),
+                ('palm_verts', C.c_int32 * 2), ('scale', C.c_float), ('reserved', C.c_int32),
+                ('jtr16', C.c_void_p), ('trans', C.c_void_p), ('verts', C.c_void_p), ('jtr', C.c_void_p), ('flag_ws', C.c_void_p)]
+
+
 class GemmArgs(C.Structure):
     _fields_ = [('M', C.c_int32), ('N', C.c_int32), ('K', C.c_int32),
                 ('lda', C.c_int32), ('ldw', C.c_int32), ('ldc', C.c_int32), ('ldr', C.c_int32),
@@ -99,12 +116,13 @@ class SmplCamArgs(C.Structure):
                 ('cam_t', C.c_void_p), ('pose_out', C.c_void_p), ('betas_out', C.c_void_p), ('trans_out', C.c_void_p)]
 
 
-_STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs, EvalArgs, Pose2dArgs, SmplCamArgs, Upsample2Args]
+_STRUCTS = [GatArgs, MdrArgs, SmplArgs, CsrArgs, GemmArgs, EvalArgs, Pose2dArgs, SmplCamArgs, Upsample2Args, LbsArgs, ManoPostArgs]
 EXPORTS = ['gator_abi_version', 'gator_last_error', 'gator_abi_sizeof', 'gator_launch_count',
            'gator_mdr_self_attention', 'gator_mdr_self_attention_image_bytes', 'gator_mdr_self_attention_f16', 'gator_mdr_self_attention_core', 'gator_mdr_layer_chain', 'gator_umma_weight_layout',
            'gator_gat_slot_name', 'gator_gat_workspace_bytes', 'gator_gat_forward',
            'gator_mdr_slot_name', 'gator_mdr_workspace_bytes', 'gator_mdr_forward',
            'gator_smpl_workspace_bytes', 'gator_smpl_forward', 'gator_csr_spmm', 'gator_mesh_upsample2', 'gator_gemm',
+           'gator_lbs_workspace_bytes', 'gator_lbs_forward', 'gator_mano_pose', 'gator_mano_post',
            'gator_eval_epilogue', 'gator_pose2d_preprocess', 'gator_smpl_cam_fixup',
            'gator_umma_wide_layout', 'gator_umma_wide_a_bytes']
 
@@ -140,9 +158,14 @@ def lib():
         for name, st in (('gator_gat_forward', GatArgs), ('gator_mdr_forward', MdrArgs),
                          ('gator_smpl_forward', SmplArgs), ('gator_csr_spmm', CsrArgs), ('gator_gemm', GemmArgs),
                          ('gator_eval_epilogue', EvalArgs), ('gator_pose2d_preprocess', Pose2dArgs),
-                         ('gator_smpl_cam_fixup', SmplCamArgs), ('gator_mesh_upsample2', Upsample2Args)):
+                         ('gator_smpl_cam_fixup', SmplCamArgs), ('gator_mesh_upsample2', Upsample2Args),
+                         ('gator_lbs_forward', LbsArgs), ('gator_mano_post', ManoPostArgs)):
             getattr(L, name).restype = C.c_int
             getattr(L, name).argtypes = [C.POINTER(st), C.c_void_p]
+        L.gator_lbs_workspace_bytes.restype = C.c_size_t
+        L.gator_lbs_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+        L.gator_mano_pose.restype = C.c_int
+        L.gator_mano_pose.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
         L.gator_launch_count.restype = C.c_longlong
         L.gator_launch_count.argtypes = [C.c_int]
         L.gator_mdr_self_attention.restype = C.c_int

@@ -44,6 +44,8 @@ extern "C" size_t gator_abi_sizeof(int which) {
     case 6: return sizeof(gator_pose2d_args);
     case 7: return sizeof(gator_smpl_cam_args);
     case 8: return sizeof(gator_upsample2_args);
+    case 9: return sizeof(gator_lbs_args);
+    case 10: return sizeof(gator_mano_post_args);
     default: return 0;
   }
 }

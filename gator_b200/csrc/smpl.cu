@@ -48,6 +48,8 @@ struct PoseParams {
   int batch;
   int center_idx;
   float out_scale;          // applied to jtr after the translation
+  int nj;                   // joints (24 for SMPL, 16 for MANO; <= 32: one lane per joint)
+  int kb;                   // row length of aop: 10 + 9 (nj - 1), zero-padded to a multiple of 4
 };
 
 __global__ void __launch_bounds__(128)
@@ -58,12 +60,13 @@ smpl_pose_kernel(PoseParams p) {
   const bool use_betas = p.betas && (!p.flags || p.flags[0]);
   const bool use_trans = p.trans && (!p.flags || p.flags[1]);
   const float* beta = use_betas ? p.betas + (size_t)b * 10 : p.def_betas;
+  const int NJ = p.nj, KB = p.kb;          // (shadow the SMPL constants: the kernel serves any LBS model of <= 32 joints)
   const int i = lane < NJ ? lane : NJ - 1;
 
   // --- Rodrigues: axis-angle -> unit quaternion -> rotation matrix ---
-  const float ax = p.pose[(size_t)b * 72 + i * 3 + 0];
-  const float ay = p.pose[(size_t)b * 72 + i * 3 + 1];
-  const float az = p.pose[(size_t)b * 72 + i * 3 + 2];
+  const float ax = p.pose[((size_t)b * NJ + i) * 3 + 0];
+  const float ay = p.pose[((size_t)b * NJ + i) * 3 + 1];
+  const float az = p.pose[((size_t)b * NJ + i) * 3 + 2];
   const float ex = ax + 1e-8f, ey = ay + 1e-8f, ez = az + 1e-8f;
   const float angle = sqrtf(ex * ex + ey * ey + ez * ez);
   const float nx = ax / angle, ny = ay / angle, nz = az / angle;
@@ -86,7 +89,10 @@ smpl_pose_kernel(PoseParams p) {
 #pragma unroll
     for (int e = 0; e < 9; ++e) arow[10 + (lane - 1) * 9 + e] = R[e] - ((e == 0 || e == 4 || e == 8) ? 1.0f : 0.0f);
   }
-  if (lane >= NJ && lane < NJ + 3) arow[217 + lane - NJ] = 0.f;
+  {
+    const int used = 10 + 9 * (NJ - 1);    // 217 for SMPL, 145 for MANO
+    if (lane < KB - used) arow[used + lane] = 0.f;
+  }
 
   // --- rest joints: J_regressor @ (T + S beta) with the regressor pre-applied to T and S ---
   float j[3];
@@ -170,8 +176,9 @@ constexpr int SK_PD = 4;    // prefetch depth (samples)
 __global__ void __launch_bounds__(SK_VT)
 smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ amat, const float* __restrict__ offset,
                  const int* __restrict__ sidx, const float* __restrict__ sw, int KW, float* __restrict__ verts, int batch,
-                 float out_scale) {
-  __shared__ float sA[SK_SG][12 * NJ];   // component-major [e][joint]: lanes reading different joints hit different banks
+                 float out_scale, int nv, int nj, int ld) {
+  const int NV = nv, NJ = nj, NV3 = nv * 3, VP_LD = ld;   // (shadow the SMPL constants: any model with nj <= 24, nv even)
+  __shared__ float sA[SK_SG][12 * GATOR_SMPL_JOINTS];   // component-major [e][joint]: lanes reading different joints hit different banks
   __shared__ float soff[SK_SG][4];
   __shared__ __align__(16) float stage[SK_VT / 32][96];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -260,11 +267,7 @@ smpl_skin_kernel(const float* __restrict__ vposed, const float* __restrict__ ama
 // 8192 -> 1.64: the persistent blend-shape GEMM needs many tiles per CTA to fill its waves, and keeping v_posed
 // L2-resident with small chunks does not pay.  (Numbers taken with the CUDA-core skinning kernel and 4 epilogue warps
 // in the GEMM; with the tensor-core skinning kernel of smpl_skin_umma.cu and 8-16 epilogue warps the same batch takes 1.05 ms.)
-static int chunk_samples() {
-  static const int v = [] { const char* e = getenv("GATOR_SMPL_CHUNK"); const int c = e ? atoi(e) : 0; return c >= 20 && c <= 65536 ? c : 8192; }();
-  return v;
-}
-#define kChunk chunk_samples()
+constexpr int kChunk = 8192;
 
 struct Ws {
   float *aop, *amat, *offset, *vposed;
@@ -346,6 +349,8 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     p.batch = nb;
     p.center_idx = a->center_idx;
     p.out_scale = out_scale;
+    p.nj = NJ;
+    p.kb = KB;
     smpl_pose_kernel<<<ceil_div(nb, 4), 128, 0, stream>>>(p);
     GATOR_TRY(check_launch("smpl_pose"));
     Epilogue e;
@@ -361,9 +366,103 @@ extern "C" int gator_smpl_forward(const gator_smpl_args* a, void* stream_) {
     } else {
       dim3 grid(ceil_div(NV, SK_VT), ceil_div(nb, SK_SG));
       smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w,
-                                                   a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb, out_scale);
+                                                   a->weights_per_vertex, a->verts + (size_t)b0 * NV3, nb, out_scale, NV, NJ, VP_LD);
       GATOR_TRY(check_launch("smpl_skin"));
     }
+  }
+  return GATOR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Any body model shaped like SMPL (MANO: 778 vertices, 16 joints, 145 blend terms - manopth/manolayer.py:170-230 is the
+// same arithmetic as smpl_layer.py:87-145) on the fp32 kernels above: pose kernel -> FFMA blend-shape GEMM -> skinning.
+// ---------------------------------------------------------------------------------------------
+namespace gator {
+namespace {
+struct LbsWs { float *aop, *amat, *offset, *vposed; int* flags; size_t bytes; int ld; };
+LbsWs carve_lbs(char* base, int nb, int nv, int nj, int kb) {
+  LbsWs w;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* p = base ? base + off : nullptr; off += align_up(bytes, 256); return p; };
+  w.ld = (nv * 3 + 3) & ~3;
+  w.flags = reinterpret_cast<int*>(take(16));
+  w.aop = reinterpret_cast<float*>(take((size_t)nb * kb * 4));
+  w.amat = reinterpret_cast<float*>(take((size_t)nb * nj * 12 * 4));
+  w.offset = reinterpret_cast<float*>(take((size_t)nb * 3 * 4));
+  w.vposed = reinterpret_cast<float*>(take((size_t)nb * w.ld * 4));
+  w.bytes = off;
+  return w;
+}
+bool lbs_dims_ok(int nv, int nj, int kb) {
+  return nv >= 2 && nv % 2 == 0 && nj >= 2 && nj <= GATOR_SMPL_JOINTS && kb == ((10 + 9 * (nj - 1) + 3) & ~3);
+}
+}  // namespace
+}  // namespace gator
+
+extern "C" size_t gator_lbs_workspace_bytes(int32_t batch, int32_t n_verts, int32_t n_joints) {
+  using namespace gator;
+  const int kb = (10 + 9 * (n_joints - 1) + 3) & ~3;
+  if (batch <= 0 || !lbs_dims_ok(n_verts, n_joints, kb)) return 0;
+  return carve_lbs(nullptr, batch < kChunk ? batch : kChunk, n_verts, n_joints, kb).bytes;
+}
+
+extern "C" int gator_lbs_forward(const gator_lbs_args* a, void* stream_) {
+  using namespace gator;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  GATOR_REQUIRE(a, "gator_lbs_forward: null args");
+  const int B = a->batch, nv = a->n_verts, nj = a->n_joints, kb = a->k_blend;
+  GATOR_REQUIRE(lbs_dims_ok(nv, nj, kb), "gator_lbs_forward: need an even vertex count, 2..24 joints and k_blend = 10 + 9 (joints - 1) rounded up to a multiple of 4");
+  if (B == 0) return GATOR_OK;
+  GATOR_REQUIRE(B > 0 && a->pose && a->verts && a->jtr, "gator_lbs_forward: null buffer");
+  GATOR_REQUIRE(a->parents && a->j_template && a->j_shapedirs && a->default_betas && a->blend_w && a->v_template && a->skin_idx &&
+                    a->skin_w, "gator_lbs_forward: null model buffer");
+  GATOR_REQUIRE(a->weights_per_vertex >= 1 && a->weights_per_vertex <= nj, "gator_lbs_forward: bad weights_per_vertex");
+  GATOR_REQUIRE(a->center_idx >= -1 && a->center_idx < nj, "gator_lbs_forward: bad center_idx");
+  GATOR_REQUIRE(!a->has_betas || a->betas, "gator_lbs_forward: has_betas without betas");
+  GATOR_REQUIRE(!a->has_trans || a->trans, "gator_lbs_forward: has_trans without trans");
+  const size_t need = gator_lbs_workspace_bytes(B, nv, nj);
+  if (!a->workspace || a->workspace_bytes < need) {
+    set_error("gator_lbs_forward: workspace %zu < %zu bytes", a->workspace_bytes, need);
+    return GATOR_ERR_WORKSPACE;
+  }
+  const int cb = B < kChunk ? B : kChunk;
+  const float out_scale = a->out_scale == 0.f ? 1.f : a->out_scale;
+  LbsWs w = carve_lbs(static_cast<char*>(a->workspace), cb, nv, nj, kb);
+  const bool flags = a->check_zero_norm && (a->has_betas || a->has_trans);
+  if (flags) {
+    smpl_flags_kernel<<<1, 256, 0, stream>>>(a->has_betas ? a->betas : nullptr, a->has_betas ? B * 10 : 0,
+                                             a->has_trans ? a->trans : nullptr, a->has_trans ? B * 3 : 0, w.flags);
+    GATOR_TRY(check_launch("smpl_flags"));
+  }
+  for (int b0 = 0; b0 < B; b0 += cb) {
+    const int nb = (B - b0 < cb) ? B - b0 : cb;
+    PoseParams p;
+    p.pose = a->pose + (size_t)b0 * nj * 3;
+    p.betas = a->has_betas ? a->betas + (size_t)b0 * 10 : nullptr;
+    p.trans = a->has_trans ? a->trans + (size_t)b0 * 3 : nullptr;
+    p.def_betas = a->default_betas;
+    p.jt = a->j_template;
+    p.js = a->j_shapedirs;
+    p.parents = a->parents;
+    p.flags = flags ? w.flags : nullptr;
+    p.aop = w.aop;
+    p.amat = w.amat;
+    p.offset = w.offset;
+    p.jtr = a->jtr + (size_t)b0 * nj * 3;
+    p.batch = nb;
+    p.center_idx = a->center_idx;
+    p.out_scale = out_scale;
+    p.nj = nj;
+    p.kb = kb;
+    smpl_pose_kernel<<<ceil_div(nb, 4), 128, 0, stream>>>(p);
+    GATOR_TRY(check_launch("smpl_pose"));
+    Epilogue e;
+    e.bias = a->v_template;
+    GATOR_TRY(gemm(GATOR_PREC_FP32, w.aop, kb, a->blend_w, kb, PackedW{nullptr, nullptr}, w.vposed, w.ld, nb, nv * 3, kb, e, stream));
+    dim3 grid(ceil_div(nv, SK_VT), ceil_div(nb, SK_SG));
+    smpl_skin_kernel<<<grid, SK_VT, 0, stream>>>(w.vposed, w.amat, w.offset, a->skin_idx, a->skin_w, a->weights_per_vertex,
+                                                 a->verts + (size_t)b0 * nv * 3, nb, out_scale, nv, nj, w.ld);
+    GATOR_TRY(check_launch("smpl_skin"));
   }
   return GATOR_OK;
 }

@@ -4,7 +4,7 @@
 
 After this ``models.GATOR.get_model`` (lib/core/base.py:57, demo/run.py:96), ``models.GAT.get_model``
 (base.py:59), ``models.MDR.get_model``, ``smplpytorch.pytorch.smpl_layer.SMPL_Layer`` (lib/smpl.py:8) and
-``models.backbones.mesh.Mesh`` resolve to gator_b200's modules; constructor signatures, state_dict keys
+``models.backbones.mesh.Mesh`` and ``manopth.manolayer.ManoLayer`` resolve to gator_b200's modules; constructor signatures, state_dict keys
 and return values are identical, so ``model.load_state_dict(checkpoint['model_state_dict'])`` works.
 """
 from __future__ import annotations
@@ -14,7 +14,7 @@ import sys
 
 
 def install(verbose: bool = False):
-    from . import mesh as b_mesh, smpl_layer as b_smpl
+    from . import mano_layer as b_mano, mesh as b_mesh, smpl_layer as b_smpl
     from .models import GAT as b_GAT, GATOR as b_GATOR, MDR as b_MDR
     done = []
 
@@ -33,6 +33,7 @@ def install(verbose: bool = False):
     rebind('models.backbones.mesh', {'Mesh': b_mesh.Mesh})
     rebind('smplpytorch.pytorch.smpl_layer', {'SMPL_Layer': b_smpl.SMPL_Layer})
     rebind('smpl', {'SMPL_Layer': b_smpl.SMPL_Layer})
+    rebind('manopth.manolayer', {'ManoLayer': b_mano.ManoLayer})
     if verbose:
         print('gator_b200.install: rebound', ', '.join(done))
     return done

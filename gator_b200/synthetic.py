@@ -261,6 +261,52 @@ def smpl_buffers() -> Dict[str, np.ndarray]:
     }
 
 
+MANO_PARENTS = [-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14]
+MANO_VERTS = 778
+
+
+def mano_data() -> Dict[str, np.ndarray]:
+    """Synthetic arrays with the shapes ManoLayer.__init__ reads from the MANO pkl (manolayer.py:62-103): a hand-sized
+    template (~0.1 m), 10 shape and 135 pose blend shapes, 16-joint regressor and skinning weights, the 45 x 45 PCA
+    basis of the finger poses and its mean."""
+    r = _rng('mano_model')
+    nv = MANO_VERTS
+    jreg = np.zeros((16, nv), np.float32)
+    for j in range(16):
+        cols = r.choice(nv, size=12, replace=False)
+        w = r.random(12) + 0.1
+        jreg[j, cols] = (w / w.sum()).astype(np.float32)
+    weights = np.zeros((nv, 16), np.float32)
+    for v in range(nv):
+        cols = r.choice(16, size=4, replace=False)
+        w = r.random(4) + 0.05
+        weights[v, cols] = (w / w.sum()).astype(np.float32)
+    q, _ = np.linalg.qr(r.standard_normal((45, 45)))
+    return {
+        'betas': np.zeros(10, np.float32),
+        'shapedirs': (r.standard_normal((nv, 3, 10)) * 0.003).astype(np.float32),
+        'posedirs': (r.standard_normal((nv, 3, 135)) * 0.0005).astype(np.float32),
+        'v_template': (r.standard_normal((nv, 3)) * np.array([0.04, 0.02, 0.06])).astype(np.float32),
+        'J_regressor': jreg,
+        'weights': weights,
+        'f': r.integers(0, nv, size=(1538, 3)).astype(np.int64),
+        'hands_components': (q * np.linspace(1.5, 0.05, 45)[:, None]).astype(np.float32),
+        'hands_mean': (r.standard_normal(45) * 0.2).astype(np.float32),
+        'kintree_table': np.stack([np.asarray([4294967295] + MANO_PARENTS[1:], dtype=np.int64), np.arange(16)]),
+    }
+
+
+def mano_inputs(batch: int, ncomps: int = 6, seed: int = 5):
+    """pose coefficients (B, 3 + ncomps): root axis-angle U(-1,1) (row 0 all zero, row 1 with |a| > pi) and PCA
+    coefficients N(0,1); betas N(0,1); trans N(0, 0.1)."""
+    r = np.random.default_rng(1000 + seed)
+    pose = np.concatenate([r.uniform(-1, 1, (batch, 3)), r.standard_normal((batch, ncomps))], 1).astype(np.float32)
+    pose[0] = 0.0
+    if batch > 1:
+        pose[1, :3] = (2.1, -2.0, 1.9)
+    return pose, r.standard_normal((batch, 10)).astype(np.float32), (r.standard_normal((batch, 3)) * 0.1).astype(np.float32)
+
+
 def smpl_inputs(batch: int, seed: int = 3):
     """pose U(-0.2,0.2) incl. an all-zero row and a row with |a| > pi; betas N(0,1); trans N(0,1)."""
     r = _rng('smpl_inputs', seed)

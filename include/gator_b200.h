@@ -49,7 +49,7 @@ typedef enum {
 int gator_abi_version(void);
 const char* gator_last_error(void);
 /* sizeof() of the ABI structs as compiled, so the ctypes mirror can be verified at load time:
- * which = 0 gat, 1 mdr, 2 smpl, 3 csr, 4 gemm, 5 eval, 6 pose2d, 7 smpl_cam, 8 upsample2 */
+ * which = 0 gat, 1 mdr, 2 smpl, 3 csr, 4 gemm, 5 eval, 6 pose2d, 7 smpl_cam, 8 upsample2, 9 lbs, 10 mano_post */
 size_t gator_abi_sizeof(int which);
 /* number of kernels this library has launched (process-wide); reset != 0 zeroes it after reading.
  * bench.py reports it as `gpu_launches`. */
@@ -264,6 +264,73 @@ typedef struct {
 
 size_t gator_smpl_workspace_bytes(int32_t batch);
 int gator_smpl_forward(const gator_smpl_args* a, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Any body model shaped like SMPL on the fp32 kernels - used for the MANO hand layer
+ * (manopth/manopth/manolayer.py:170-230 is the arithmetic of smpl_layer.py:87-145 with 778 vertices, 16 joints and
+ * 10 + 135 blend terms).  Same meaning of every field as gator_smpl_args; dimensions are arguments:
+ * n_verts even, n_joints in [2, 24], k_blend = 10 + 9 (n_joints - 1) rounded up to a multiple of 4.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t batch;
+  int32_t n_verts;
+  int32_t n_joints;
+  int32_t k_blend;
+  int32_t center_idx;          /* -1 = None; a chain joint                                */
+  int32_t has_betas;
+  int32_t has_trans;
+  int32_t check_zero_norm;     /* 1: `norm(x)==0` switches of smpl_layer.py:87,148 on device */
+  int32_t weights_per_vertex;
+  float out_scale;             /* 0 = 1.0                                                 */
+  const int32_t* parents;      /* (n_joints) DEVICE int32, parents[0] ignored             */
+  const float* j_template;     /* (n_joints,3)    J_regressor @ v_template                */
+  const float* j_shapedirs;    /* (n_joints,3,10) J_regressor @ shapedirs                 */
+  const float* default_betas;  /* (10)                                                    */
+  const float* blend_w;        /* (n_verts*3, k_blend) [shapedirs | posedirs | 0]         */
+  const float* v_template;     /* (n_verts*3)                                             */
+  const int32_t* skin_idx;     /* (n_verts, weights_per_vertex)                           */
+  const float* skin_w;         /* (n_verts, weights_per_vertex)                           */
+  const float* pose;           /* (B, n_joints*3) axis-angle                              */
+  const float* betas;          /* (B,10) or NULL                                          */
+  const float* trans;          /* (B,3) or NULL                                           */
+  float* verts;                /* (B,n_verts,3)                                           */
+  float* jtr;                  /* (B,n_joints,3)                                          */
+  void* workspace;
+  size_t workspace_bytes;
+} gator_lbs_args;
+
+size_t gator_lbs_workspace_bytes(int32_t batch, int32_t n_verts, int32_t n_joints);
+int gator_lbs_forward(const gator_lbs_args* a, void* stream);
+
+/* MANO pose pre-step (manolayer.py:128-143): full_pose (B,48) = [coeffs[:, :3] | hands_mean + coeffs[:, 3:3+ncomps] @ comps]
+ * (comps (ncomps,45); comps = NULL: use_pca = False with joint_rot_mode = 'axisang', coeffs holds the 45 axis-angle
+ * values).  `ld` = row stride of coeffs in floats. */
+int gator_mano_pose(const float* coeffs, int32_t ld, int32_t ncomps, const float* comps, const float* hands_mean,
+                    float* full_pose, int32_t batch, void* stream);
+
+/* MANO post-step (manolayer.py:232-256) on the outputs of gator_lbs_forward (metres, no translation): finger tips
+ * sampled from the vertices, optional palm root, re-ordering into the 21-joint convention, centring on joint
+ * `center_idx` of that convention or translation by `trans`, then `scale` (1000: metres -> millimetres) on vertices
+ * (in place) and joints. */
+typedef struct {
+  int32_t batch;
+  int32_t n_verts;             /* 778                                                     */
+  int32_t center_idx;          /* -1 = None; index into the 21 re-ordered joints          */
+  int32_t has_trans;
+  int32_t check_zero_norm;     /* 1: `norm(th_trans)==0` -> centre branch, decided on the device (needs flag_ws) */
+  int32_t root_palm;           /* 1: joint 0 = mean of the two palm vertices              */
+  int32_t tip_verts[5];        /* 745, 317, 444 (right) | 445 (left), 556, 673            */
+  int32_t palm_verts[2];       /* 95, 22                                                  */
+  float scale;                 /* 0 = 1.0                                                 */
+  int32_t reserved;
+  const float* jtr16;          /* (B,16,3) chain joints from gator_lbs_forward            */
+  const float* trans;          /* (B,3) or NULL                                           */
+  float* verts;                /* (B,n_verts,3) in / out                                  */
+  float* jtr;                  /* (B,21,3) out                                            */
+  int32_t* flag_ws;            /* DEVICE, 4 bytes, or NULL                                */
+} gator_mano_post_args;
+
+int gator_mano_post(const gator_mano_post_args* a, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Ground-truth mesh generation, camera fix-up - the per-item host arithmetic of Human36M.get_smpl_coord

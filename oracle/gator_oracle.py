@@ -405,6 +405,70 @@ def smpl_forward(buf: Dict[str, torch.Tensor], parents: Sequence[int], pose, bet
     return verts, jtr, {'v_posed': v_posed, 'th_j': th_j, 'rotmats': torch.cat([root_rot.reshape(B, 9), rot], 1)}
 
 
+MANO_PARENTS = (-1, 0, 1, 2, 0, 4, 5, 0, 7, 8, 0, 10, 11, 0, 13, 14)
+MANO_JOINT_ORDER = (0, 13, 14, 15, 16, 1, 2, 3, 17, 4, 5, 6, 18, 10, 11, 12, 19, 7, 8, 9, 20)
+
+
+def mano_forward(buf: Dict[str, torch.Tensor], pose_coeffs, betas=None, trans=None, *, ncomps=6, use_pca=True, side='right',
+                 center_idx=None, root_palm=False, share_betas=False):
+    """manopth/manopth/manolayer.py:109-273 for root_rot_mode = joint_rot_mode = 'axisang' (+ manopth/tensutils.py).
+    buf: th_betas, th_shapedirs, th_posedirs, th_v_template, th_J_regressor, th_weights, th_hands_mean,
+    th_selected_comps.  Returns (verts (B,778,3), jtr (B,21,3)) in millimetres."""
+    B = pose_coeffs.shape[0]
+    dt = pose_coeffs.dtype
+    hand = pose_coeffs[:, 3:3 + ncomps]                                                  # :130-131
+    full_hand = hand.mm(buf['th_selected_comps'].to(dt)) if use_pca else hand            # :132-136
+    full_pose = torch.cat([pose_coeffs[:, :3], buf['th_hands_mean'].to(dt) + full_hand], 1)   # :139-142
+    rot = batch_rodrigues(full_pose.contiguous().view(-1, 3)).view(B, 16 * 9)            # tensutils.py:6-12
+    pose_map = (rot - torch.eye(3, dtype=dt).view(1, 9).repeat(B, 16))[:, 9:]            # tensutils.py:31-39, :147
+    root_rot = rot[:, :9].view(B, 3, 3)
+    rot = rot[:, 9:]
+    S, P = buf['th_shapedirs'].to(dt), buf['th_posedirs'].to(dt)
+    T, Jr, W = buf['th_v_template'].to(dt), buf['th_J_regressor'].to(dt), buf['th_weights'].to(dt)
+    if betas is None or betas.numel() == 1:                                              # :172-178
+        v_shaped = torch.matmul(S, buf['th_betas'].to(dt).transpose(1, 0)).permute(2, 0, 1) + T
+        th_j = torch.matmul(Jr, v_shaped).repeat(B, 1, 1)
+    else:
+        if share_betas:
+            betas = betas.mean(0, keepdim=True).expand(betas.shape[0], 10)
+        v_shaped = torch.matmul(S, betas.transpose(1, 0)).permute(2, 0, 1) + T
+        th_j = torch.matmul(Jr, v_shaped)
+    v_posed = v_shaped + torch.matmul(P, pose_map.transpose(0, 1)).permute(2, 0, 1)      # :188-189
+
+    def with_zeros(t):
+        pad = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=dt).view(1, 1, 4).repeat(t.shape[0], 1, 1)
+        return torch.cat([t, pad], 1)
+    # :194-231: the three finger levels are the kinematic tree MANO_PARENTS walked breadth first
+    results = [with_zeros(torch.cat([root_rot, th_j[:, 0, :].contiguous().view(B, 3, 1)], 2))]
+    for i in range(1, 16):
+        par = MANO_PARENTS[i]
+        jr = rot[:, (i - 1) * 9:i * 9].contiguous().view(B, 3, 3)
+        rel = with_zeros(torch.cat([jr, (th_j[:, i, :] - th_j[:, par, :]).view(B, 3, 1)], 2))
+        results.append(torch.matmul(results[par], rel))
+    th_results = torch.stack(results, 1)                                                 # (B,16,4,4), joint order (:229-230)
+    joint_js = torch.cat([th_j, th_j.new_zeros(B, 16, 1)], 2)
+    tmp2 = torch.matmul(th_results, joint_js.unsqueeze(3))
+    res2 = (th_results - torch.cat([tmp2.new_zeros(B, 16, 4, 3), tmp2], 3)).permute(0, 2, 3, 1)   # :233-235
+    th_T = torch.matmul(res2, W.transpose(0, 1))
+    rest_h = torch.cat([v_posed.transpose(2, 1), torch.ones((B, 1, v_posed.shape[1]), dtype=dt)], 1)
+    verts = (th_T * rest_h.unsqueeze(1)).sum(2).transpose(2, 1)[:, :, :3]
+    jtr = th_results[:, :, :3, 3]
+    tips = verts[:, [745, 317, 444 if side == 'right' else 445, 556, 673]]               # :249-252
+    if root_palm:
+        palm = (verts[:, 95] + verts[:, 22]).unsqueeze(1) / 2
+        jtr = torch.cat([palm, jtr[:, 1:]], 1)
+    jtr = torch.cat([jtr, tips], 1)[:, list(MANO_JOINT_ORDER)]                           # :256-259
+    if trans is None or bool(torch.norm(trans) == 0):                                    # :261-268
+        if center_idx is not None:
+            cj = jtr[:, center_idx].unsqueeze(1)
+            jtr = jtr - cj
+            verts = verts - cj
+    else:
+        jtr = jtr + trans.unsqueeze(1)
+        verts = verts + trans.unsqueeze(1)
+    return verts * 1000, jtr * 1000                                                      # :271-272
+
+
 # ----------------------------------------------------------------------------------------------
 # evaluation helpers restated for the drift metric (not on the hot path)
 # ----------------------------------------------------------------------------------------------

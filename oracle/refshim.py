@@ -161,6 +161,45 @@ def build_smpl_layer(buffers, center_idx=None):
     return layer.eval()
 
 
+def build_mano_layer(data, center_idx=None, ncomps=6, use_pca=True, side='right', flat_hand_mean=True):
+    """Reference ManoLayer with __init__ bypassed (it needs chumpy + the licensed MANO pkl, manolayer.py:62-103): the
+    buffers and attributes __init__ would set are filled from `data` (gator_b200.synthetic.mano_data), then the
+    reference ``forward`` runs unmodified.  `mano.webuser.smpl_handpca_wrapper_HAND_only` (imports chumpy at module
+    level) is stubbed - only its ``ready_arguments`` name is needed for the import of manolayer.py to succeed."""
+    import numpy as np
+    import torch
+    install_shims()
+    if os.path.join(REF, 'manopth') not in sys.path:
+        sys.path.insert(0, os.path.join(REF, 'manopth'))
+    for name in ('mano', 'mano.webuser', 'mano.webuser.smpl_handpca_wrapper_HAND_only'):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__path__ = []
+            m.ready_arguments = lambda *a, **k: (_ for _ in ()).throw(RuntimeError('pkl loader unavailable'))
+            sys.modules[name] = m
+    from manopth.manolayer import ManoLayer
+    layer = ManoLayer.__new__(ManoLayer)
+    torch.nn.Module.__init__(layer)
+    layer.center_idx, layer.robust_rot, layer.rot = center_idx, False, 3
+    layer.flat_hand_mean, layer.side, layer.use_pca = flat_hand_mean, side, use_pca
+    layer.joint_rot_mode = layer.root_rot_mode = 'axisang'
+    layer.ncomps = ncomps if use_pca else 45
+    T = lambda a: torch.Tensor(np.asarray(a, dtype=np.float32))
+    layer.register_buffer('th_betas', T(data['betas']).unsqueeze(0))
+    layer.register_buffer('th_shapedirs', T(data['shapedirs']))
+    layer.register_buffer('th_posedirs', T(data['posedirs']))
+    layer.register_buffer('th_v_template', T(data['v_template']).unsqueeze(0))
+    layer.register_buffer('th_J_regressor', T(data['J_regressor']))
+    layer.register_buffer('th_weights', T(data['weights']))
+    layer.register_buffer('th_faces', torch.as_tensor(np.asarray(data['f']).astype(np.int32)).long())
+    mean = np.zeros(45, np.float32) if flat_hand_mean else np.asarray(data['hands_mean'], np.float32)
+    layer.register_buffer('th_hands_mean', T(mean).unsqueeze(0))
+    layer.register_buffer('th_selected_comps', T(np.asarray(data['hands_components'])[:ncomps]))
+    layer.kintree_table = np.asarray(data['kintree_table'])
+    layer.kintree_parents = list(layer.kintree_table[0].tolist())
+    return layer.eval()
+
+
 def ref_mesh(root: str):
     import torch
     install_shims()
