@@ -288,6 +288,18 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
           }
         }
       }
+      if (tid == 0 && it + 1 < n_my) {
+        // the next tile's rows of x (and att) are 128 consecutive 256-byte rows: two bulk prefetches bring them from HBM
+        // into L2 while this tile computes, so the loads at the top of the next iteration do not pay the DRAM latency
+        // (issued before the FINAL pass branches off: that pass is little more than these loads - without the prefetch it
+        //  ran at 3.1 TB/s with 77 % of its stall samples on the scoreboard, profiles/r02_ncu_top_kernels.txt)
+        const long long r0 = (long long)(tile + gridDim.x) * 128;
+        const long long nr = (p.rows_total - r0 < 128) ? p.rows_total - r0 : 128;
+        if (nr > 0) {
+          if (p.x_in) bulk_prefetch_l2(p.x_in + r0 * E, (uint32_t)(nr * E * 4));
+          if (has_so) bulk_prefetch_l2(p.att_in + r0 * E, (uint32_t)(nr * E * 4));
+        }
+      }
       auto store_x = [&]() {                         // x (registers) -> my half of the accumulator columns
         uint32_t r[32];
 #pragma unroll
@@ -345,16 +357,6 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
         }
         write_a(v);
         submit(S_Q);
-      }
-      if (tid == 0 && it + 1 < n_my) {
-        // the next tile's rows of x (and att) are 128 consecutive 256-byte rows: two bulk prefetches bring them from HBM
-        // into L2 while this tile computes, so the loads at the top of the next iteration do not pay the DRAM latency
-        const long long r0 = (long long)(tile + gridDim.x) * 128;
-        const long long nr = (p.rows_total - r0 < 128) ? p.rows_total - r0 : 128;
-        if (nr > 0) {
-          if (p.x_in) bulk_prefetch_l2(p.x_in + r0 * E, (uint32_t)(nr * E * 4));
-          if (has_so) bulk_prefetch_l2(p.att_in + r0 * E, (uint32_t)(nr * E * 4));
-        }
       }
       cp_async_wait_all();
       named_sync(1, NCOMP * 32);                     // K|V staged (every thread's copies landed)

@@ -160,6 +160,11 @@ umma_gemm_wide_kernel(WideParams p) {
       for (int slab = grp; slab < WBN / 32; slab += EPI_GROUPS) {
         const int nb = n0 + slab * 32;
         if (nb >= p.N) break;                          // uniform over the group
+        // (the bias of this thread's four columns is requested before the accumulator is read: its L2 latency used to
+        //  sit between the staging barrier and the first store)
+        const int c4v = (lane & 7) * 4;
+        float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.vec && e.bias && nb + c4v + 3 < p.N) bn = __ldg(reinterpret_cast<const float4*>(e.bias + nb + c4v));
         float v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * WBN + slab * 32, v);
         tmem_ld_wait();
@@ -183,15 +188,16 @@ umma_gemm_wide_kernel(WideParams p) {
           const int c4 = (lane & 7) * 4, n = nb + c4;
           const int rs = gw * 4 + (lane >> 3);
           if (n + 3 < p.N) {
-            const float4 bn = e.bias ? __ldg(reinterpret_cast<const float4*>(e.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+            // all eight row segments are read before the first store: with one load / add / store per iteration the
+            // compiler reused one register quad and every load waited for the previous store to drain
+            float4 x[WBM / 16];
+#pragma unroll
+            for (int i = 0; i < WBM / 16; ++i) x[i] = *reinterpret_cast<const float4*>(stg + stg_idx(rs + i * 16, c4));
 #pragma unroll
             for (int i = 0; i < WBM / 16; ++i) {
-              const int r = rs + i * 16, m = m0 + r;
-              if (m < p.M) {
-                float4 x = *reinterpret_cast<const float4*>(stg + stg_idx(r, c4));
-                x.x += bn.x; x.y += bn.y; x.z += bn.z; x.w += bn.w;
-                *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = x;
-              }
+              const int m = m0 + rs + i * 16;
+              if (m < p.M)
+                *reinterpret_cast<float4*>(p.C + (size_t)m * p.ldc + n) = make_float4(x[i].x + bn.x, x[i].y + bn.y, x[i].z + bn.z, x[i].w + bn.w);
             }
           } else {
             for (int i = 0; i < WBM / 16; ++i) {
