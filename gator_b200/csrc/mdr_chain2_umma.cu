@@ -64,8 +64,8 @@ struct Chain2Params {
   float* x3_out;          // (nb*431, 64)
   float* qkv_out;         // optional (nb*431, 192) fp32 q|k|v
   uint8_t* img_out;       // optional fp16 [Q | K | V] operand images, one 3 x 27 648-byte record per (sample, head)
-  float* hd_out;          // non-null: FINAL pass - x = x_in + att_in Wo^T + b, hd = x W_head^T + b_head (nb*431, 28);
-                          // blob = [linears[3] of the last layer, head (28 rows zero-padded to 64)], prm[0] = so_b, prm[1] = head_b
+  float* hd_out;          // non-null: FINAL pass - hd = (x_in + att_in Wo^T + b_o) W_head^T + b_head (nb*431, 28), folded;
+                          // blob = [head Wh (28 rows zero-padded to 64), Wh Wo, 64 floats of folded bias Wh b_o + b_h]
   int J;
   long long rows_total;   // nb * 431
   int ntiles;
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
       case S_MID: from_w(0); from_w(1); from_a(C_W, false); from_a(C_W + 64, false); break;   // x += fc2 half 0; fc1 quarters 2, 3
       case S_FC2B: from_w(0); from_w(1); break;                                               // x += fc2 half 1
       case S_QKV: from_a(C_X, false); from_a(C_W, false); from_a(C_W + 64, false); break;     // q | k | v into columns [0, 192)
-      default: from_a(C_W, false); break;                                                     // S_HEAD
+      default: from_a(C_X, false); unit_mma(C_X, true, C_W, 16, 32); break;                   // S_HEAD: hd = x3 Wh^T + att (Wh Wo)^T
     }
     if (elect_one()) mma_commit(&bars.d_ready);
     __syncwarp();
@@ -306,6 +306,40 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
         for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(x[i]);
         tmem_st32(t_x, r);
       };
+      if (final_pass) {
+        // FINAL pass: hd = (x3 + att Wo^T + b_o) Wh^T + b_h = x3 Wh^T + att (Wh Wo)^T + (Wh b_o + b_h) - the composite
+        // weight and bias are folded at pack time (gator_b200/models/MDR.py), so the pass is ONE MMA group (two K = 64
+        // units into the same accumulator) and x is never materialised: [motion_linear | bias_linear | scale_linear] (MDR.py:156-162)
+        const float4* src = reinterpret_cast<const float4*>(p.att_in + grow * E + c0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 t = valid ? __ldg(src + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+        }
+        write_a(x);                                  // x3 -> A region (K = 64)
+        {
+          uint32_t hi[16], lo[16];                   // att -> work columns, 32-column group `ch`: [hi 16 | lo 16]
+          split32(v, hi, lo);
+          const uint32_t taddr = tmem + lane_addr + C_W + ch * 32;
+          tmem_st16(taddr, hi);
+          tmem_st16(taddr + 16, lo);
+        }
+        submit(S_HEAD);
+        await();
+        if (ch == 0) {
+          ld32f(tmem + lane_addr + C_X, v);
+          if (valid) {
+            const float* hb = reinterpret_cast<const float*>(p.blob + 2 * UNIT_BYTES);   // folded bias behind the two units
+            float* dst = p.hd_out + grow * 28;
+#pragma unroll
+            for (int i = 0; i < 28; i += 4) {
+              const float4 bb = __ldg(reinterpret_cast<const float4*>(hb + i));
+              *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
+            }
+          }
+        }
+        continue;
+      }
       store_x();
       if (has_so) {
         const float4* src = reinterpret_cast<const float4*>(p.att_in + grow * E + c0);
@@ -324,25 +358,7 @@ __global__ void __launch_bounds__(NT, 2) mdr_chain2_kernel(Chain2Params p) {
           const float4 t = prm4(P_SO_B, c0 + 4 * i);
           x[4 * i] += t.x; x[4 * i + 1] += t.y; x[4 * i + 2] += t.z; x[4 * i + 3] += t.w;
         }
-        if (!final_pass) store_x();
-      }
-      if (final_pass) {
-        // x = x3 + linears[3](att) + b is complete: MDR head projection [motion_linear | bias_linear | scale_linear] (MDR.py:156-162)
-        write_a(x);
-        submit(S_HEAD);
-        await();
-        if (ch == 0) {
-          ld32f(tmem + lane_addr + C_W, v);
-          if (valid) {
-            float* dst = p.hd_out + grow * 28;
-#pragma unroll
-            for (int i = 0; i < 28; i += 4) {
-              const float4 bb = prm4(P_N1W, i);
-              *reinterpret_cast<float4*>(dst + i) = make_float4(v[i] + bb.x, v[i + 1] + bb.y, v[i + 2] + bb.z, v[i + 3] + bb.w);
-            }
-          }
-        }
-        continue;
+        store_x();
       }
       // ---- LayerNorm1 -> q ----
       {

@@ -213,9 +213,15 @@ class MDR(nn.Module):
             l['CHAIN'] = pack_umma_blob(units)
             prev_so = l['SO_W']
             layer_dicts.append(l)
+        # FINAL pass of the fused kernel: hd = (x3 + att Wo^T + b_o) Wh^T + b_h, folded (in fp64) into two K = 64 units
+        # [Wh, Wh Wo] and one bias Wh b_o + b_h stored behind them (MDR.py:153,156-162; vanilla_transformer_encoder.py:94)
         head64 = torch.zeros(E, E, device=dev)
         head64[:28] = t['HEAD_W']
-        t['CHAIN_FINAL'] = pack_umma_blob([prev_so, head64])
+        comp = (head64.double() @ prev_so.double()).float()
+        bias64 = torch.zeros(E, device=dev)
+        bias64[:28] = (t['HEAD_W'].double() @ layer_dicts[-1]['SO_B'].double() + t['HEAD_B'].double()).float()
+        t['CHAIN_FINAL'] = torch.cat([pack_umma_blob([head64, comp]).reshape(-1).view(torch.uint8),
+                                      bias64.contiguous().view(torch.uint8)]).contiguous()
         tensors = [t[n] for n in gnames]
         for l in layer_dicts:
             tensors += [l[n] for n in lnames]
