@@ -36,3 +36,18 @@ if which in ('all', 'eval'):
     pose = Pose2DPreprocessor((384, 288), COCO_MID_PAIRS)(torch.from_numpy(golden('preproc')['input'].astype(np.float32)).to(dev))
     torch.cuda.synchronize()
     print('eval', float(r.joint_error), float(r.pa_joint_error), float(pose.abs().max()))
+if which in ('all', 'mesh'):
+    from builders import base_data_root
+    from gator_b200.mesh import Mesh
+    mesh_op = Mesh(os.path.join(base_data_root(), 'data', 'base_data', 'mesh_downsampling.npz'), device=torch.device(dev))
+    xc = torch.randn(7, 431, 3, device=dev)
+    up = mesh_op.upsample(xc, n1=2, n2=0)          # fused two-level kernel, ragged last group
+    torch.cuda.synchronize()
+    print('upsample2', float(up.abs().max()))
+if which in ('all', 'mano'):
+    from gator_b200.mano_layer import ManoLayer
+    hand = ManoLayer(mano_data=synthetic.mano_data(), ncomps=6, center_idx=8).to(dev)
+    hp, hb, ht = [torch.from_numpy(a).to(dev) for a in synthetic.mano_inputs(21)]
+    v, j = hand(hp, hb, torch.zeros_like(ht))
+    torch.cuda.synchronize()
+    print('mano', float(v.abs().max()), float(j.abs().max()))
