@@ -241,18 +241,22 @@ mdr_self_attn_kernel(const float* __restrict__ qkv, float* __restrict__ out) {
 // bias branch norm + GELU + Conv1d(431->20,k3,p1), softmax(A) @ B, alpha scaling, + C; then the im2col
 // rows of upsample_conv's input (MDR.py:167).  One CTA per sample.
 // ---------------------------------------------------------------------------------------------
+constexpr int HD_NS = 4;   // samples per CTA: the 103 KB of Conv1d weights are read from L2 once per CTA and reused from
+                           // registers for its samples (one sample per CTA moved 423 MB through L2 per 4096 samples: 176 us)
 __global__ void __launch_bounds__(256)
 mdr_head_kernel(const float* __restrict__ hd, const float* __restrict__ nscale, const float* __restrict__ nshift,
                 const float* __restrict__ cw, const float* __restrict__ cb, int alpha, float* __restrict__ coarse_out,
-                float* __restrict__ a3) {
-  __shared__ float gB[V + 2][3];
-  __shared__ float matB[20][3];
-  __shared__ float sc[V][3];
-  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const float* hb = hd + (size_t)b * V * HEADN;
-  for (int v = tid; v < V; v += 256) {
+                float* __restrict__ a3, int nb) {
+  __shared__ float gB[HD_NS][V + 2][3];
+  __shared__ float matB[HD_NS][20][3];
+  __shared__ float sc[HD_NS][V][3];
+  const int b0 = blockIdx.x * HD_NS, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ns = min(HD_NS, nb - b0);
+  for (int i = tid; i < ns * V; i += 256) {
+    const int s = i / V, v = i - s * V;
+    const float* hb = hd + ((size_t)(b0 + s) * V + v) * HEADN;
     float y[3];
-    const float x0 = hb[v * HEADN + 23], x1 = hb[v * HEADN + 24], x2 = hb[v * HEADN + 25];
+    const float x0 = hb[23], x1 = hb[24], x2 = hb[25];
     if (alpha) {   // nn.LayerNorm(3)
       const float mean = (x0 + x1 + x2) / 3.0f;
       const float d0 = x0 - mean, d1 = x1 - mean, d2 = x2 - mean;
@@ -261,32 +265,41 @@ mdr_head_kernel(const float* __restrict__ hd, const float* __restrict__ nscale, 
       y[1] = d1 * rstd * nscale[1] + nshift[1];
       y[2] = d2 * rstd * nscale[2] + nshift[2];
     } else {       // eval BatchNorm1d(431): channel = vertex
-      const float s = nscale[v], t = nshift[v];
-      y[0] = fmaf(x0, s, t); y[1] = fmaf(x1, s, t); y[2] = fmaf(x2, s, t);
+      const float sc_ = nscale[v], t = nshift[v];
+      y[0] = fmaf(x0, sc_, t); y[1] = fmaf(x1, sc_, t); y[2] = fmaf(x2, sc_, t);
     }
 #pragma unroll
-    for (int t = 0; t < 3; ++t) gB[v][t] = gelu_erf(y[t]);
+    for (int t = 0; t < 3; ++t) gB[s][v][t] = gelu_erf(y[t]);
   }
   __syncthreads();
   for (int o = warp; o < 20; o += 8) {
-    float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+    float p0[HD_NS], p1[HD_NS], p2[HD_NS];
+#pragma unroll
+    for (int s = 0; s < HD_NS; ++s) p0[s] = p1[s] = p2[s] = 0.f;
     const float* w = cw + (size_t)o * V * 3;
     for (int c = lane; c < V; c += 32) {
       const float w0 = __ldg(w + c * 3), w1 = __ldg(w + c * 3 + 1), w2 = __ldg(w + c * 3 + 2);
-      const float g0 = gB[c][0], g1 = gB[c][1], g2 = gB[c][2];
-      p0 = fmaf(w1, g0, fmaf(w2, g1, p0));
-      p1 = fmaf(w0, g0, fmaf(w1, g1, fmaf(w2, g2, p1)));
-      p2 = fmaf(w0, g1, fmaf(w1, g2, p2));
+#pragma unroll
+      for (int s = 0; s < HD_NS; ++s) {
+        if (s < ns) {
+          const float g0 = gB[s][c][0], g1 = gB[s][c][1], g2 = gB[s][c][2];
+          p0[s] = fmaf(w1, g0, fmaf(w2, g1, p0[s]));
+          p1[s] = fmaf(w0, g0, fmaf(w1, g1, fmaf(w2, g2, p1[s])));
+          p2[s] = fmaf(w0, g1, fmaf(w1, g2, p2[s]));
+        }
+      }
     }
-    p0 = warp_sum(p0); p1 = warp_sum(p1); p2 = warp_sum(p2);
-    if (lane == 0) {
-      const float bb = cb[o];
-      matB[o][0] = p0 + bb; matB[o][1] = p1 + bb; matB[o][2] = p2 + bb;
+    const float bb = cb[o];
+#pragma unroll
+    for (int s = 0; s < HD_NS; ++s) {
+      const float q0 = warp_sum(p0[s]), q1 = warp_sum(p1[s]), q2 = warp_sum(p2[s]);
+      if (lane == 0 && s < ns) { matB[s][o][0] = q0 + bb; matB[s][o][1] = q1 + bb; matB[s][o][2] = q2 + bb; }
     }
   }
   __syncthreads();
-  for (int v = tid; v < V; v += 256) {
-    const float* r = hb + v * HEADN;
+  for (int i = tid; i < ns * V; i += 256) {
+    const int s = i / V, v = i - s * V;
+    const float* r = hd + ((size_t)(b0 + s) * V + v) * HEADN;
     float a[20];
     float m = -INFINITY;
 #pragma unroll
@@ -298,25 +311,28 @@ mdr_head_kernel(const float* __restrict__ hd, const float* __restrict__ nscale, 
 #pragma unroll
     for (int o = 0; o < 20; ++o) {
       const float p = a[o] / l;
-      c0 = fmaf(p, matB[o][0], c0); c1 = fmaf(p, matB[o][1], c1); c2 = fmaf(p, matB[o][2], c2);
+      c0 = fmaf(p, matB[s][o][0], c0); c1 = fmaf(p, matB[s][o][1], c1); c2 = fmaf(p, matB[s][o][2], c2);
     }
     const float al = alpha ? powf(1.1f, r[26]) : 1.0f;
-    sc[v][0] = al * c0 + r[20]; sc[v][1] = al * c1 + r[21]; sc[v][2] = al * c2 + r[22];
+    sc[s][v][0] = al * c0 + r[20]; sc[s][v][1] = al * c1 + r[21]; sc[s][v][2] = al * c2 + r[22];
   }
   __syncthreads();
-  if (coarse_out) {
-    float* co = coarse_out + (size_t)b * V * 3;
-    for (int i = tid; i < V * 3; i += 256) co[i] = (&sc[0][0])[i];
-  }
-  float* ab = a3 + (size_t)b * 3 * UPK;
-  for (int i = tid; i < 3 * UPK; i += 256) {
-    const int t = i / UPK, r = i - t * UPK;
-    float val = 0.f;
-    if (r < V * 3) {
-      const int c = r / 3, k = r - c * 3, tt = t + k - 1;
-      if (tt >= 0 && tt < 3) val = sc[c][tt];
+  for (int s = 0; s < ns; ++s) {
+    const int b = b0 + s;
+    if (coarse_out) {
+      float* co = coarse_out + (size_t)b * V * 3;
+      for (int i = tid; i < V * 3; i += 256) co[i] = (&sc[s][0][0])[i];
     }
-    ab[i] = val;
+    float* ab = a3 + (size_t)b * 3 * UPK;
+    for (int i = tid; i < 3 * UPK; i += 256) {
+      const int t = i / UPK, r = i - t * UPK;
+      float val = 0.f;
+      if (r < V * 3) {
+        const int c = r / 3, k = r - c * 3, tt = t + k - 1;
+        if (tt >= 0 && tt < 3) val = sc[s][c][tt];
+      }
+      ab[i] = val;
+    }
   }
 }
 
@@ -579,9 +595,9 @@ extern "C" int gator_mdr_forward(const gator_mdr_args* a, void* stream_) {
       e.bias = G(MDR_HEAD_B);
       GATOR_TRY(gemm(P(8), w.x, E, G(MDR_HEAD_W), E, GB(MDR_HEAD_W), w.hd, HEADN, Mv, HEADN, E, e, stream));
     }
-    mdr_head_kernel<<<nb, 256, 0, stream>>>(w.hd, G(MDR_BNORM_SCALE), G(MDR_BNORM_SHIFT), G(MDR_BCONV_W),
-                                            G(MDR_BCONV_B), a->alpha, a->coarse ? a->coarse + (size_t)b0 * V * 3 : nullptr,
-                                            w.a3 + (size_t)(b0 - s0) * 3 * UPK);
+    mdr_head_kernel<<<ceil_div(nb, HD_NS), 256, 0, stream>>>(w.hd, G(MDR_BNORM_SCALE), G(MDR_BNORM_SHIFT), G(MDR_BCONV_W),
+                                                             G(MDR_BCONV_B), a->alpha, a->coarse ? a->coarse + (size_t)b0 * V * 3 : nullptr,
+                                                             w.a3 + (size_t)(b0 - s0) * 3 * UPK, nb);
     GATOR_TRY(check_launch("mdr_head"));
   }
   // upsample_conv + template for the whole super-chunk: (3 ns) x 1296 @ 1296 x 6890, scattered to (b, vertex, xyz)
