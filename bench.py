@@ -44,6 +44,7 @@ SA_FLOP_PER_SAMPLE = 2 * 2 * 2 * 431 * 431 * 32   # self-attention core: 2 heads
 MESH_BYTES = 6890 * 3 * 4
 GLOBAL_BATCH_MULTI = 65536        # BASELINE configs[4]
 GATHER_BLOCK = 2048               # samples per rank and gather round
+GATHER_MIN_BLOCK = 1024           # P2P gather: the last rounds taper down to this (gator_b200.dist.round_plan)
 
 
 def measured_peaks():
@@ -336,9 +337,9 @@ def run_b200(args):
         g_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in gevs) / args.steps)
         # check on rank 0: the gathered batch equals a local forward of samples the other ranks computed
         ok = True
+        probe = [total - 1, total // 2 + 3, GATHER_BLOCK + 1]
         if rank == 0:
             with torch.no_grad():
-                probe = [total - 1, total // 2 + 3, GATHER_BLOCK + 1]
                 ok = all(torch.equal(model(xg[i:i + 1])[0][0], full[i]) for i in probe)
         recv = (world - 1) / world * total * MESH_BYTES
         # same slicing without the collective, to separate the cost of the gather from the cost of running in 1024-sample calls
@@ -364,6 +365,61 @@ def run_b200(args):
                   'block_samples': GATHER_BLOCK, 'rounds': -(-total // (world * GATHER_BLOCK)), 'verified': bool(ok),
                   'how': 'block-cyclic deal; the lifter runs once over the rank\'s samples, the decoder per round; all_gather_into_tensor of round k on a side stream while round k+1 computes; '
                          'output (65536, 6890, 3) fp32 written in place, no pad / cat copies'}
+        # the same deal without a collective kernel: symmetric-memory output, decoder writes in place, copy engines push each
+        # round to the peers over NVLink (gator_b200.dist.P2PGather) - no SMs are taken from the compute kernels
+        try:
+            from gator_b200.dist import P2PGather, forward_gathered_p2p
+            pg = P2PGather(total, (6890, 3), dev)
+            plan_p = round_plan(total, world, GATHER_BLOCK, GATHER_MIN_BLOCK)       # tapered: 2048 ... 2048, 1024, 1024
+            spans_p = [rank_span(total, st, n, rank) for st, n in plan_p]
+            idx_p = torch.cat([torch.arange(a, b) for a, b in spans_p]).to(dev)
+            offs_p, acc = {}, 0
+            for a, b in spans_p:
+                offs_p[a] = acc
+                acc += b - a
+            x_mine_p = xg[idx_p].contiguous()
+            state_p = {}
+
+            def fn_out(a, b, out):
+                o = offs_p[a]
+                model.pose2mesh.forward_parts(x_mine_p[o:o + b - a], state_p['p3'][o:o + b - a], state_p['feat'][o:o + b - a], out=out)
+
+            def p2p_step():
+                p3_, feat_ = model.pose_lifter(x_mine_p.reshape(x_mine_p.shape[0], -1))
+                state_p['p3'], state_p['feat'] = p3_.reshape(-1, J, 3), feat_
+                forward_gathered_p2p(fn_out, total, GATHER_BLOCK, pg, GATHER_MIN_BLOCK)
+            with torch.no_grad():
+                for _ in range(2):
+                    p2p_step()
+                barrier()
+                pevs = []
+                for _ in range(args.steps):
+                    flush.zero_()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    p2p_step()
+                    e1.record()
+                    pevs.append((e0, e1))
+                barrier()
+            p_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in pevs) / args.steps)
+            okp = True
+            if rank == 0:
+                with torch.no_grad():
+                    okp = all(torch.equal(model(xg[i:i + 1])[0][0], pg.out[i]) for i in probe)
+            try:
+                _mc = bool(pg.hdl.multicast_ptr)
+            except Exception:
+                _mc = None
+            gather['p2p'] = {'value': total / (p_ms * 1e-3), 'unit': UNIT, 'ms_per_step': p_ms, 'efficiency_vs_no_gather': step_ms / p_ms,
+                             'nvlink_gbs_in_per_gpu_over_step': recv / (p_ms * 1e-3) / 1e9, 'verified': bool(okp),
+                             'rounds_per_rank': [n for _, n in plan_p],
+                             'multicast_ptr': _mc,
+                             'how': 'same block-cyclic deal; the output buffer is symmetric memory (torch.distributed._symmetric_memory), the decoder '
+                                    'writes its rows in place and device-to-device copies on side streams (copy engines) push them to every peer '
+                                    'while the next round computes (one copy per peer on up to 7 streams); one cross-rank barrier at the end of the step'}
+            del pg, x_mine_p, state_p
+        except Exception as e:      # symmetric memory unavailable: the NCCL figure above stands alone
+            gather['p2p'] = {'error': f'{type(e).__name__}: {e}'[:300]}
         del full, xg, x_mine, state
 
     # ---- end to end: pinned host input -> H2D -> forward -> mesh + pose3d D2H ----
@@ -496,7 +552,7 @@ def run_b200(args):
                 'whole_step_fraction_of_tensor_peak': FLOP_PER_MESH * value / world / 1e12 / peaks['bf16_tflops_sustained']}
         if gather is not None:
             line['with_gather'] = gather
-            line['value_with_gather'] = gather['value']
+            line['value_with_gather'] = max(gather['value'], gather.get('p2p', {}).get('value', 0.0))
         if latency is not None:
             line['latency_b1'] = latency
         if world == 1:

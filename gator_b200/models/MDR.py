@@ -255,10 +255,11 @@ class MDR(nn.Module):
             self._ws = torch.empty(need, dtype=torch.uint8, device=dev)
         return self._ws
 
-    def forward_parts(self, pose2d, pose3d_mm, feat, want_coarse=False, pose3d_metres=False):
+    def forward_parts(self, pose2d, pose3d_mm, feat, want_coarse=False, pose3d_metres=False, out=None):
         """The fused entry: what GATOR.forward feeds MDR, without materialising the (B,J,133) concat
         (GATOR.py:19).  pose2d (B,J,2), pose3d_mm (B,J,3) millimetres (metres with pose3d_metres=True),
-        feat (B,J,128) -> (B,6890,3) m."""
+        feat (B,J,128) -> (B,6890,3) m.  `out`: an existing contiguous fp32 (B,6890,3) tensor on the weights' device to write
+        the mesh into (e.g. a slice of a gathered / symmetric-memory output buffer) instead of a fresh one."""
         if self.training:
             raise NotImplementedError('gator_b200.MDR implements the eval() forward only')
         if self._packed is None or (self._need_full_pack() and not self._packed_full):
@@ -273,7 +274,12 @@ class MDR(nn.Module):
         p2 = pose2d.detach().reshape(B, J, 2).float().contiguous()
         p3 = pose3d_mm.detach().reshape(B, J, 3).float().contiguous()
         ft = feat.detach().reshape(B, J, 128).float().contiguous()
-        mesh = torch.empty((B, V_FULL, 3), dtype=torch.float32, device=dev)
+        if out is not None:
+            if out.shape != (B, V_FULL, 3) or out.dtype != torch.float32 or out.device != dev or not out.is_contiguous():
+                raise ValueError('gator_b200.MDR: `out` must be a contiguous float32 (B, 6890, 3) tensor on the weights\' device')
+            mesh = out
+        else:
+            mesh = torch.empty((B, V_FULL, 3), dtype=torch.float32, device=dev)
         coarse = torch.empty((B, V_COARSE, 3), dtype=torch.float32, device=dev) if want_coarse else None
         if B > 0:
             ws = self._workspace(B, dev)

@@ -119,3 +119,22 @@ def test_numa_binding_is_best_effort():
     before = os.sched_getaffinity(0)
     assert bind_to_gpu_numa_node(0) is None or isinstance(bind_to_gpu_numa_node(0), int)
     assert os.sched_getaffinity(0) <= before
+
+
+def test_round_plan_taper():
+    """round_plan(min_block): the rounds tile the batch exactly, every rank's span is contiguous inside its round, and the
+    last rounds shrink by halves down to min_block (only a small transfer is left exposed at the end of the step)."""
+    from gator_b200.dist import rank_span, round_plan
+    assert [n for _, n in round_plan(65536, 8, 2048, 512)] == [2048, 2048, 2048, 1024, 512, 512]
+    assert round_plan(65536, 8, 2048) == round_plan(65536, 8, 2048, 0) == [(i * 8 * 2048, 2048) for i in range(4)]
+    for total, world, block, mb in ((65536, 4, 2048, 512), (1000, 3, 128, 32), (37, 8, 16, 4), (5, 2, 8, 2), (301, 1, 128, 64)):
+        plan = round_plan(total, world, block, mb)
+        covered = []
+        for start, n in plan:
+            assert n >= 1
+            for r in range(world):
+                lo, hi = rank_span(total, start, n, r)
+                covered += list(range(lo, hi))
+        assert covered == list(range(total)), (total, world, block, mb)
+        sizes = [n for _, n in plan]
+        assert all(a >= b for a, b in zip(sizes[:-1], sizes[1:-1] + sizes[-1:])) or sizes[-1] <= sizes[0]

@@ -486,3 +486,38 @@ def test_cuda_graph_capture(models):
         assert torch.equal(out, ref)
     finally:
         m.set_precision('fp32')
+
+
+def test_p2p_gather_single_rank_plumbing():
+    """gator_b200.dist.P2PGather / forward_gathered_p2p (symmetric-memory output, in-place decoder writes, copy-engine
+    pushes) with a one-rank NCCL group in a subprocess: the rounds tile the batch, ragged last round included, and the
+    buffer equals the plain forward.  (The multi-rank path is exercised by `bench.py --gpus N`, which verifies samples
+    computed by other ranks.)"""
+    import subprocess, sys, os, textwrap
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = textwrap.dedent('''
+        import os, sys
+        sys.path.insert(0, %r); sys.path.insert(0, os.path.join(%r, 'tests'))
+        import torch, torch.distributed as dist
+        from builders import build_b200_gator, synthetic
+        from gator_b200.dist import P2PGather, forward_gathered_p2p
+        dev = torch.device('cuda', 0)
+        torch.cuda.set_device(dev)
+        dist.init_process_group('nccl', init_method='tcp://127.0.0.1:29577', rank=0, world_size=1, device_id=dev)
+        m = build_b200_gator('h36m', dev).set_precision('bf16x3')
+        B = 301
+        x = torch.from_numpy(synthetic.poses2d(B, 17, seed=31)).to(dev)
+        with torch.no_grad():
+            want, _ = m(x)
+            p3, feat = m.pose_lifter(x.reshape(B, -1))
+            p3 = p3.reshape(B, 17, 3)
+            g = P2PGather(B, (6890, 3), dev)
+            fn = lambda lo, hi, out: m.pose2mesh.forward_parts(x[lo:hi], p3[lo:hi], feat[lo:hi], out=out)
+            got = forward_gathered_p2p(fn, B, 128, g)
+            torch.cuda.synchronize()
+            assert torch.equal(got, want), float((got - want).abs().max())
+        dist.destroy_process_group()
+        print('P2P_OK')
+    ''' % (root, root))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
+    assert 'P2P_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
