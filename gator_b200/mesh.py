@@ -95,22 +95,21 @@ def _apply2(first: _Csr, second: _Csr, x: torch.Tensor, scale: float = 1.0) -> t
 
 
 def adjmat_sparse(adjmat, nsize=1):
-    """mesh.py:29-48: row-normalised adjacency (with self loops) as a torch sparse COO tensor."""
+    """Row-normalised neighbourhood operator of a mesh level as a torch sparse COO tensor - what mesh.py:29-48 builds:
+    pattern of A^nsize with unit weights, self loops added, every row divided by its number of entries."""
     import scipy.sparse
-    adjmat = scipy.sparse.csr_matrix(adjmat)
-    if nsize > 1:
-        orig = adjmat.copy()
-        for _ in range(1, nsize):
-            adjmat = adjmat * orig
-    adjmat.data = np.ones_like(adjmat.data)
-    adjmat = scipy.sparse.lil_matrix(adjmat)
-    adjmat.setdiag(1)
-    adjmat = scipy.sparse.csr_matrix(adjmat)
-    num_neighbors = np.array(1 / adjmat.sum(axis=-1))
-    adjmat = scipy.sparse.coo_matrix(adjmat.multiply(num_neighbors))
-    i = torch.from_numpy(np.array([adjmat.row, adjmat.col])).long()
-    v = torch.from_numpy(adjmat.data).float()
-    return torch.sparse_coo_tensor(i, v, adjmat.shape, check_invariants=False)
+    pattern = scipy.sparse.csr_matrix(adjmat)
+    reach = pattern.copy()
+    for _ in range(nsize - 1):
+        reach = reach @ pattern                       # walks of length <= nsize
+    reach = (reach + scipy.sparse.identity(reach.shape[0], format='csr', dtype=reach.dtype)).tocsr()
+    reach.sum_duplicates()
+    reach.eliminate_zeros()
+    counts = np.diff(reach.indptr)                    # entries per row, self loop included
+    rows = np.repeat(np.arange(reach.shape[0]), counts)
+    vals = (1.0 / counts)[rows]
+    idx = torch.from_numpy(np.stack([rows, reach.indices]).astype(np.int64))
+    return torch.sparse_coo_tensor(idx, torch.from_numpy(vals).float(), reach.shape, check_invariants=False)
 
 
 class Mesh(object):
