@@ -124,3 +124,22 @@ def test_install_rebinds_reference_modules():
             import importlib
             for name in ('models.GATOR', 'models.GAT', 'models.MDR', 'models.backbones.mesh'):
                 importlib.reload(importlib.import_module(name))
+
+
+@pytest.mark.needs_reference
+def test_adjmat_equals_reference():
+    """gator_b200.mesh.adjmat_sparse (CSR pattern + row counts) against the reference's lil/coo construction
+    (lib/models/backbones/mesh.py:29-48) on every synthetic mesh level, nsize 1 and 2: same pattern, same values."""
+    import tempfile
+    from oracle import refshim
+    from gator_b200.mesh import adjmat_sparse
+    refshim.install_shims()
+    root = tempfile.mkdtemp()
+    synthetic.write_base_data(root)
+    with refshim.chdir(root):
+        from models.backbones import mesh as ref_mesh
+        A, _, _ = synthetic.mesh_sampling_matrices()
+        for a in A:
+            for nsize in (1, 2):
+                mine, ref = adjmat_sparse(a, nsize).coalesce(), ref_mesh.adjmat_sparse(a, nsize).coalesce()
+                assert torch.equal(mine.indices(), ref.indices()) and torch.equal(mine.values(), ref.values())
