@@ -90,6 +90,21 @@ def to_csr(m):
     return (c.indptr.astype(np.int32), c.indices.astype(np.int32), c.data.astype(np.float32), c.shape)
 
 
+def csr_to_ell4(rowptr: np.ndarray, colidx: np.ndarray, values: np.ndarray):
+    """CSR -> ELL records of four (col, val) per row for gator_mesh_upsample2 (include/gator_b200.h): (width, col (rows,4)
+    int32, val (rows,4) float32) with the non-zeros in CSR order, rows with fewer than four padded with val = 0 on a
+    column the row already uses; None when a row is empty or has more than four non-zeros."""
+    nnz = np.diff(rowptr)
+    if len(nnz) == 0 or nnz.min() < 1 or nnz.max() > 4:
+        return None
+    k = np.arange(4)[None, :]
+    valid = k < nnz[:, None]
+    pos = rowptr[:-1][:, None] + np.where(valid, k, 0)
+    col = np.ascontiguousarray(colidx[pos]).astype(np.int32)
+    val = np.where(valid, values[pos], 0).astype(np.float32)
+    return int(nnz.max()), col, val
+
+
 def dense_to_csr(a: np.ndarray):
     import scipy.sparse
     return to_csr(scipy.sparse.csr_matrix(np.asarray(a)))

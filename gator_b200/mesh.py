@@ -30,15 +30,10 @@ class _Csr:
         self.device = torch.device(device)
         # ELL copy (records of four (col, val) per row) for the fused two-level upsampling kernel; rows with fewer
         # non-zeros are padded with weight 0 on a column the row already uses
-        nnz = np.diff(rp)
-        self.ell_width = int(nnz.max()) if len(nnz) else 0
-        self.ell_col = self.ell_val = None
-        if 1 <= self.ell_width <= 4 and nnz.min() >= 1:
-            k = np.arange(4)[None, :]
-            valid = k < nnz[:, None]
-            pos = rp[:-1][:, None] + np.where(valid, k, 0)
-            self.ell_col = torch.from_numpy(np.ascontiguousarray(ci[pos]).astype(np.int32)).to(device)
-            self.ell_val = torch.from_numpy(np.where(valid, va[pos], 0).astype(np.float32)).to(device)
+        ell = graph.csr_to_ell4(rp, ci, va)
+        self.ell_width = ell[0] if ell else 0
+        self.ell_col = torch.from_numpy(ell[1]).to(device) if ell else None
+        self.ell_val = torch.from_numpy(ell[2]).to(device) if ell else None
 
     def apply(self, x: torch.Tensor, scale: float = 1.0) -> torch.Tensor:
         """y[..., r, :] = scale * sum_k val_k x[..., col_k, :] for x of shape (N,F) or (B,N,F)."""

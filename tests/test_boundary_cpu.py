@@ -143,3 +143,26 @@ def test_adjmat_equals_reference():
             for nsize in (1, 2):
                 mine, ref = adjmat_sparse(a, nsize).coalesce(), ref_mesh.adjmat_sparse(a, nsize).coalesce()
                 assert torch.equal(mine.indices(), ref.indices()) and torch.equal(mine.values(), ref.values())
+
+
+def test_ell_records_of_the_upsampling_operators():
+    """graph.csr_to_ell4: the ELL form gator_mesh_upsample2 reads reproduces the CSR operator exactly (a dense product
+    through the records equals the scipy product), padding has weight 0 on a column of the same row, and operators it
+    cannot hold are refused."""
+    import scipy.sparse
+    from gator_b200 import graph
+    _, D, U = synthetic.mesh_sampling_matrices()
+    rng = np.random.default_rng(0)
+    for m in list(U) + list(D):
+        rp, ci, va, shape = graph.to_csr(m)
+        w, col, val = graph.csr_to_ell4(rp, ci, va)
+        assert 1 <= w <= 4 and col.shape == val.shape == (shape[0], 4) and col.dtype == np.int32 and val.dtype == np.float32
+        x = rng.standard_normal((shape[1], 3)).astype(np.float32)
+        assert np.abs((val[:, :, None] * x[col]).sum(1) - scipy.sparse.csr_matrix(m).astype(np.float32) @ x).max() <= 1e-6
+        nnz = np.diff(rp)
+        pad = np.arange(4)[None, :] >= nnz[:, None]
+        assert (val[pad] == 0).all() and (col[pad] == np.broadcast_to(col[:, :1], col.shape)[pad]).all()
+    dense5 = scipy.sparse.csr_matrix(np.ones((3, 5), np.float32))
+    assert graph.csr_to_ell4(*graph.to_csr(dense5)[:3]) is None              # five non-zeros per row
+    empty_row = scipy.sparse.csr_matrix(np.array([[1.0, 0.0], [0.0, 0.0]], np.float32))
+    assert graph.csr_to_ell4(*graph.to_csr(empty_row)[:3]) is None

@@ -79,6 +79,64 @@ def test_forward_gathered_world2_gloo(total, block):
     assert sum(r[2] for r in res) == total
 
 
+class _GlooGather:
+    """Stand-in for gator_b200.dist.P2PGather on CPU (same interface: world, rank, out, push, finish): push() records
+    the rows this rank wrote in place, finish() ships them with gloo broadcasts - the transport is a copy engine on the
+    GPU; what the test exercises is forward_gathered_p2p's round logic (tapered plans, ragged rounds, in-place writes)."""
+
+    def __init__(self, total, feat):
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.out = torch.full((total,) + tuple(feat), float('nan'))
+        self.sent = []
+
+    def push(self, lo, hi):
+        self.sent.append((lo, hi))
+
+    def finish(self):
+        spans = [None] * self.world
+        dist.all_gather_object(spans, self.sent)
+        for r, lst in enumerate(spans):
+            for lo, hi in lst:
+                buf = self.out[lo:hi].clone()
+                dist.broadcast(buf, src=r)
+                self.out[lo:hi] = buf
+        self.sent = []
+
+
+def _worker_p2p(rank, world, port, total, block, min_block, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from gator_b200.dist import forward_gathered_p2p
+    full = torch.arange(total * 5 * 3, dtype=torch.float32).reshape(total, 5, 3)
+    g = _GlooGather(total, (5, 3))
+    calls = []
+
+    def fn(lo, hi, out):
+        calls.append((lo, hi))
+        out.copy_(full[lo:hi])                      # written IN PLACE into the gathered buffer
+    got = forward_gathered_p2p(fn, total, block, g, min_block)
+    q.put((rank, bool(torch.equal(got, full)), sum(hi - lo for lo, hi in calls)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('total,block,min_block', [(64, 16, 4), (13, 4, 1), (5, 4, 2), (16, 2, 0)])
+def test_forward_gathered_p2p_round_logic_world2_gloo(total, block, min_block):
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_worker_p2p, args=(r, 2, port, total, block, min_block, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = [q.get(timeout=120) for _ in ps]
+    for p in ps:
+        p.join(60)
+    assert sorted(r[:2] for r in res) == [(0, True), (1, True)]
+    assert sum(r[2] for r in res) == total
+
+
 @pytest.mark.parametrize('total', [8, 7])
 def test_gather_world2_gloo(total):
     s = socket.socket()
