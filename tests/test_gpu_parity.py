@@ -521,3 +521,29 @@ def test_p2p_gather_single_rank_plumbing():
     ''' % (root, root))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=600)
     assert 'P2P_OK' in r.stdout, r.stdout[-2000:] + r.stderr[-3000:]
+
+
+def test_mesh_upsample_fused_mixed_widths():
+    """gator_mesh_upsample2 on operators whose rows hold 1 to 4 non-zeros (the ELL width-4 instantiations and the padded
+    entries), small level sizes, ragged batches: bit-identical to gator_csr_spmm applied twice."""
+    import scipy.sparse
+    from gator_b200.mesh import _Csr, _apply2, _fusable
+    rng = np.random.default_rng(12)
+
+    def op(rows, cols, max_nnz):
+        r, c, v = [], [], []
+        for i in range(rows):
+            k = int(rng.integers(1, max_nnz + 1))
+            cc = rng.choice(cols, size=k, replace=False)
+            r += [i] * k; c += list(cc); v += list(rng.standard_normal(k))
+        return scipy.sparse.csr_matrix((np.asarray(v, np.float32), (r, c)), shape=(rows, cols))
+
+    for w1, w2 in ((4, 4), (2, 4), (4, 3), (1, 2)):
+        first, second = _Csr(op(211, 53, w1), DEV), _Csr(op(777, 211, w2), DEV)
+        assert first.ell_width <= w1 and second.ell_width <= w2
+        for B in (1, 4, 6, 301):
+            x = torch.randn(B, 53, 3, device=DEV)
+            assert _fusable(first, second, x)
+            fused = _apply2(first, second, x, scale=1000.0)
+            two = second.apply(first.apply(x), scale=1000.0)
+            assert torch.equal(fused, two), (w1, w2, B)
