@@ -166,3 +166,25 @@ def test_ell_records_of_the_upsampling_operators():
     assert graph.csr_to_ell4(*graph.to_csr(dense5)[:3]) is None              # five non-zeros per row
     empty_row = scipy.sparse.csr_matrix(np.array([[1.0, 0.0], [0.0, 0.0]], np.float32))
     assert graph.csr_to_ell4(*graph.to_csr(empty_row)[:3]) is None
+
+
+def test_new_entry_points_validate_before_touching_the_gpu(lib):
+    """gator_lbs_forward / gator_mesh_upsample2 / gator_mano_post / gator_mano_pose reject bad arguments with a status
+    code and a message (no CUDA call is made before validation, so this runs without a GPU)."""
+    from gator_b200 import _lib
+    a = _lib.LbsArgs(batch=4, n_verts=777, n_joints=16, k_blend=148)                 # odd vertex count
+    assert lib.gator_lbs_forward(a, None) == -1 and b'even vertex count' in lib.gator_last_error()
+    a = _lib.LbsArgs(batch=4, n_verts=778, n_joints=16, k_blend=145)                 # k_blend not padded to a multiple of 4
+    assert lib.gator_lbs_forward(a, None) == -1
+    a = _lib.LbsArgs(batch=0, n_verts=778, n_joints=16, k_blend=148)                 # empty batch is fine
+    assert lib.gator_lbs_forward(a, None) == 0
+    assert lib.gator_lbs_workspace_bytes(8, 778, 16) > 0 and lib.gator_lbs_workspace_bytes(8, 777, 16) == 0
+    u = _lib.Upsample2Args(batch=2, cols=431, rows1=1723, rows2=6890, width1=5, width2=3, scale=1.0)
+    assert lib.gator_mesh_upsample2(u, None) == -1 and b'ELL width' in lib.gator_last_error()
+    u = _lib.Upsample2Args(batch=2, cols=4000, rows1=9000, rows2=20000, width1=3, width2=3, scale=1.0)
+    assert lib.gator_mesh_upsample2(u, None) == -1                                   # null buffers / levels too large
+    u = _lib.Upsample2Args(batch=0, cols=431, rows1=1723, rows2=6890, width1=3, width2=3, scale=1.0)
+    assert lib.gator_mesh_upsample2(u, None) == 0
+    q = _lib.ManoPostArgs(batch=1, n_verts=778, center_idx=21)                       # 21 joints: valid indices are 0..20
+    assert lib.gator_mano_post(q, None) == -1
+    assert lib.gator_mano_pose(None, 9, 46, None, None, None, 1, None) == -1        # more than 45 PCA components
