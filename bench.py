@@ -9,14 +9,17 @@ batch of 65 536 sharded over the N GPUs (65 536 / N samples per rank), reported 
 One JSON line on stdout (rank 0):
   value           whole-job meshes/s, inputs resident in HBM, CUDA events per step, L2 flushed before every step, max over ranks
   with_gather     (N > 1) the same job ending with the FULL (65 536, 6890, 3) result on every rank: block-cyclic deal,
-                  chunked all_gather_into_tensor on a side stream overlapped with the next chunk's kernels
+                  chunked all_gather_into_tensor (NCCL) on a side stream overlapped with the next chunk's kernels;
+                  with_gather.p2p = the same over symmetric memory: decoder writes in place, copy engines push each round
+                  to the peers over NVLink (no SMs); value_with_gather = the better of the two
   e2e             host -> host through the public API (gator_b200.pipeline.HostPipeline.submit/result): pinned inputs, H2D,
                   forward, full mesh + pose3d copied back to pinned host memory, all inside the timed region; the copy of
                   step i overlaps the kernels of step i+1 (double-buffered pinned outputs, the last copy is exposed and counted)
   e2e_sync        the same through the synchronous HostPipeline.forward (a batch's own copy overlaps its own sliced decoder)
   e2e_eval        host -> device -> host with the evaluation epilogue (row f1) on the device: only per-sample errors return
   roofline        the dominant kernel timed alone through its C-ABI entry (plus the other hot kernels)
-  other_workloads BASELINE configs[2]: SMPL_Layer alone at batch 16 384, fp32 and tensor-core path, HBM roofline
+  other_workloads BASELINE configs[2]: SMPL_Layer alone at batch 16 384, fp32 and tensor-core path, HBM roofline; the fused
+                  two-level Mesh.upsample at batch 4096; the MANO layer at batch 16 384
   cpu_baseline    (N = 1) the CPU oracle (port of the reference forward, same ATen ops) on the box's host cores
   gpu_eager_baseline (N = 1, informational) the same oracle ops run eagerly on this GPU (fp32, TF32 off, chunks of 256)
 --impl reference times the CPU oracle as the reference arm (the reference is plain PyTorch and is not installable offline).
